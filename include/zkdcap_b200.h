@@ -1,0 +1,271 @@
+/*
+ * zkdcap_b200.h -- C ABI of the B200-native halo2 prover backend.
+ *
+ * This is the drop-in boundary for the hot path of zk-dcap-verifier's proof
+ * generation.  The reference has no FFI of its own: the
+ * boundary is the three halo2_proofs functions that `create_proof`
+ * (reference call site circuits/src/sgx_dcap_verifier.rs:814-822), `keygen_vk`
+ * (:803), `keygen_pk` (:807) and snark-verifier-sdk `gen_proof`
+ * (crates/p256-ecdsa/src/base.rs:193-212) reach:
+ *
+ *   halo2_proofs::arithmetic::best_multiexp          -> zk_msm / zk_commit*
+ *   halo2_proofs::arithmetic::best_fft               -> zk_ntt
+ *   halo2_proofs::poly::EvaluationDomain::*          -> zk_domain_* / zk_lagrange_to_coeff ...
+ *   halo2_proofs::plonk::evaluation::Evaluator::evaluate_h -> zk_evaluate_h
+ *
+ * (halo2_proofs 0.2.0 @ zkwebauthn/halo2 c254c75f, Cargo.lock:1314-1316;
+ *  halo2curves 0.3.1 @ bdb2e661, Cargo.lock:1329-1331 -- sources not vendored.)
+ *
+ * Data layout is exactly what halo2curves keeps in memory:
+ *   Fr / Fq   : 4 x u64 little-endian limbs, MONTGOMERY form (R = 2^256)
+ *   G1Affine  : {x, y}, 64 bytes, identity encoded as (0, 0)
+ *   G1        : Jacobian {x, y, z}, 96 bytes, identity has z = 0
+ * No conversion happens at the boundary.
+ *
+ * Every entry point returns 0 on success or a negative zk_status; the text of
+ * the last failure of a context is available from zk_last_error().  The
+ * library has NO CPU fallback: without a CUDA device every compute entry point
+ * fails with ZK_ERR_CUDA.
+ *
+ * Threading: one zk_ctx = one device + one stream; calls on a context are
+ * synchronous at the boundary unless the name ends in _async/_dev.  Different
+ * contexts may be driven from different host threads concurrently.
+ */
+#ifndef ZKDCAP_B200_H
+#define ZKDCAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } zk_fr;        /* bn256::Fr, Montgomery */
+typedef struct { uint64_t l[4]; } zk_fq;        /* bn256::Fq, Montgomery */
+typedef struct { zk_fq x, y; } zk_g1_affine;    /* bn256::G1Affine */
+typedef struct { zk_fq x, y, z; } zk_g1;        /* bn256::G1 (Jacobian) */
+
+typedef enum {
+  ZK_OK = 0,
+  ZK_ERR_ARG = -1,     /* bad argument (null pointer, size not a power of two ...) */
+  ZK_ERR_CUDA = -2,    /* CUDA runtime failure, or no device */
+  ZK_ERR_OOM = -3,     /* device allocation failed */
+  ZK_ERR_STATE = -4    /* object used before the data it needs was uploaded */
+} zk_status;
+
+typedef struct zk_ctx zk_ctx;
+typedef struct zk_domain zk_domain;
+typedef struct zk_pk zk_pk;
+
+/* ---- context ----------------------------------------------------------- */
+
+/* Create a context on `device`.  `cuda_stream` may be NULL (the context then
+ * owns a private non-blocking stream) or an existing cudaStream_t, e.g.
+ * torch.cuda.current_stream().cuda_stream, on which all work is enqueued. */
+int zk_ctx_create(int device, void* cuda_stream, zk_ctx** out);
+void zk_ctx_destroy(zk_ctx* ctx);
+const char* zk_last_error(const zk_ctx* ctx);
+int zk_ctx_sync(zk_ctx* ctx);
+/* Library/ABI version and the sm architecture the kernels were built for. */
+const char* zk_version(void);
+
+/* Per-kernel timing (CUDA events on the context's stream).  When enabled every
+ * kernel family records its device time and launch count. */
+typedef struct {
+  char name[40];
+  uint64_t launches;
+  double total_ms;
+} zk_kernel_stat;
+int zk_ctx_timing(zk_ctx* ctx, int enable);
+int zk_ctx_timing_reset(zk_ctx* ctx);
+/* Returns the number of rows written (<= cap). Resolves pending events. */
+int zk_ctx_timing_read(zk_ctx* ctx, zk_kernel_stat* rows, int cap);
+/* Number of kernels this context has launched since creation. */
+uint64_t zk_ctx_launch_count(const zk_ctx* ctx);
+
+/* Device memory helpers (so a host language without a CUDA binding can keep
+ * operands resident).  Pointers are plain device addresses. */
+int zk_dev_alloc(zk_ctx* ctx, size_t bytes, void** dptr);
+int zk_dev_free(zk_ctx* ctx, void* dptr);
+int zk_h2d(zk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int zk_d2h(zk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- ParamsKZG: SRS resident in HBM ------------------------------------- */
+
+/* Mirrors ParamsKZG { k, n, g, g_lagrange } (halo2_proofs poly/kzg/commitment.rs).
+ * Uploads both base sets once; with `precompute_windows` != 0 the library also
+ * builds, on the device, the table 2^(c*w) * base[i] for every Pippenger window
+ * so that all windows share one bucket set (costs W x the base memory). */
+int zk_srs_upload(zk_ctx* ctx, uint32_t k, const zk_g1_affine* g,
+                  const zk_g1_affine* g_lagrange, int precompute_windows);
+
+/* ---- best_multiexp ------------------------------------------------------ */
+
+typedef enum { ZK_BASES_HOST = 0, ZK_BASES_G = 1, ZK_BASES_G_LAGRANGE = 2 } zk_bases;
+
+/* out = sum_i scalars[i] * bases[i]  (arithmetic.rs best_multiexp).
+ * which == ZK_BASES_HOST : `bases` is a host array of n points;
+ * otherwise `bases` is ignored and the first n resident SRS points are used
+ * (ParamsKZG::commit / commit_lagrange).  `out` is normalised: z = 1, or the
+ * identity (0, 1, 0). */
+int zk_msm(zk_ctx* ctx, const zk_fr* scalars, const zk_g1_affine* bases,
+           int which, size_t n, zk_g1* out);
+/* Same with scalars (and, for ZK_BASES_HOST, bases) already in device memory
+ * and the result left in device memory; asynchronous on the context stream. */
+int zk_msm_dev(zk_ctx* ctx, const zk_fr* d_scalars, const zk_g1_affine* d_bases,
+               int which, size_t n, zk_g1* d_out);
+/* Batch of `count` commitments over the same resident base set: scalars is
+ * count x n (row-major, device); d_out receives count points. */
+int zk_msm_batch_dev(zk_ctx* ctx, const zk_fr* d_scalars, int which, size_t n,
+                     size_t count, zk_g1* d_out);
+/* out = sum of `count` Jacobian points (used to fold per-GPU partial MSMs). */
+int zk_g1_sum(zk_ctx* ctx, const zk_g1* points, size_t count, zk_g1* out);
+int zk_g1_sum_dev(zk_ctx* ctx, const zk_g1* d_points, size_t count, zk_g1* d_out);
+
+/* ---- best_fft ------------------------------------------------------------ */
+
+/* In-place radix-2 FFT over Fr, natural order in and out, a.len() = 2^log_n
+ * (arithmetic.rs best_fft).  `omega` must be a primitive 2^log_n-th root. */
+int zk_ntt(zk_ctx* ctx, zk_fr* a, const zk_fr* omega, uint32_t log_n);
+int zk_ntt_dev(zk_ctx* ctx, zk_fr* d_a, const zk_fr* omega_host, uint32_t log_n);
+
+/* ---- EvaluationDomain ---------------------------------------------------- */
+
+/* EvaluationDomain::new(j, k) (poly/domain.rs): j = cs.degree(). */
+int zk_domain_create(zk_ctx* ctx, uint32_t j, uint32_t k, zk_domain** out);
+void zk_domain_destroy(zk_domain* d);
+uint32_t zk_domain_k(const zk_domain* d);
+uint32_t zk_domain_extended_k(const zk_domain* d);
+/* Writes omega, omega_inv, extended_omega, extended_omega_inv, g_coset,
+ * g_coset_inv, ifft_divisor, extended_ifft_divisor (8 elements). */
+int zk_domain_constants(const zk_domain* d, zk_fr out[8]);
+
+/* lagrange_to_coeff: a (n values) -> coefficients, in place. */
+int zk_lagrange_to_coeff(zk_domain* d, zk_fr* a);
+/* coeff_to_lagrange (fft with omega), in place -- halo2 `coeff_to_lagrange`. */
+int zk_coeff_to_lagrange(zk_domain* d, zk_fr* a);
+/* coeff_to_extended: n coefficients -> 2^extended_k coset evaluations. */
+int zk_coeff_to_extended(zk_domain* d, const zk_fr* a, zk_fr* out_ext);
+/* extended_to_coeff: 2^extended_k coset evaluations -> n*(j-1) coefficients. */
+int zk_extended_to_coeff(zk_domain* d, const zk_fr* a_ext, zk_fr* out);
+/* divide_by_vanishing_poly, in place on 2^extended_k values. */
+int zk_divide_by_vanishing_poly(zk_domain* d, zk_fr* a_ext);
+/* Device-pointer variants (asynchronous on the context stream).  `count`
+ * independent polynomials stored back to back are transformed per call. */
+int zk_lagrange_to_coeff_dev(zk_domain* d, zk_fr* d_a, size_t count);
+int zk_coeff_to_lagrange_dev(zk_domain* d, zk_fr* d_a, size_t count);
+int zk_coeff_to_extended_dev(zk_domain* d, const zk_fr* d_a, zk_fr* d_out_ext, size_t count);
+int zk_extended_to_coeff_dev(zk_domain* d, zk_fr* d_a_ext /* clobbered */, zk_fr* d_out);
+int zk_divide_by_vanishing_poly_dev(zk_domain* d, zk_fr* d_a_ext);
+
+/* ---- Evaluator (plonk/evaluation.rs) -------------------------------------- */
+
+/* ValueSource */
+typedef enum {
+  ZK_VS_CONSTANT = 0,      /* a = index into constants */
+  ZK_VS_INTERMEDIATE = 1,  /* a = index into intermediates */
+  ZK_VS_FIXED = 2,         /* a = column index, b = index into rotations */
+  ZK_VS_ADVICE = 3,
+  ZK_VS_INSTANCE = 4,
+  ZK_VS_CHALLENGE = 5,     /* a = challenge index */
+  ZK_VS_BETA = 6,
+  ZK_VS_GAMMA = 7,
+  ZK_VS_THETA = 8,
+  ZK_VS_Y = 9,
+  ZK_VS_PREVIOUS_VALUE = 10
+} zk_vs_kind;
+typedef struct { uint32_t kind, a, b; } zk_value_source;
+
+/* Calculation */
+typedef enum {
+  ZK_CALC_ADD = 0, ZK_CALC_SUB = 1, ZK_CALC_MUL = 2, ZK_CALC_SQUARE = 3,
+  ZK_CALC_DOUBLE = 4, ZK_CALC_NEGATE = 5,
+  ZK_CALC_HORNER = 6,      /* a = start value, b = factor, parts = horner_parts[parts_off .. +parts_len] */
+  ZK_CALC_STORE = 7
+} zk_calc_kind;
+/* CalculationInfo { calculation, target } */
+typedef struct {
+  uint32_t kind;
+  zk_value_source a, b;
+  uint32_t parts_off, parts_len;
+  uint32_t target;           /* intermediate written by this calculation */
+} zk_calculation;
+
+/* GraphEvaluator { constants, rotations, calculations, num_intermediates } */
+typedef struct {
+  const zk_fr* constants;      uint32_t n_constants;
+  const int32_t* rotations;    uint32_t n_rotations;
+  const zk_calculation* calcs; uint32_t n_calcs;
+  const zk_value_source* horner_parts; uint32_t n_horner_parts;
+  uint32_t num_intermediates;
+} zk_graph;
+
+typedef enum { ZK_COL_ADVICE = 0, ZK_COL_FIXED = 1, ZK_COL_INSTANCE = 2 } zk_col_type;
+typedef struct { uint32_t column_type, index; } zk_column;
+
+/* What Evaluator::evaluate_h reads from ProvingKey / ConstraintSystem. */
+typedef struct {
+  uint32_t k;                  /* domain size 2^k */
+  uint32_t degree;             /* cs.degree() */
+  uint32_t blinding_factors;   /* cs.blinding_factors() */
+  uint32_t n_fixed, n_advice, n_instance, n_challenges;
+  zk_graph custom_gates;       /* Evaluator.custom_gates */
+  const zk_graph* lookups;     /* Evaluator.lookups */
+  uint32_t n_lookups;
+  const zk_column* perm_columns; /* cs.permutation.columns, in order */
+  uint32_t n_perm_columns;
+} zk_evaluator_desc;
+
+/* Upload the proving-key side of evaluate_h and keep it resident in HBM:
+ * pk.fixed_cosets (n_fixed x ext), pk.permutation.cosets (n_perm_columns x
+ * ext), pk.l0 / l_last / l_active_row (ext each), all in extended Lagrange
+ * form exactly as ProvingKey stores them (host pointers; copied).
+ * Alternatively pass the coefficient forms (n each) with coeff_form != 0 and
+ * the cosets are produced on the device (l_active_row is then derived from
+ * l_last and l_blind: pass l_blind's coefficients in its place). */
+int zk_pk_upload(zk_ctx* ctx, const zk_evaluator_desc* desc,
+                 const zk_fr* const* fixed, const zk_fr* const* perm,
+                 const zk_fr* l0, const zk_fr* l_last, const zk_fr* l_active_row,
+                 int coeff_form, zk_pk** out);
+void zk_pk_destroy(zk_pk* pk);
+zk_domain* zk_pk_domain(zk_pk* pk);
+/* Number of field multiplications the compiled per-row program performs and
+ * the number of distinct extended columns it reads (roofline bookkeeping). */
+int zk_pk_program_stats(const zk_pk* pk, uint64_t* muls_per_row, uint64_t* columns_read);
+
+/* Evaluator::evaluate_h for one circuit instance.  Polynomials are in
+ * coefficient form (n each), host pointers:
+ *   advice_polys[n_advice], instance_polys[n_instance], challenges[n_challenges],
+ *   lookup_polys[3*n_lookups] = {product, permuted_input, permuted_table} per lookup,
+ *   perm_product_polys[n_sets], n_sets = ceil(n_perm_columns / (degree-2)).
+ * out_ext receives 2^extended_k values of h's numerator in extended Lagrange
+ * form (before divide_by_vanishing_poly, like the Rust function). */
+int zk_evaluate_h(zk_pk* pk,
+                  const zk_fr* const* advice_polys, const zk_fr* const* instance_polys,
+                  const zk_fr* challenges,
+                  const zk_fr* y, const zk_fr* beta, const zk_fr* gamma, const zk_fr* theta,
+                  const zk_fr* const* lookup_polys, const zk_fr* const* perm_product_polys,
+                  zk_fr* out_ext);
+/* Same with every polynomial already resident: the pointer tables are host
+ * arrays of DEVICE pointers; d_out_ext is a device buffer. Asynchronous. */
+int zk_evaluate_h_dev(zk_pk* pk,
+                      const zk_fr* const* d_advice_polys, const zk_fr* const* d_instance_polys,
+                      const zk_fr* challenges,
+                      const zk_fr* y, const zk_fr* beta, const zk_fr* gamma, const zk_fr* theta,
+                      const zk_fr* const* d_lookup_polys, const zk_fr* const* d_perm_product_polys,
+                      zk_fr* d_out_ext);
+
+/* ---- micro-benchmarks (roofline denominators measured on the box) -------- */
+
+/* Runs a register-resident chain of `iters` Montgomery multiplications per
+ * thread over the whole chip and returns 1e9 field multiplications / second. */
+int zk_bench_modmul(zk_ctx* ctx, int field /*0 Fr, 1 Fq*/, uint32_t iters, double* gmul_per_s);
+/* Raw 32-bit integer multiply-add throughput, in 1e12 IMAD / s; kind 0 =
+ * mad.lo.u32 chains, 1 = mad.wide.u32 chains. */
+int zk_bench_imad(zk_ctx* ctx, int kind, uint32_t iters, double* timad_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKDCAP_B200_H */
