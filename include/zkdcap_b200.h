@@ -100,6 +100,14 @@ int zk_d2h(zk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int zk_srs_upload(zk_ctx* ctx, uint32_t k, const zk_g1_affine* g,
                   const zk_g1_affine* g_lagrange, int precompute_windows);
 
+/* Same with both base sets already in device memory (they are copied). */
+int zk_srs_upload_dev(zk_ctx* ctx, uint32_t k, const zk_g1_affine* d_g,
+                      const zk_g1_affine* d_g_lagrange, int precompute_windows);
+/* d_out[i] = d_scalars[i] * base, affine (the fixed-base products of
+ * ParamsKZG::setup: g[i] = s^i * G).  Device pointers; asynchronous. */
+int zk_g1_fixed_base_mul_dev(zk_ctx* ctx, const zk_g1_affine* base, const zk_fr* d_scalars,
+                             size_t n, zk_g1_affine* d_out);
+
 /* ---- best_multiexp ------------------------------------------------------ */
 
 typedef enum { ZK_BASES_HOST = 0, ZK_BASES_G = 1, ZK_BASES_G_LAGRANGE = 2 } zk_bases;
@@ -255,6 +263,12 @@ int zk_evaluate_h_dev(zk_pk* pk,
                       const zk_fr* y, const zk_fr* beta, const zk_fr* gamma, const zk_fr* theta,
                       const zk_fr* const* d_lookup_polys, const zk_fr* const* d_perm_product_polys,
                       zk_fr* d_out_ext);
+
+/* ---- element-wise field arithmetic (parity self-test of the device field) --- */
+/* op: 0 add, 1 sub, 2 mul, 3 neg, 4 invert, 5 square, 6 to Montgomery form,
+ * 7 from Montgomery form (to_repr), 8 double.  field: 0 = Fr, 1 = Fq.
+ * a, b (b may be NULL for unary ops) and out are host arrays of n elements. */
+int zk_field_op(zk_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 
 /* ---- micro-benchmarks (roofline denominators measured on the box) -------- */
 

@@ -1,0 +1,18 @@
+"""zk-dcap-verifier_b200 -- B200-native backend for the halo2 hot path of zk-dcap-verifier.
+
+The directory name carries a hyphen, so import it with importlib (or through the
+`zkdcap_b200` shim at the repository root):
+
+    import importlib; zk = importlib.import_module("zk-dcap-verifier_b200")
+
+Only csrc/ (hand-written sm_100a CUDA + the C ABI) computes; this package is the host-side
+mirror of the halo2 interface above that ABI.  There is no CPU fallback.
+"""
+from . import _abi
+from ._abi import ZkError, LIB_PATH
+from .halo2 import (Context, ConstraintSystem, EvaluationDomain, Evaluator, Expression, GraphEvaluator, ParamsKZG,
+                    ProvingKey, best_fft, best_multiexp, default_context, fq_to_limbs, fr_to_limbs, g1_sum)
+
+__all__ = ["Context", "ConstraintSystem", "EvaluationDomain", "Evaluator", "Expression", "GraphEvaluator",
+           "ParamsKZG", "ProvingKey", "best_fft", "best_multiexp", "default_context", "fq_to_limbs", "fr_to_limbs",
+           "g1_sum", "ZkError", "LIB_PATH"]

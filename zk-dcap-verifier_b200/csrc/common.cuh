@@ -1,0 +1,119 @@
+// common.cuh -- context object, error plumbing, kernel launch bookkeeping.
+// One zk_ctx = one device + one stream (SURVEY.md 8b "Threading"); no global state.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zkdcap_b200.h"
+
+struct zk_srs_set {
+  void* bases = nullptr;       // n affine points (64 B each)
+  void* table = nullptr;       // optional window table: W x n affine points, table[w][i] = 2^(c*w) * bases[i]
+  int table_c = 0, table_w = 0;
+};
+
+struct zk_timing_rec { const char* name; cudaEvent_t a, b; };
+struct zk_stat { uint64_t launches = 0; double ms = 0; };
+
+struct zk_scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct zk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string err;
+  uint64_t launches = 0;
+  // timing
+  bool timing = false;
+  std::vector<zk_timing_rec> pending;
+  std::vector<cudaEvent_t> event_pool;
+  std::map<std::string, zk_stat> stats;
+  // SRS (ParamsKZG)
+  uint32_t srs_k = 0;
+  size_t srs_n = 0;
+  zk_srs_set srs_g, srs_lagrange;
+  // grow-only scratch buffers, reused across calls on this context
+  zk_scratch msm_scalars, msm_bases, msm_work, msm_out, ntt_buf, ntt_buf2, misc;
+  // cached twiddle tables: key = (log_n, first 8 bytes of omega...) -> device table of omega^e, e < n/2
+  struct tw_entry { uint32_t log_n; zk_fr omega; void* table; };
+  std::vector<tw_entry> twiddles;
+};
+
+#define ZK_FAIL(ctx, code, ...)                                  \
+  do {                                                           \
+    char _b[512];                                                \
+    snprintf(_b, sizeof _b, __VA_ARGS__);                        \
+    (ctx)->err = _b;                                             \
+    return (code);                                               \
+  } while (0)
+
+#define ZK_CUDA(ctx, expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      ZK_FAIL(ctx, _e == cudaErrorMemoryAllocation ? ZK_ERR_OOM : ZK_ERR_CUDA, "%s:%d: %s: %s", \
+              __FILE__, __LINE__, #expr, cudaGetErrorString(_e));                            \
+  } while (0)
+
+#define ZK_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != ZK_OK) return _r; \
+  } while (0)
+
+static inline int zk_scratch_reserve(zk_ctx* ctx, zk_scratch& s, size_t bytes) {
+  if (s.cap >= bytes) return ZK_OK;
+  if (s.p) {
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, cudaFree(s.p));
+    s.p = nullptr; s.cap = 0;
+  }
+  size_t cap = bytes + (bytes >> 3);
+  ZK_CUDA(ctx, cudaMalloc(&s.p, cap));
+  s.cap = cap;
+  return ZK_OK;
+}
+
+static inline cudaEvent_t zk_get_event(zk_ctx* ctx) {
+  if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+static inline void zk_timing_begin(zk_ctx* ctx, const char* name) {
+  ctx->launches++;
+  if (!ctx->timing) return;
+  zk_timing_rec r; r.name = name; r.a = zk_get_event(ctx); r.b = zk_get_event(ctx);
+  cudaEventRecord(r.a, ctx->stream);
+  ctx->pending.push_back(r);
+}
+static inline void zk_timing_end(zk_ctx* ctx) {
+  if (!ctx->timing) return;
+  cudaEventRecord(ctx->pending.back().b, ctx->stream);
+}
+
+// Launch `kernel` on the context stream; `name` is the kernel family used for statistics.
+#define ZK_LAUNCH(ctx, name, kernel, grid, block, smem, ...)                         \
+  do {                                                                               \
+    zk_timing_begin(ctx, name);                                                      \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                 \
+    zk_timing_end(ctx);                                                              \
+    cudaError_t _le = cudaGetLastError();                                            \
+    if (_le != cudaSuccess)                                                          \
+      ZK_FAIL(ctx, ZK_ERR_CUDA, "%s:%d: launch %s: %s", __FILE__, __LINE__, name, cudaGetErrorString(_le)); \
+  } while (0)
+
+static inline unsigned zk_div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// entry points implemented across translation units
+int zk_twiddles_get(zk_ctx* ctx, const zk_fr* omega, uint32_t log_n, const void** table);

@@ -1,0 +1,431 @@
+// msm.cu -- BN254 G1 multi-scalar multiplication (Pippenger) for sm_100a.
+//
+// Replaces halo2_proofs arithmetic::best_multiexp / multiexp_serial ([UPSTREAM]
+// src/arithmetic.rs @ c254c75f, Cargo.lock:1314-1316) behind ParamsKZG::commit and
+// commit_lagrange (src/poly/kzg/commitment.rs), i.e. every KZG commitment made by
+// create_proof (circuits/src/sgx_dcap_verifier.rs:814), keygen_vk (:803) and the
+// snark-verifier-sdk provers (crates/p256-ecdsa/src/base.rs:193-212).
+//
+// The result of an MSM is a group element, so any correct evaluation order gives the same
+// canonical point; the device algorithm is therefore free to differ from the CPU one:
+//
+//   1. digits    scalar -> canonical integer (one Montgomery reduction) -> W signed digits of
+//                c bits, d in (-2^(c-1), 2^(c-1)], so only 2^(c-1) buckets per window exist.
+//   2. sort      counting sort of the (digit, point) pairs by bucket: histogram (atomics in
+//                L2), exclusive scan, scatter.  An entry is a 32-bit point index + sign bit.
+//   3. buckets   every bucket (split over S threads when there are few buckets) adds up its
+//                points with mixed XYZZ additions (8M + 2S, no inversion); points are fetched
+//                as 64-byte AoS records because the access is a gather.
+//   4. reduce    sum_b (b+1) * B_b  =  sum_k 2^k * (sum of the buckets whose weight has bit k),
+//                i.e. c independent plain sums done as parallel segmented sums, then a c-step
+//                double-and-add -- no long serial running-sum chain.
+//   5. windows   with resident bases the table 2^(c*w) * G_i is precomputed once per SRS, so all
+//                windows share ONE bucket set and step 5 vanishes; otherwise the W window sums
+//                are combined by Horner with c doublings each.
+#include "common.cuh"
+#include "ec.cuh"
+
+using namespace zk;
+
+namespace {
+
+struct MsmPlan {
+  uint32_t c, W, G;        // window bits, windows, bucket groups (1 when the window table is used)
+  uint32_t B;              // buckets per group = 2^(c-1)
+  uint32_t S;              // threads per bucket
+  size_t n, count;         // points per MSM, MSMs in the batch
+  size_t stride;           // window table: table[w * stride + i]
+  size_t nb;               // G * B buckets per MSM
+  size_t ent_per_msm;      // n * W
+};
+
+// ---- 1+2: digits, histogram, scatter --------------------------------------------------------------
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_msm_digits(const uint4* scalars, MsmPlan P, uint32_t* counts,
+                                                   const uint32_t* starts, uint32_t* entries) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t msm = blockIdx.y;
+  if (i >= P.n) return;
+  Fr s = Fr::load(scalars + 2 * (msm * P.n + i)).from_mont();
+  uint32_t* cnt = counts + msm * P.nb;
+  int carry = 0;
+  for (uint32_t w = 0; w < P.W; w++) {
+    int d = signed_digit(s.l, (int)w, (int)P.c, carry);
+    if (d == 0) continue;
+    uint32_t neg = d < 0 ? 1u : 0u;
+    uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+    size_t bucket = (P.G == 1 ? 0 : (size_t)w * P.B) + (mag - 1);
+    if (!SCATTER) {
+      atomicAdd(&cnt[bucket], 1u);
+    } else {
+      uint32_t pos = atomicAdd(&cnt[bucket], 1u);   // cnt is the zeroed cursor array here
+      uint32_t idx = (P.G == 1) ? (uint32_t)(w * P.stride + i) : (uint32_t)i;
+      entries[msm * P.ent_per_msm + starts[msm * (P.nb + 1) + bucket] + pos] = idx | (neg << 31);
+    }
+  }
+}
+
+// exclusive scan of nb counts per MSM (one CTA per MSM), writes nb+1 offsets and clears the counts
+__global__ void __launch_bounds__(1024) k_msm_scan(uint32_t* counts, uint32_t* starts, size_t nb) {
+  __shared__ uint32_t part[1024];
+  size_t msm = blockIdx.x;
+  uint32_t* cnt = counts + msm * nb;
+  uint32_t* st = starts + msm * (nb + 1);
+  size_t per = (nb + 1023) / 1024;
+  size_t lo = threadIdx.x * per, hi = lo + per < nb ? lo + per : nb;
+  uint32_t sum = 0;
+  for (size_t b = lo; b < hi; b++) sum += cnt[b];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (uint32_t off = 1; off < 1024; off <<= 1) {
+    uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+  for (size_t b = lo; b < hi; b++) { uint32_t c = cnt[b]; st[b] = run; run += c; cnt[b] = 0; }
+  if (threadIdx.x == 1023) st[nb] = part[1023];
+}
+
+// ---- 3: bucket accumulation -------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_msm_accumulate(const uint4* points, const uint32_t* entries,
+                                                        const uint32_t* starts, MsmPlan P, uint4* buckets) {
+  size_t vb = blockIdx.x * (size_t)blockDim.x + threadIdx.x;   // virtual bucket = bucket * S + lane
+  size_t msm = blockIdx.y;
+  if (vb >= P.nb * P.S) return;
+  size_t b = vb / P.S;
+  uint32_t lane = (uint32_t)(vb % P.S);
+  const uint32_t* st = starts + msm * (P.nb + 1);
+  const uint32_t* ent = entries + msm * P.ent_per_msm;
+  uint32_t lo = st[b], hi = st[b + 1];
+  XYZZ acc = XYZZ::identity();
+  for (uint32_t q = lo + lane; q < hi; q += P.S) {
+    uint32_t e = ent[q];
+    Affine pt = Affine::load(points + 4 * (size_t)(e & 0x7fffffffu)).cneg((e >> 31) != 0);
+    acc = acc.madd(pt);
+  }
+  acc.store(buckets + 8 * (msm * P.nb * P.S + vb));
+}
+
+// ---- 4: reduction -------------------------------------------------------------------------------------
+// level 1: out[msm][g][k][j] = sum over virtual buckets v in segment j of group g whose weight
+// (v / S + 1) has bit k set.
+__global__ void __launch_bounds__(128) k_msm_reduce_bits(const uint4* buckets, MsmPlan P, uint32_t seg,
+                                                         uint32_t nseg, uint4* out) {
+  size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t msm = blockIdx.y;
+  size_t total = (size_t)P.G * P.c * nseg;
+  if (tid >= total) return;
+  uint32_t j = (uint32_t)(tid % nseg);
+  uint32_t k = (uint32_t)((tid / nseg) % P.c);
+  uint32_t g = (uint32_t)(tid / ((size_t)nseg * P.c));
+  size_t vper = (size_t)P.B * P.S;
+  size_t v0 = (size_t)j * seg, v1 = v0 + seg < vper ? v0 + seg : vper;
+  const uint4* base = buckets + 8 * (msm * P.nb * P.S + (size_t)g * vper);
+  XYZZ acc = XYZZ::identity();
+  for (size_t v = v0; v < v1; v++) {
+    uint32_t weight = (uint32_t)(v / P.S) + 1;
+    if ((weight >> k) & 1) acc = acc.add(XYZZ::load(base + 8 * v));
+  }
+  acc.store(out + 8 * (msm * total + tid));
+}
+// further levels: rows of `len` points -> rows of ceil(len/seg) points
+__global__ void __launch_bounds__(128) k_xyzz_segsum(const uint4* in, size_t rows, uint32_t len, uint32_t seg,
+                                                     uint32_t nseg, uint4* out) {
+  size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (tid >= rows * nseg) return;
+  size_t row = tid / nseg;
+  uint32_t j = (uint32_t)(tid % nseg);
+  uint32_t a = j * seg, b = a + seg < len ? a + seg : len;
+  XYZZ acc = XYZZ::identity();
+  for (uint32_t i = a; i < b; i++) acc = acc.add(XYZZ::load(in + 8 * (row * len + i)));
+  acc.store(out + 8 * tid);
+}
+// final: per MSM, sums[g][k] -> sum_g 2^(c*g) * sum_k 2^k * sums[g][k]; writes a normalised G1
+__global__ void k_msm_final(const uint4* sums, MsmPlan P, uint4* out) {
+  size_t msm = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (msm >= P.count) return;
+  const uint4* s = sums + 8 * (msm * P.G * P.c);
+  XYZZ acc = XYZZ::identity();
+  for (int g = (int)P.G - 1; g >= 0; g--) {
+    if (g != (int)P.G - 1)
+      for (uint32_t i = 0; i < P.c; i++) acc = acc.dbl();
+    XYZZ win = XYZZ::identity();
+    for (int k = (int)P.c - 1; k >= 0; k--) {
+      win = win.dbl();
+      win = win.add(XYZZ::load(s + 8 * ((size_t)g * P.c + k)));
+    }
+    acc = acc.add(win);
+  }
+  store_g1_normalised(out + 6 * msm, acc.to_affine());
+}
+
+// ---- window table: table[w][i] = 2^(c*w) * base[i] ------------------------------------------------------
+__global__ void __launch_bounds__(128) k_msm_precompute(const uint4* bases, size_t n, uint32_t c, uint32_t W, uint4* table) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine a = Affine::load(bases + 4 * i);
+  a.store(table + 4 * i);
+  XYZZ p = XYZZ::from_affine(a);
+  for (uint32_t w = 1; w < W; w++) {
+    for (uint32_t k = 0; k < c; k++) p = p.dbl();
+    Affine q = p.to_affine();
+    q.store(table + 4 * ((size_t)w * n + i));
+    p = XYZZ::from_affine(q);
+  }
+}
+
+// out[i] = scalar[i] * base (double-and-add), affine.  ParamsKZG::setup-style fixed-base products.
+__global__ void __launch_bounds__(128) k_fixed_base_mul(const uint4* scalars, size_t n, Affine base, uint4* out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = Fr::load(scalars + 2 * i).from_mont();
+  XYZZ acc = XYZZ::identity();
+  for (int bit = 253; bit >= 0; bit--) {
+    acc = acc.dbl();
+    if ((s.l[bit >> 5] >> (bit & 31)) & 1) acc = acc.madd(base);
+  }
+  acc.to_affine().store(out + 4 * i);
+}
+
+// sum of `count` Jacobian points -> one normalised G1 (single thread; count is the GPU count)
+__global__ void k_g1_sum(const uint4* pts, size_t count, uint4* out) {
+  if (blockIdx.x || threadIdx.x) return;
+  XYZZ acc = XYZZ::identity();
+  for (size_t i = 0; i < count; i++) acc = acc.add(load_g1_as_xyzz(pts + 6 * i));
+  store_g1_normalised(out, acc.to_affine());
+}
+
+uint32_t ilog2(size_t x) { uint32_t l = 0; while (((size_t)1 << (l + 1)) <= x) l++; return l; }
+
+MsmPlan make_plan(size_t n, size_t count, bool table, uint32_t table_c, size_t stride, int sm_count) {
+  MsmPlan P; memset(&P, 0, sizeof P);
+  P.n = n; P.count = count; P.stride = stride;
+  uint32_t lg = ilog2(n ? n : 1);
+  if (table) {
+    P.c = table_c;
+  } else {
+    int c = (int)lg - 5;            // W separate bucket sets: keep the reduction small
+    if (c < 3) c = 3;
+    if (c > 14) c = 14;
+    P.c = (uint32_t)c;
+  }
+  P.W = 254 / P.c + 1;
+  P.G = table ? 1 : P.W;
+  P.B = 1u << (P.c - 1);
+  P.nb = (size_t)P.G * P.B;
+  P.ent_per_msm = n * P.W;
+  // enough threads to fill the chip: sm_count * 1024 virtual buckets over the whole batch
+  size_t want = (size_t)sm_count * 1024;
+  uint32_t S = 1;
+  while (S < 32 && P.nb * count * S < want) S <<= 1;
+  // a bucket holds n*W/nb entries on average: do not split below ~8 entries per thread
+  size_t avg = P.nb ? P.ent_per_msm / P.nb : 0;
+  while (S > 1 && avg / S < 8) S >>= 1;
+  P.S = S;
+  return P;
+}
+
+uint32_t table_window_bits(uint32_t k) {
+  int c = (int)k - 3;
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
+  return (uint32_t)c;
+}
+
+// Runs the whole pipeline for `count` MSMs over the same point array.
+int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmPlan& P, void* d_out) {
+  if (P.n == 0) {
+    // empty sum = identity
+    std::vector<zk_g1> ids(P.count);
+    memset(ids.data(), 0, ids.size() * sizeof(zk_g1));
+    // Montgomery one for y
+    const uint32_t one[8] = {FqParams::R0, FqParams::R1, FqParams::R2_, FqParams::R3_, FqParams::R4, FqParams::R5, FqParams::R6, FqParams::R7};
+    for (auto& g : ids) memcpy(&g.y, one, 32);
+    ZK_CUDA(ctx, cudaMemcpyAsync(d_out, ids.data(), ids.size() * sizeof(zk_g1), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+  }
+  if (P.ent_per_msm >= ((size_t)1 << 31) || (P.G == 1 && P.W * P.stride >= ((size_t)1 << 31)))
+    ZK_FAIL(ctx, ZK_ERR_ARG, "msm: n*W = %zu entries exceed the 31-bit entry index", P.ent_per_msm);
+  const size_t cnt_bytes = P.count * P.nb * 4, st_bytes = P.count * (P.nb + 1) * 4;
+  const size_t ent_bytes = P.count * P.ent_per_msm * 4;
+  const size_t bucket_bytes = P.count * P.nb * P.S * 128;
+  // reduction levels
+  const uint32_t seg = 16;
+  size_t vper = (size_t)P.B * P.S;
+  uint32_t nseg1 = (uint32_t)((vper + seg - 1) / seg);
+  size_t lvl1 = P.count * P.G * P.c * nseg1;            // points after level 1
+  const size_t red_bytes = lvl1 * 128;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off_cnt = 0, off_st = off_cnt + align(cnt_bytes), off_ent = off_st + align(st_bytes);
+  size_t off_bk = off_ent + align(ent_bytes), off_r1 = off_bk + align(bucket_bytes), off_r2 = off_r1 + align(red_bytes);
+  size_t total = off_r2 + align(red_bytes / seg + 128 * P.count * P.G * P.c);
+  ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_work, total));
+  char* w = (char*)ctx->msm_work.p;
+  uint32_t* counts = (uint32_t*)(w + off_cnt);
+  uint32_t* starts = (uint32_t*)(w + off_st);
+  uint32_t* entries = (uint32_t*)(w + off_ent);
+  uint4* buckets = (uint4*)(w + off_bk);
+  uint4* r1 = (uint4*)(w + off_r1);
+  uint4* r2 = (uint4*)(w + off_r2);
+
+  ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, cnt_bytes, ctx->stream));
+  dim3 gd(zk_div_up(P.n, 256), (unsigned)P.count);
+  ZK_LAUNCH(ctx, "msm_digits_hist", k_msm_digits<false>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)nullptr, (uint32_t*)nullptr);
+  ZK_LAUNCH(ctx, "msm_scan", k_msm_scan, (unsigned)P.count, 1024, 0, counts, starts, P.nb);
+  ZK_LAUNCH(ctx, "msm_digits_scatter", k_msm_digits<true>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)starts, entries);
+  dim3 ga(zk_div_up(P.nb * P.S, 128), (unsigned)P.count);
+  ZK_LAUNCH(ctx, "msm_accumulate", k_msm_accumulate, ga, 128, 0, (const uint4*)d_points, (const uint32_t*)entries, (const uint32_t*)starts, P, buckets);
+  size_t rows = P.count * P.G * P.c;
+  dim3 gr(zk_div_up((size_t)P.G * P.c * nseg1, 128), (unsigned)P.count);
+  ZK_LAUNCH(ctx, "msm_reduce_bits", k_msm_reduce_bits, gr, 128, 0, (const uint4*)buckets, P, seg, nseg1, r1);
+  uint32_t len = nseg1;
+  uint4 *src = r1, *dst = r2;
+  while (len > 1) {
+    uint32_t nseg = (len + seg - 1) / seg;
+    ZK_LAUNCH(ctx, "msm_segsum", k_xyzz_segsum, zk_div_up(rows * nseg, 128), 128, 0, (const uint4*)src, rows, len, seg, nseg, dst);
+    uint4* t = src; src = dst; dst = t;
+    len = nseg;
+  }
+  ZK_LAUNCH(ctx, "msm_final", k_msm_final, zk_div_up(P.count, 32), 32, 0, (const uint4*)src, P, (uint4*)d_out);
+  return ZK_OK;
+}
+
+int build_table(zk_ctx* ctx, zk_srs_set& s, size_t n, uint32_t k) {
+  uint32_t c = table_window_bits(k), W = 254 / c + 1;
+  size_t bytes = (size_t)W * n * 64;
+  if (cudaMalloc(&s.table, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    ZK_FAIL(ctx, ZK_ERR_OOM, "window table: cannot allocate %zu bytes", bytes);
+  }
+  s.table_c = (int)c; s.table_w = (int)W;
+  ZK_LAUNCH(ctx, "msm_precompute", k_msm_precompute, zk_div_up(n, 128), 128, 0, (const uint4*)s.bases, n, c, W, (uint4*)s.table);
+  return ZK_OK;
+}
+
+}  // namespace
+
+extern "C" int zk_srs_upload(zk_ctx* ctx, uint32_t k, const zk_g1_affine* g, const zk_g1_affine* g_lagrange,
+                             int precompute_windows) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!g || !g_lagrange || k > 27) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_srs_upload: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t n = (size_t)1 << k;
+  zk_srs_set* sets[2] = {&ctx->srs_g, &ctx->srs_lagrange};
+  const zk_g1_affine* src[2] = {g, g_lagrange};
+  for (int i = 0; i < 2; i++) {
+    if (sets[i]->bases) cudaFree(sets[i]->bases);
+    if (sets[i]->table) cudaFree(sets[i]->table);
+    *sets[i] = zk_srs_set();
+    ZK_CUDA(ctx, cudaMalloc(&sets[i]->bases, n * 64));
+    ZK_CUDA(ctx, cudaMemcpyAsync(sets[i]->bases, src[i], n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    if (precompute_windows) ZK_TRY(build_table(ctx, *sets[i], n, k));
+  }
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->srs_k = k; ctx->srs_n = n;
+  return ZK_OK;
+}
+
+// Same as zk_srs_upload with the two base sets already in device memory (copied).
+extern "C" int zk_srs_upload_dev(zk_ctx* ctx, uint32_t k, const zk_g1_affine* d_g, const zk_g1_affine* d_g_lagrange,
+                                 int precompute_windows) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!d_g || !d_g_lagrange || k > 27) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_srs_upload_dev: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t n = (size_t)1 << k;
+  zk_srs_set* sets[2] = {&ctx->srs_g, &ctx->srs_lagrange};
+  const zk_g1_affine* src[2] = {d_g, d_g_lagrange};
+  for (int i = 0; i < 2; i++) {
+    if (sets[i]->bases) cudaFree(sets[i]->bases);
+    if (sets[i]->table) cudaFree(sets[i]->table);
+    *sets[i] = zk_srs_set();
+    ZK_CUDA(ctx, cudaMalloc(&sets[i]->bases, n * 64));
+    ZK_CUDA(ctx, cudaMemcpyAsync(sets[i]->bases, src[i], n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (precompute_windows) ZK_TRY(build_table(ctx, *sets[i], n, k));
+  }
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->srs_k = k; ctx->srs_n = n;
+  return ZK_OK;
+}
+
+extern "C" int zk_msm_batch_dev(zk_ctx* ctx, const zk_fr* d_scalars, int which, size_t n, size_t count, zk_g1* d_out) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!d_out || (n && !d_scalars) || (which != ZK_BASES_G && which != ZK_BASES_G_LAGRANGE))
+    ZK_FAIL(ctx, ZK_ERR_ARG, "zk_msm_batch_dev: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!count) return ZK_OK;
+  zk_srs_set& s = which == ZK_BASES_G ? ctx->srs_g : ctx->srs_lagrange;
+  if (!s.bases) ZK_FAIL(ctx, ZK_ERR_STATE, "msm: no SRS uploaded (zk_srs_upload)");
+  if (n > ctx->srs_n) ZK_FAIL(ctx, ZK_ERR_ARG, "msm: n = %zu exceeds the SRS size %zu", n, ctx->srs_n);
+  // the window table is indexed w * srs_n + i; shorter commitments use the first n columns
+  bool table = s.table != nullptr;
+  MsmPlan P = make_plan(n, count, table, (uint32_t)s.table_c, ctx->srs_n, ctx->sm_count);
+  return run_msm(ctx, d_scalars, table ? s.table : s.bases, P, d_out);
+}
+
+extern "C" int zk_msm_dev(zk_ctx* ctx, const zk_fr* d_scalars, const zk_g1_affine* d_bases, int which, size_t n, zk_g1* d_out) {
+  if (!ctx) return ZK_ERR_ARG;
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (which == ZK_BASES_HOST) {
+    if (!d_out || (n && (!d_scalars || !d_bases))) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_msm_dev: bad argument");
+    MsmPlan P = make_plan(n, 1, false, 0, n, ctx->sm_count);
+    return run_msm(ctx, d_scalars, d_bases, P, d_out);
+  }
+  return zk_msm_batch_dev(ctx, d_scalars, which, n, 1, d_out);
+}
+
+extern "C" int zk_msm(zk_ctx* ctx, const zk_fr* scalars, const zk_g1_affine* bases, int which, size_t n, zk_g1* out) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!out || (n && !scalars) || (which == ZK_BASES_HOST && n && !bases)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_msm: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_scalars, n * 32 + 32));
+  ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_out, sizeof(zk_g1)));
+  ZK_CUDA(ctx, cudaMemcpyAsync(ctx->msm_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  const zk_g1_affine* d_bases = nullptr;
+  if (which == ZK_BASES_HOST) {
+    ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_bases, n * 64 + 64));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->msm_bases.p, bases, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    d_bases = (const zk_g1_affine*)ctx->msm_bases.p;
+  }
+  ZK_TRY(zk_msm_dev(ctx, (const zk_fr*)ctx->msm_scalars.p, d_bases, which, n, (zk_g1*)ctx->msm_out.p));
+  ZK_CUDA(ctx, cudaMemcpyAsync(out, ctx->msm_out.p, sizeof(zk_g1), cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZK_OK;
+}
+
+extern "C" int zk_g1_sum_dev(zk_ctx* ctx, const zk_g1* d_points, size_t count, zk_g1* d_out) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!d_out || (count && !d_points)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_g1_sum_dev: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZK_LAUNCH(ctx, "g1_sum", k_g1_sum, 1, 32, 0, (const uint4*)d_points, count, (uint4*)d_out);
+  return ZK_OK;
+}
+extern "C" int zk_g1_sum(zk_ctx* ctx, const zk_g1* points, size_t count, zk_g1* out) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!out || (count && !points)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_g1_sum: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZK_TRY(zk_scratch_reserve(ctx, ctx->misc, (count + 1) * sizeof(zk_g1)));
+  zk_g1* d = (zk_g1*)ctx->misc.p;
+  ZK_CUDA(ctx, cudaMemcpyAsync(d + 1, points, count * sizeof(zk_g1), cudaMemcpyHostToDevice, ctx->stream));
+  ZK_TRY(zk_g1_sum_dev(ctx, d + 1, count, d));
+  ZK_CUDA(ctx, cudaMemcpyAsync(out, d, sizeof(zk_g1), cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZK_OK;
+}
+
+// d_out[i] = d_scalars[i] * base as affine points (ParamsKZG::setup computes g[i] = s^i * G this way)
+extern "C" int zk_g1_fixed_base_mul_dev(zk_ctx* ctx, const zk_g1_affine* base, const zk_fr* d_scalars, size_t n,
+                                        zk_g1_affine* d_out) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!base || (n && (!d_scalars || !d_out))) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_g1_fixed_base_mul_dev: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!n) return ZK_OK;
+  Affine b; memcpy(b.x.l, &base->x, 32); memcpy(b.y.l, &base->y, 32);
+  ZK_LAUNCH(ctx, "fixed_base_mul", k_fixed_base_mul, zk_div_up(n, 128), 128, 0, (const uint4*)d_scalars, n, b, (uint4*)d_out);
+  return ZK_OK;
+}

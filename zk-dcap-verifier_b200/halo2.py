@@ -1,0 +1,558 @@
+"""
+halo2.py -- host-side mirror of the halo2_proofs interface for the GPU hot path.
+
+Same names, argument meaning and error behaviour as the functions the reference reaches
+through `create_proof` / `keygen_pk` (circuits/src/sgx_dcap_verifier.rs:803-822):
+
+    best_multiexp(coeffs, bases)                       arithmetic.rs
+    best_fft(a, omega, log_n)                          arithmetic.rs
+    EvaluationDomain(j, k).{lagrange_to_coeff, coeff_to_extended, extended_to_coeff, ...}   poly/domain.rs
+    ParamsKZG.{commit, commit_lagrange}                poly/kzg/commitment.rs
+    Expression / ConstraintSystem.{degree, blinding_factors}                 plonk/circuit.rs
+    GraphEvaluator.add_expression / Evaluator.new(cs) / Evaluator.evaluate_h plonk/evaluation.rs
+
+Every compute call goes through the C ABI of libzkdcap_b200.so (include/zkdcap_b200.h);
+nothing here computes on the CPU and nothing here touches oracle/.  Field elements and points
+are numpy uint64 arrays in halo2curves' in-memory layout (Montgomery limbs): Fr (..., 4),
+G1Affine (..., 8), G1 (..., 12).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import ZkError
+
+R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+P_MOD = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+_MONT_R = 1 << 256
+
+
+def fr_to_limbs(v):
+    """canonical int -> Montgomery limbs (host-side constant preparation only)"""
+    m = (v % R_MOD) * _MONT_R % R_MOD
+    return np.array([(m >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def fq_to_limbs(v):
+    m = (v % P_MOD) * _MONT_R % P_MOD
+    return np.array([(m >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Context:
+    """One device + one stream (zk_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = _abi.load()
+        h = C.c_void_p()
+        rc = self.lib.zk_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise ZkError("zk_ctx_create(device=%d) failed with %d: no CUDA device? (this backend has no CPU fallback)"
+                          % (device, rc))
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc < 0:
+            raise ZkError("%s (status %d)" % (self.lib.zk_last_error(self.h).decode(), rc))
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zk_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self.check(self.lib.zk_ctx_sync(self.h))
+
+    def timing(self, enable=True):
+        self.check(self.lib.zk_ctx_timing(self.h, 1 if enable else 0))
+
+    def timing_reset(self):
+        self.check(self.lib.zk_ctx_timing_reset(self.h))
+
+    def timing_read(self):
+        rows = (_abi.zk_kernel_stat * 64)()
+        n = self.check(self.lib.zk_ctx_timing_read(self.h, rows, 64))
+        return {rows[i].name.decode(): (int(rows[i].launches), float(rows[i].total_ms)) for i in range(n)}
+
+    def launch_count(self):
+        return int(self.lib.zk_ctx_launch_count(self.h))
+
+    def bench_modmul(self, field=0, iters=2000):
+        out = C.c_double()
+        self.check(self.lib.zk_bench_modmul(self.h, field, iters, C.byref(out)))
+        return out.value
+
+    def bench_imad(self, kind=0, iters=2000):
+        out = C.c_double()
+        self.check(self.lib.zk_bench_imad(self.h, kind, iters, C.byref(out)))
+        return out.value
+
+    def field_op(self, field, op, a, b=None):
+        ops = {"add": 0, "sub": 1, "mul": 2, "neg": 3, "inv": 4, "sqr": 5, "to_mont": 6, "from_mont": 7, "double": 8}
+        a = _u64(a)
+        out = np.empty_like(a)
+        bb = _u64(b) if b is not None else None
+        self.check(self.lib.zk_field_op(self.h, 0 if field == "fr" else 1, ops[op], _ptr(a),
+                                        _ptr(bb) if bb is not None else None, _ptr(out), a.size // 4))
+        return out
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ---- arithmetic.rs ---------------------------------------------------------------------------------
+def best_multiexp(coeffs, bases, ctx=None):
+    """sum_i coeffs[i] * bases[i] -> G1 (12 limbs, normalised).  Panics (raises) on length mismatch like the
+    Rust `assert_eq!(coeffs.len(), bases.len())`."""
+    ctx = ctx or default_context()
+    coeffs = _u64(coeffs, (-1, 4))
+    bases = _u64(bases, (-1, 8))
+    if coeffs.shape[0] != bases.shape[0]:
+        raise AssertionError("best_multiexp: coeffs.len() != bases.len()")
+    out = np.empty(12, dtype=np.uint64)
+    ctx.check(ctx.lib.zk_msm(ctx.h, _ptr(coeffs), _ptr(bases), _abi.BASES_HOST, coeffs.shape[0], _ptr(out)))
+    return out
+
+
+def best_fft(a, omega, log_n, ctx=None):
+    """In-place FFT of `a` (numpy (2^log_n, 4) uint64)."""
+    ctx = ctx or default_context()
+    if not (isinstance(a, np.ndarray) and a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]):
+        raise TypeError("best_fft works in place on a C-contiguous uint64 array")
+    if a.size != 4 << log_n:
+        raise AssertionError("best_fft: a.len() != 1 << log_n")
+    ctx.check(ctx.lib.zk_ntt(ctx.h, _ptr(a), _ptr(_u64(omega)), log_n))
+    return a
+
+
+def g1_sum(points, ctx=None):
+    ctx = ctx or default_context()
+    points = _u64(points, (-1, 12))
+    out = np.empty(12, dtype=np.uint64)
+    ctx.check(ctx.lib.zk_g1_sum(ctx.h, _ptr(points), points.shape[0], _ptr(out)))
+    return out
+
+
+# ---- poly/kzg/commitment.rs -----------------------------------------------------------------------
+class ParamsKZG:
+    """ParamsKZG { k, n, g, g_lagrange } with both base sets resident in HBM."""
+
+    def __init__(self, k, g, g_lagrange, ctx=None, precompute=True):
+        self.ctx = ctx or default_context()
+        self.k, self.n = k, 1 << k
+        g = _u64(g, (self.n, 8))
+        gl = _u64(g_lagrange, (self.n, 8))
+        self.ctx.check(self.ctx.lib.zk_srs_upload(self.ctx.h, k, _ptr(g), _ptr(gl), 1 if precompute else 0))
+
+    def _commit(self, poly, which):
+        poly = _u64(poly, (-1, 4))
+        if poly.shape[0] > self.n:
+            raise AssertionError("commit: polynomial longer than the SRS")
+        out = np.empty(12, dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.zk_msm(self.ctx.h, _ptr(poly), None, which, poly.shape[0], _ptr(out)))
+        return out
+
+    def commit(self, poly, blind=None):
+        """commit(&Polynomial<Fr, Coeff>, Blind) -- the blind is ignored by KZG, as upstream."""
+        return self._commit(poly, _abi.BASES_G)
+
+    def commit_lagrange(self, poly, blind=None):
+        return self._commit(poly, _abi.BASES_G_LAGRANGE)
+
+
+# ---- poly/domain.rs ---------------------------------------------------------------------------------
+class EvaluationDomain:
+    """EvaluationDomain::new(j, k)"""
+
+    def __init__(self, j, k, ctx=None, _handle=None):
+        self.ctx = ctx or default_context()
+        self.j, self.k = j, k
+        self._owned = _handle is None
+        if _handle is None:
+            h = C.c_void_p()
+            self.ctx.check(self.ctx.lib.zk_domain_create(self.ctx.h, j, k, C.byref(h)))
+            self.h = h
+        else:
+            self.h = _handle
+        self.extended_k = self.ctx.lib.zk_domain_extended_k(self.h)
+        self.n, self.ext_n = 1 << k, 1 << self.extended_k
+        c = np.zeros((8, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.zk_domain_constants(self.h, _ptr(c)))
+        (self.omega, self.omega_inv, self.extended_omega, self.extended_omega_inv,
+         self.g_coset, self.g_coset_inv, self.ifft_divisor, self.extended_ifft_divisor) = c
+
+    def __del__(self):
+        try:
+            if self._owned and self.h and self.ctx.h:
+                self.ctx.lib.zk_domain_destroy(self.h)
+        except Exception:
+            pass
+
+    def extended_len(self):
+        return self.ext_n
+
+    def get_quotient_poly_degree(self):
+        return self.j - 1
+
+    def lagrange_to_coeff(self, a):
+        a = _u64(a, (self.n, 4)).copy()
+        self.ctx.check(self.ctx.lib.zk_lagrange_to_coeff(self.h, _ptr(a)))
+        return a
+
+    def coeff_to_lagrange(self, a):
+        a = _u64(a, (self.n, 4)).copy()
+        self.ctx.check(self.ctx.lib.zk_coeff_to_lagrange(self.h, _ptr(a)))
+        return a
+
+    def coeff_to_extended(self, a):
+        a = _u64(a, (self.n, 4))
+        out = np.empty((self.ext_n, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.zk_coeff_to_extended(self.h, _ptr(a), _ptr(out)))
+        return out
+
+    def extended_to_coeff(self, a):
+        a = _u64(a, (self.ext_n, 4))
+        out = np.empty((self.n * (self.j - 1), 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.zk_extended_to_coeff(self.h, _ptr(a), _ptr(out)))
+        return out
+
+    def divide_by_vanishing_poly(self, a):
+        a = _u64(a, (self.ext_n, 4)).copy()
+        self.ctx.check(self.ctx.lib.zk_divide_by_vanishing_poly(self.h, _ptr(a)))
+        return a
+
+
+# ---- plonk/circuit.rs: Expression ---------------------------------------------------------------------
+class Expression:
+    """Expression<F> tree; field constants are canonical Python ints."""
+
+    def __init__(self, tag, *args):
+        self.tag, self.args = tag, args
+
+    @staticmethod
+    def Constant(v): return Expression("Constant", v % R_MOD)
+    @staticmethod
+    def Fixed(column_index, rotation=0): return Expression("Fixed", column_index, rotation)
+    @staticmethod
+    def Advice(column_index, rotation=0): return Expression("Advice", column_index, rotation)
+    @staticmethod
+    def Instance(column_index, rotation=0): return Expression("Instance", column_index, rotation)
+    @staticmethod
+    def Challenge(index): return Expression("Challenge", index)
+
+    def __neg__(self): return Expression("Negated", self)
+    def __add__(self, o): return Expression("Sum", self, o)
+    def __sub__(self, o): return Expression("Sum", self, Expression("Negated", o))    # a + (-b), as upstream
+    def __mul__(self, o):
+        if isinstance(o, int):
+            return Expression("Scaled", self, o % R_MOD)
+        return Expression("Product", self, o)
+
+    def degree(self):
+        t, a = self.tag, self.args
+        if t in ("Constant", "Challenge"):
+            return 0
+        if t in ("Fixed", "Advice", "Instance"):
+            return 1
+        if t in ("Negated", "Scaled"):
+            return a[0].degree()
+        if t == "Sum":
+            return max(a[0].degree(), a[1].degree())
+        return a[0].degree() + a[1].degree()
+
+
+class ConstraintSystem:
+    """The part of ConstraintSystem<F> that keygen and evaluate_h depend on."""
+
+    def __init__(self, num_fixed=0, num_advice=0, num_instance=0, num_challenges=0):
+        self.num_fixed_columns, self.num_advice_columns = num_fixed, num_advice
+        self.num_instance_columns, self.num_challenges = num_instance, num_challenges
+        self.gates = []            # list of gate polynomials (Expression), cs.gates order flattened
+        self.lookups = []          # list of (input_expressions, table_expressions)
+        self.permutation_columns = []   # list of (column_type, index); _abi.COL_*
+        self.minimum_degree = None
+        self.num_advice_queries = [0] * num_advice
+
+    def create_gate(self, polys):
+        for p in polys:
+            self.gates.append(p)
+            self._count_queries(p)
+
+    def lookup(self, inputs, tables):
+        self.lookups.append((list(inputs), list(tables)))
+        for e in list(inputs) + list(tables):
+            self._count_queries(e)
+
+    def enable_equality(self, column_type, index):
+        if (column_type, index) not in self.permutation_columns:
+            self.permutation_columns.append((column_type, index))
+
+    def _count_queries(self, e, seen=None):
+        # num_advice_queries counts DISTINCT (column, rotation) queries per advice column
+        if not hasattr(self, "_advice_q"):
+            self._advice_q = set()
+        stack = [e]
+        while stack:
+            x = stack.pop()
+            if x.tag == "Advice":
+                if (x.args[0], x.args[1]) not in self._advice_q:
+                    self._advice_q.add((x.args[0], x.args[1]))
+                    self.num_advice_queries[x.args[0]] += 1
+            for a in x.args:
+                if isinstance(a, Expression):
+                    stack.append(a)
+
+    def degree(self):
+        degree = 3                                          # permutation::Argument::required_degree()
+        for inputs, tables in self.lookups:
+            idg = max([1] + [e.degree() for e in inputs])
+            tdg = max([1] + [e.degree() for e in tables])
+            degree = max(degree, max(4, 2 + idg + tdg))     # lookup::Argument::required_degree()
+        for g in self.gates:
+            degree = max(degree, g.degree())
+        if self.minimum_degree is not None:
+            degree = max(degree, self.minimum_degree)
+        return degree
+
+    def blinding_factors(self):
+        factors = max([1] + self.num_advice_queries)
+        return max(3, factors) + 2
+
+
+# ---- plonk/evaluation.rs ------------------------------------------------------------------------------
+class GraphEvaluator:
+    """GraphEvaluator<C>: constants seeded with [0, 1, 2]; identical calculations share an intermediate."""
+
+    def __init__(self):
+        self.constants = [0, 1, 2]
+        self.rotations = []
+        self.calculations = []      # (calculation tuple, target)
+        self.num_intermediates = 0
+
+    def add_rotation(self, rot):
+        if rot not in self.rotations:
+            self.rotations.append(rot)
+        return self.rotations.index(rot)
+
+    def add_constant(self, c):
+        c %= R_MOD
+        if c not in self.constants:
+            self.constants.append(c)
+        return (_abi.VS_CONSTANT, self.constants.index(c), 0)
+
+    def add_calculation(self, calc):
+        for c, target in self.calculations:
+            if c == calc:
+                return (_abi.VS_INTERMEDIATE, target, 0)
+        target = self.num_intermediates
+        self.calculations.append((calc, target))
+        self.num_intermediates += 1
+        return (_abi.VS_INTERMEDIATE, target, 0)
+
+    def add_expression(self, e):
+        ZERO, ONE, TWO = (_abi.VS_CONSTANT, 0, 0), (_abi.VS_CONSTANT, 1, 0), (_abi.VS_CONSTANT, 2, 0)
+        t, a = e.tag, e.args
+        if t == "Constant":
+            return self.add_constant(a[0])
+        if t in ("Fixed", "Advice", "Instance"):
+            kind = {"Fixed": _abi.VS_FIXED, "Advice": _abi.VS_ADVICE, "Instance": _abi.VS_INSTANCE}[t]
+            return self.add_calculation(("Store", (kind, a[0], self.add_rotation(a[1]))))
+        if t == "Challenge":
+            return self.add_calculation(("Store", (_abi.VS_CHALLENGE, a[0], 0)))
+        if t == "Negated":
+            if a[0].tag == "Constant":
+                return self.add_constant(-a[0].args[0])
+            ra = self.add_expression(a[0])
+            return ra if ra == ZERO else self.add_calculation(("Negate", ra))
+        if t == "Sum":
+            if a[1].tag == "Negated":
+                ra, rb = self.add_expression(a[0]), self.add_expression(a[1].args[0])
+                if ra == ZERO:
+                    return self.add_calculation(("Negate", rb))
+                if rb == ZERO:
+                    return ra
+                return self.add_calculation(("Sub", ra, rb))
+            ra, rb = self.add_expression(a[0]), self.add_expression(a[1])
+            if ra == ZERO:
+                return rb
+            if rb == ZERO:
+                return ra
+            return self.add_calculation(("Add", ra, rb) if ra <= rb else ("Add", rb, ra))
+        if t == "Product":
+            ra, rb = self.add_expression(a[0]), self.add_expression(a[1])
+            if ra == ZERO or rb == ZERO:
+                return ZERO
+            if ra == ONE:
+                return rb
+            if rb == ONE:
+                return ra
+            if ra == TWO:
+                return self.add_calculation(("Double", rb))
+            if rb == TWO:
+                return self.add_calculation(("Double", ra))
+            if ra == rb:
+                return self.add_calculation(("Square", ra))
+            return self.add_calculation(("Mul", ra, rb) if ra <= rb else ("Mul", rb, ra))
+        if t == "Scaled":
+            if a[1] == 0:
+                return ZERO
+            if a[1] == 1:
+                return self.add_expression(a[0])
+            cst = self.add_constant(a[1])
+            ra = self.add_expression(a[0])
+            return self.add_calculation(("Mul", ra, cst))
+        raise ValueError("Selector expressions never reach the evaluator (compressed into fixed columns at keygen)")
+
+    def to_c(self):
+        """-> (zk_graph, keepalive list)"""
+        consts = np.stack([fr_to_limbs(c) for c in self.constants]) if self.constants else np.zeros((1, 4), np.uint64)
+        rots = (C.c_int32 * max(1, len(self.rotations)))(*self.rotations)
+        calcs = (_abi.zk_calculation * max(1, len(self.calculations)))()
+        parts = []
+        kinds = {"Add": _abi.CALC_ADD, "Sub": _abi.CALC_SUB, "Mul": _abi.CALC_MUL, "Square": _abi.CALC_SQUARE,
+                 "Double": _abi.CALC_DOUBLE, "Negate": _abi.CALC_NEGATE, "Horner": _abi.CALC_HORNER,
+                 "Store": _abi.CALC_STORE}
+        for i, (calc, target) in enumerate(self.calculations):
+            c = calcs[i]
+            c.kind, c.target = kinds[calc[0]], target
+            c.a = _abi.zk_value_source(*calc[1])
+            if calc[0] in ("Add", "Sub", "Mul"):
+                c.b = _abi.zk_value_source(*calc[2])
+            if calc[0] == "Horner":           # ("Horner", start, parts, factor)
+                c.b = _abi.zk_value_source(*calc[3])
+                c.parts_off, c.parts_len = len(parts), len(calc[2])
+                parts.extend(calc[2])
+        hp = (_abi.zk_value_source * max(1, len(parts)))(*[_abi.zk_value_source(*p) for p in parts])
+        g = _abi.zk_graph()
+        g.constants, g.n_constants = consts.ctypes.data, len(self.constants)
+        g.rotations, g.n_rotations = C.cast(rots, C.POINTER(C.c_int32)), len(self.rotations)
+        g.calcs, g.n_calcs = C.cast(calcs, C.POINTER(_abi.zk_calculation)), len(self.calculations)
+        g.horner_parts, g.n_horner_parts = C.cast(hp, C.POINTER(_abi.zk_value_source)), len(parts)
+        g.num_intermediates = self.num_intermediates
+        return g, [consts, rots, calcs, hp]
+
+
+class Evaluator:
+    """Evaluator<C> { custom_gates, lookups }"""
+
+    def __init__(self):
+        self.custom_gates = GraphEvaluator()
+        self.lookups = []
+
+    @staticmethod
+    def new(cs):
+        ev = Evaluator()
+        parts = [ev.custom_gates.add_expression(p) for p in cs.gates]
+        ev.custom_gates.add_calculation(("Horner", (_abi.VS_PREVIOUS_VALUE, 0, 0), tuple(parts), (_abi.VS_Y, 0, 0)))
+        for inputs, tables in cs.lookups:
+            g = GraphEvaluator()
+
+            def evaluate_lc(exprs):
+                ps = tuple(g.add_expression(e) for e in exprs)
+                return g.add_calculation(("Horner", (_abi.VS_CONSTANT, 0, 0), ps, (_abi.VS_THETA, 0, 0)))
+            compressed_input_coset = evaluate_lc(inputs)
+            compressed_table_coset = evaluate_lc(tables)
+            right_gamma = g.add_calculation(("Add", compressed_table_coset, (_abi.VS_GAMMA, 0, 0)))
+            lc = g.add_calculation(("Add", compressed_input_coset, (_abi.VS_BETA, 0, 0)))
+            g.add_calculation(("Mul", lc, right_gamma))
+            ev.lookups.append(g)
+        return ev
+
+    def describe(self, cs, k):
+        """-> (zk_evaluator_desc, keepalive) : the C image evaluate_h consumes"""
+        keep = []
+        d = _abi.zk_evaluator_desc()
+        d.k, d.degree, d.blinding_factors = k, cs.degree(), cs.blinding_factors()
+        d.n_fixed, d.n_advice = cs.num_fixed_columns, cs.num_advice_columns
+        d.n_instance, d.n_challenges = cs.num_instance_columns, cs.num_challenges
+        g, ka = self.custom_gates.to_c()
+        d.custom_gates = g
+        keep.append(ka)
+        lk = (_abi.zk_graph * max(1, len(self.lookups)))()
+        for i, lg in enumerate(self.lookups):
+            lk[i], ka = lg.to_c()
+            keep.append(ka)
+        d.lookups, d.n_lookups = C.cast(lk, C.POINTER(_abi.zk_graph)), len(self.lookups)
+        pc = (_abi.zk_column * max(1, len(cs.permutation_columns)))(
+            *[_abi.zk_column(t, i) for t, i in cs.permutation_columns])
+        d.perm_columns, d.n_perm_columns = C.cast(pc, C.POINTER(_abi.zk_column)), len(cs.permutation_columns)
+        keep += [lk, pc]
+        return d, keep
+
+
+def _ptr_table(arrs):
+    arrs = [_u64(a) for a in arrs]
+    tab = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+    return tab, arrs
+
+
+class ProvingKey:
+    """The slice of ProvingKey<C> evaluate_h reads (fixed_cosets, permutation.cosets, l0, l_last,
+    l_active_row, ev), resident in HBM."""
+
+    def __init__(self, cs, k, fixed, perm, l0, l_last, l_active_row, coeff_form=False, ctx=None):
+        self.ctx = ctx or default_context()
+        self.cs, self.k = cs, k
+        self.ev = Evaluator.new(cs)
+        self.desc, self._keep = self.ev.describe(cs, k)
+        tf, kf = _ptr_table(fixed)
+        tp, kp = _ptr_table(perm)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.zk_pk_upload(self.ctx.h, C.byref(self.desc), tf, tp, _ptr(_u64(l0)),
+                                                 _ptr(_u64(l_last)), _ptr(_u64(l_active_row)),
+                                                 1 if coeff_form else 0, C.byref(h)))
+        self.h = h
+        self.domain = EvaluationDomain(cs.degree(), k, self.ctx, _handle=C.c_void_p(self.ctx.lib.zk_pk_domain(h)))
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.zk_pk_destroy(self.h)
+        except Exception:
+            pass
+
+    def program_stats(self):
+        m, c = C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx.lib.zk_pk_program_stats(self.h, C.byref(m), C.byref(c)))
+        return {"muls_per_row": m.value, "columns_read": c.value}
+
+    def evaluate_h(self, advice_polys, instance_polys, challenges, y, beta, gamma, theta, lookups, permutations):
+        """Evaluator::evaluate_h(pk, advice_polys, instance_polys, challenges, y, beta, gamma, theta, lookups,
+        permutations) for one circuit instance.  lookups: list of (product_poly, permuted_input_poly,
+        permuted_table_poly); permutations: list of permutation_product_poly; all in coefficient form."""
+        ta, ka = _ptr_table(advice_polys)
+        ti, ki = _ptr_table(instance_polys)
+        flat = [p for triple in lookups for p in triple]
+        tl, kl = _ptr_table(flat)
+        tz, kz = _ptr_table(permutations)
+        ch = _u64(challenges, (-1, 4)) if len(challenges) else np.zeros((1, 4), np.uint64)
+        out = np.empty((self.domain.ext_n, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.zk_evaluate_h(self.h, ta, ti, _ptr(ch), _ptr(_u64(y)), _ptr(_u64(beta)),
+                                                  _ptr(_u64(gamma)), _ptr(_u64(theta)), tl, tz, _ptr(out)))
+        return out
