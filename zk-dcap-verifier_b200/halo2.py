@@ -556,3 +556,65 @@ class ProvingKey:
         self.ctx.check(self.ctx.lib.zk_evaluate_h(self.h, ta, ti, _ptr(ch), _ptr(_u64(y)), _ptr(_u64(beta)),
                                                   _ptr(_u64(gamma)), _ptr(_u64(theta)), tl, tz, _ptr(out)))
         return out
+
+
+# ---- device-pointer variants (operands already resident in HBM; asynchronous on the context stream) -----
+def _vp(x):
+    return C.c_void_p(int(x)) if x else None
+
+
+def commit_dev(params, d_scalars, count, d_out, lagrange=True, n=None):
+    """`count` commitments over the resident SRS: d_scalars = count x n Fr (device), d_out = count G1 (device)."""
+    ctx = params.ctx
+    which = _abi.BASES_G_LAGRANGE if lagrange else _abi.BASES_G
+    ctx.check(ctx.lib.zk_msm_batch_dev(ctx.h, _vp(d_scalars), which, n or params.n, count, _vp(d_out)))
+
+
+def msm_dev(ctx, d_scalars, d_bases, n, d_out):
+    """best_multiexp with scalars and bases in device memory."""
+    ctx.check(ctx.lib.zk_msm_dev(ctx.h, _vp(d_scalars), _vp(d_bases), _abi.BASES_HOST, n, _vp(d_out)))
+
+
+def lagrange_to_coeff_dev(domain, d_a, count=1):
+    domain.ctx.check(domain.ctx.lib.zk_lagrange_to_coeff_dev(domain.h, _vp(d_a), count))
+
+
+def coeff_to_extended_dev(domain, d_a, d_out, count=1):
+    domain.ctx.check(domain.ctx.lib.zk_coeff_to_extended_dev(domain.h, _vp(d_a), _vp(d_out), count))
+
+
+def extended_to_coeff_dev(domain, d_a_ext, d_out):
+    domain.ctx.check(domain.ctx.lib.zk_extended_to_coeff_dev(domain.h, _vp(d_a_ext), _vp(d_out)))
+
+
+def divide_by_vanishing_poly_dev(domain, d_a_ext):
+    domain.ctx.check(domain.ctx.lib.zk_divide_by_vanishing_poly_dev(domain.h, _vp(d_a_ext)))
+
+
+def ntt_dev(ctx, d_a, omega, log_n):
+    ctx.check(ctx.lib.zk_ntt_dev(ctx.h, _vp(d_a), _ptr(_u64(omega)), log_n))
+
+
+def evaluate_h_dev(pk, d_advice, d_instance, challenges, y, beta, gamma, theta, d_lookups, d_permutations, d_out):
+    """Pointer lists hold DEVICE addresses of coefficient-form polynomials; d_out = device buffer of ext_n Fr."""
+    def tab(ptrs):
+        return (C.c_void_p * max(1, len(ptrs)))(*[int(p) for p in ptrs])
+    ch = _u64(challenges, (-1, 4)) if len(challenges) else np.zeros((1, 4), np.uint64)
+    pk.ctx.check(pk.ctx.lib.zk_evaluate_h_dev(pk.h, tab(d_advice), tab(d_instance), _ptr(ch), _ptr(_u64(y)),
+                                              _ptr(_u64(beta)), _ptr(_u64(gamma)), _ptr(_u64(theta)),
+                                              tab(d_lookups), tab(d_permutations), _vp(d_out)))
+
+
+def srs_upload_dev(ctx, k, d_g, d_g_lagrange, precompute=True):
+    ctx.check(ctx.lib.zk_srs_upload_dev(ctx.h, k, _vp(d_g), _vp(d_g_lagrange), 1 if precompute else 0))
+
+
+def fixed_base_mul_dev(ctx, base_affine, d_scalars, n, d_out):
+    ctx.check(ctx.lib.zk_g1_fixed_base_mul_dev(ctx.h, _ptr(_u64(base_affine)), _vp(d_scalars), n, _vp(d_out)))
+
+
+class ResidentParams:
+    """ParamsKZG whose bases were produced on the device (synthetic SRS for benchmarks)."""
+
+    def __init__(self, ctx, k):
+        self.ctx, self.k, self.n = ctx, k, 1 << k
