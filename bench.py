@@ -103,6 +103,20 @@ class ClockSampler:
         return out
 
 
+_STREAMS = {}
+
+
+def work_stream(torch, dev):
+    """A non-default torch stream made current, so that the library's kernels, torch's copies and the
+    torch.cuda.Event timers all live on ONE stream (the legacy default stream has handle 0, which the ABI reads
+    as "create a private stream")."""
+    key = str(dev)
+    if key not in _STREAMS:
+        _STREAMS[key] = torch.cuda.Stream(dev)
+        torch.cuda.set_stream(_STREAMS[key])
+    return _STREAMS[key].cuda_stream
+
+
 # ---- synthetic inputs -----------------------------------------------------------------------------------
 def rand_fr(torch, n, device, gen):
     """n x 4 int64 limbs, every element < 2^252 < r: a valid Montgomery-form Fr (uniform over 2^252 values)"""
@@ -125,7 +139,7 @@ class Workload:
         self.h2 = __import__("importlib").import_module("zk-dcap-verifier_b200.halo2")
         dev = torch.device("cuda", device)
         self.dev = dev
-        self.ctx = zk.Context(device, torch.cuda.current_stream(dev).cuda_stream)
+        self.ctx = zk.Context(device, work_stream(torch, dev))
         self.cs = shapes.full_chain_shape()
         self.counts = shapes.counts(self.cs)
         self.calls = shapes.hot_path_calls(self.cs)
@@ -502,7 +516,7 @@ def main():
 def sweep(args, zk, torch, dev, local_rank):
     """MSM Gpts/s and NTT GB/s sweeps (BASELINE configs[2], [3]); one JSON line per size."""
     h2 = __import__("importlib").import_module("zk-dcap-verifier_b200.halo2")
-    ctx = zk.Context(local_rank, torch.cuda.current_stream(dev).cuda_stream)
+    ctx = zk.Context(local_rank, work_stream(torch, dev))
     gen = torch.Generator(device=dev); gen.manual_seed(0x5CA1A4)
     G = np.concatenate([zk.fq_to_limbs(1), zk.fq_to_limbs(2)])
     R_MOD = h2.R_MOD
@@ -549,7 +563,7 @@ def msm_sharded(args, zk, torch, dist, dev, rank, local_rank, world):
     """ONE MSM of 2^k points sharded by base range over the ranks: each GPU runs Pippenger on its slice of the
     resident bases, the 96-byte partial points are all-gathered over NVLink and folded with zk_g1_sum."""
     h2 = __import__("importlib").import_module("zk-dcap-verifier_b200.halo2")
-    ctx = zk.Context(local_rank, torch.cuda.current_stream(dev).cuda_stream)
+    ctx = zk.Context(local_rank, work_stream(torch, dev))
     k = args.k
     n = 1 << k
     per = n // world
