@@ -1,0 +1,55 @@
+//! SOURCE ONLY -- compile-unverified (no Rust toolchain in the build image).
+//! Raw bindings of include/zkdcap_b200.h; see INTEGRATION.md for the halo2_proofs patch that uses them.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)] #[derive(Clone, Copy)] pub struct zk_fr(pub [u64; 4]);
+#[repr(C)] #[derive(Clone, Copy)] pub struct zk_g1_affine { pub x: [u64; 4], pub y: [u64; 4] }
+#[repr(C)] #[derive(Clone, Copy)] pub struct zk_g1 { pub x: [u64; 4], pub y: [u64; 4], pub z: [u64; 4] }
+#[repr(C)] pub struct zk_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct zk_domain { _p: [u8; 0] }
+#[repr(C)] pub struct zk_pk { _p: [u8; 0] }
+#[repr(C)] #[derive(Clone, Copy)] pub struct zk_value_source { pub kind: u32, pub a: u32, pub b: u32 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct zk_calculation { pub kind: u32, pub a: zk_value_source, pub b: zk_value_source, pub parts_off: u32, pub parts_len: u32, pub target: u32 }
+#[repr(C)]
+pub struct zk_graph {
+    pub constants: *const zk_fr, pub n_constants: u32,
+    pub rotations: *const i32, pub n_rotations: u32,
+    pub calcs: *const zk_calculation, pub n_calcs: u32,
+    pub horner_parts: *const zk_value_source, pub n_horner_parts: u32,
+    pub num_intermediates: u32,
+}
+#[repr(C)] #[derive(Clone, Copy)] pub struct zk_column { pub column_type: u32, pub index: u32 }
+#[repr(C)]
+pub struct zk_evaluator_desc {
+    pub k: u32, pub degree: u32, pub blinding_factors: u32,
+    pub n_fixed: u32, pub n_advice: u32, pub n_instance: u32, pub n_challenges: u32,
+    pub custom_gates: zk_graph, pub lookups: *const zk_graph, pub n_lookups: u32,
+    pub perm_columns: *const zk_column, pub n_perm_columns: u32,
+}
+pub const ZK_BASES_HOST: c_int = 0;
+pub const ZK_BASES_G: c_int = 1;
+pub const ZK_BASES_G_LAGRANGE: c_int = 2;
+
+extern "C" {
+    pub fn zk_ctx_create(device: c_int, cuda_stream: *mut c_void, out: *mut *mut zk_ctx) -> c_int;
+    pub fn zk_ctx_destroy(ctx: *mut zk_ctx);
+    pub fn zk_last_error(ctx: *const zk_ctx) -> *const c_char;
+    pub fn zk_srs_upload(ctx: *mut zk_ctx, k: u32, g: *const zk_g1_affine, g_lagrange: *const zk_g1_affine, precompute_windows: c_int) -> c_int;
+    pub fn zk_msm(ctx: *mut zk_ctx, scalars: *const zk_fr, bases: *const zk_g1_affine, which: c_int, n: usize, out: *mut zk_g1) -> c_int;
+    pub fn zk_ntt(ctx: *mut zk_ctx, a: *mut zk_fr, omega: *const zk_fr, log_n: u32) -> c_int;
+    pub fn zk_domain_create(ctx: *mut zk_ctx, j: u32, k: u32, out: *mut *mut zk_domain) -> c_int;
+    pub fn zk_domain_destroy(d: *mut zk_domain);
+    pub fn zk_lagrange_to_coeff(d: *mut zk_domain, a: *mut zk_fr) -> c_int;
+    pub fn zk_coeff_to_lagrange(d: *mut zk_domain, a: *mut zk_fr) -> c_int;
+    pub fn zk_coeff_to_extended(d: *mut zk_domain, a: *const zk_fr, out_ext: *mut zk_fr) -> c_int;
+    pub fn zk_extended_to_coeff(d: *mut zk_domain, a_ext: *const zk_fr, out: *mut zk_fr) -> c_int;
+    pub fn zk_divide_by_vanishing_poly(d: *mut zk_domain, a_ext: *mut zk_fr) -> c_int;
+    pub fn zk_pk_upload(ctx: *mut zk_ctx, desc: *const zk_evaluator_desc, fixed: *const *const zk_fr, perm: *const *const zk_fr,
+                        l0: *const zk_fr, l_last: *const zk_fr, l_active_row: *const zk_fr, coeff_form: c_int, out: *mut *mut zk_pk) -> c_int;
+    pub fn zk_pk_destroy(pk: *mut zk_pk);
+    pub fn zk_evaluate_h(pk: *mut zk_pk, advice: *const *const zk_fr, instance: *const *const zk_fr, challenges: *const zk_fr,
+                         y: *const zk_fr, beta: *const zk_fr, gamma: *const zk_fr, theta: *const zk_fr,
+                         lookups: *const *const zk_fr, perm_products: *const *const zk_fr, out_ext: *mut zk_fr) -> c_int;
+}

@@ -1,0 +1,61 @@
+"""N > 1 host logic on CPU: world-size-2 `gloo` run of the base-range MSM sharding used by
+`bench.py --mode msm-sharded` (slice the bases, partial MSM per rank, all_gather of the 96-byte points, fold).
+The per-rank partial MSM is computed by the oracle here (no GPU in this container); on the GPU box the same
+partition / gather / fold runs with zk_msm_dev + NCCL + zk_g1_sum."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    per = n // world
+    bases = orc.gen_points(7, n, threads=2)
+    sc = orc.gen_scalars(8, n)
+    part = orc.best_multiexp(sc[rank * per:(rank + 1) * per], bases[rank * per:(rank + 1) * per], threads=2)
+    # normalise like the library does (z = 1) so that the gathered representation is canonical
+    t = torch.from_numpy(part.astype(np.int64))
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    acc = gathered[0].numpy().astype(np.uint64)
+    for g in gathered[1:]:
+        acc = orc.g1_add(acc, g.numpy().astype(np.uint64))
+    # value timing reduction used by bench.py: max over ranks
+    tm = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        full = orc.best_multiexp(sc, bases, threads=2)
+        q.put((orc.g1_to_affine(acc).tolist(), orc.g1_to_affine(full).tolist(), float(tm.item())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_msm_base_range_sharding_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n, world = 1 << 10, 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, want, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == want
+    assert tmax == 2.0
