@@ -67,12 +67,14 @@ extern "C" void ech_digits(const unsigned* canon, int c, int W, int* digits) {
 
 // ---- evaluate_h interpreter on the host -------------------------------------------------------
 #include "../../zk-dcap-verifier_b200/csrc/evalh_compile.hpp"
+static int g_optimise = 1;
+extern "C" void evh_set_optimise(int on) { g_optimise = on; }
 // cols: n_slots host pointers in slot order (see compile_program); returns 0 or -1 (error text in err)
 extern "C" int evh_run(const zk_evaluator_desc* desc, const void* const* cols, const void* challenges,
                        const unsigned* y, const unsigned* beta, const unsigned* gamma, const unsigned* theta,
                        const unsigned* ext_omega, unsigned* out, unsigned long long* stats, char* err) {
   CompiledEval C;
-  if (!compile_program(*desc, C)) { strncpy(err, C.error.c_str(), 200); return -1; }
+  if (!compile_program(*desc, C, g_optimise != 0)) { strncpy(err, C.error.c_str(), 200); return -1; }
   if (C.max_intermediates > 512) { strncpy(err, "too many intermediates", 200); return -1; }
   EvalScalars S;
   memcpy(S.beta.l, beta, 32); memcpy(S.gamma.l, gamma, 32); memcpy(S.theta.l, theta, 32); memcpy(S.y.l, y, 32);

@@ -200,6 +200,13 @@ def test_qe3_shape_counts_and_interpreters_agree(ffh, orc):
     assert np.array_equal(got_orc, got_dev)
     assert stats[1] >= 100     # ~109 extended columns read per row
     assert stats[0] > 200      # field multiplications per row
+    # the program optimiser (store forwarding, Horner splitting, slot allocation) is value preserving and
+    # shrinks the per-row state from ~70 intermediates to a handful
+    ffh.evh_set_optimise(0)
+    got_raw, stats_raw = host_interp_h(ffh, cs, k, case, desc)
+    ffh.evh_set_optimise(1)
+    assert np.array_equal(got_raw, got_orc)
+    assert stats_raw[0] == stats[0] and stats[3] <= 16 < stats_raw[3]
 
 
 def test_graph_evaluator_dedup_rules():

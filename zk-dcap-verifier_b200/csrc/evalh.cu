@@ -192,7 +192,9 @@ int launch_evalh(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr
   uint32_t ni = pk->C.max_intermediates;
 #define EVALH_ARGS P, S, (const uint32_t*)pk->d_code, (const uint4* const*)pk->d_cols, (const uint4*)pk->d_consts, \
                    (const uint4*)pk->d_challenges, tw, (uint4*)d_out_ext
-  if (ni <= 32) { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<32>, grid, 128, 0, EVALH_ARGS); }
+  if (ni <= 4) { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<4>, grid, 128, 0, EVALH_ARGS); }
+  else if (ni <= 16) { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<16>, grid, 128, 0, EVALH_ARGS); }
+  else if (ni <= 32) { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<32>, grid, 128, 0, EVALH_ARGS); }
   else if (ni <= 128) { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<128>, grid, 128, 0, EVALH_ARGS); }
   else { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<512>, grid, 128, 0, EVALH_ARGS); }
 #undef EVALH_ARGS

@@ -59,6 +59,31 @@ template <int NI>
 struct EvalState {
   Fr inter[NI];
   uint32_t rot[kMaxRot];
+  ZK_HD Fr get(uint32_t i) const { return inter[i]; }
+  ZK_HD void set(uint32_t i, const Fr& v) { inter[i] = v; }
+};
+// After optimisation most programs need <= 4 live intermediates: keep those in REGISTERS (a dynamically
+// indexed array would live in local memory) and pick by index with selects.
+template <>
+struct EvalState<4> {
+  Fr r0, r1, r2, r3;
+  uint32_t rot[kMaxRot];
+  ZK_HD Fr get(uint32_t i) const {
+    Fr v;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint32_t lo = (i & 1) ? r1.l[k] : r0.l[k], hi = (i & 1) ? r3.l[k] : r2.l[k];
+      v.l[k] = (i & 2) ? hi : lo;
+    }
+    return v;
+  }
+  ZK_HD void set(uint32_t i, const Fr& v) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      r0.l[k] = (i == 0) ? v.l[k] : r0.l[k]; r1.l[k] = (i == 1) ? v.l[k] : r1.l[k];
+      r2.l[k] = (i == 2) ? v.l[k] : r2.l[k]; r3.l[k] = (i == 3) ? v.l[k] : r3.l[k];
+    }
+  }
 };
 
 ZK_HD uint32_t rot_idx(size_t idx, int32_t rot, uint32_t rot_shift, size_t mask) {
@@ -74,7 +99,7 @@ ZK_HD Fr vs_fetch(uint32_t src, const EvalProgram& P, const EvalGraph& G, const 
   uint32_t kind = src >> 28, a = src & 0xFFFFFu, b = (src >> 20) & 0xFFu;
   switch (kind) {
     case VS_CONSTANT: return Fr::load(consts + 2 * (size_t)(G.const_base + a));
-    case VS_INTERMEDIATE: return st.inter[a];
+    case VS_INTERMEDIATE: return st.get(a);
     case VS_FIXED: return Fr::load(cols[P.off_fixed + a] + 2 * (size_t)st.rot[b]);
     case VS_ADVICE: return Fr::load(cols[P.off_advice + a] + 2 * (size_t)st.rot[b]);
     case VS_INSTANCE: return Fr::load(cols[P.off_instance + a] + 2 * (size_t)st.rot[b]);
@@ -118,9 +143,9 @@ ZK_HD Fr graph_eval(const EvalProgram& P, const EvalGraph& G, const uint32_t* co
       }
       default: r = a; break;
     }
-    st.inter[target] = r;
+    st.set(target, r);
   }
-  return G.n_calcs ? st.inter[G.last_target] : Fr::zero();
+  return G.n_calcs ? st.get(G.last_target) : Fr::zero();
 }
 
 // One row of Evaluator::evaluate_h.  `beta_term` = extended_omega^idx.

@@ -51,47 +51,170 @@ inline bool pack_source(const zk_value_source& s, const zk_graph& g, const zk_ev
   return true;
 }
 
+// One calculation of the intermediate representation the optimiser works on.
+struct IrOp {
+  uint32_t kind, target, a, b;          // packed sources
+  std::vector<uint32_t> parts;          // Horner parts (packed)
+};
+
+inline bool is_inter(uint32_t src) { return (src >> 28) == VS_INTERMEDIATE; }
+inline uint32_t inter_idx(uint32_t src) { return src & 0xFFFFFu; }
+
+// Value-preserving rewrites of a GraphEvaluator program (the reference's own add_expression rules are
+// likewise only value preserving):
+//   1. Store forwarding: `Store(src)` defines no new value -- its consumers read `src` directly.
+//   2. Horner splitting: Horner(start, [p0..pm), f) becomes m steps acc = acc*f + p_i, each placed right after
+//      p_i is available, so that the parts do not all have to stay live until the end.
+//   3. Slot allocation: intermediates are renamed onto a minimal set of slots by live range.
+// The result keeps per-thread state small enough to stay in L1 (the unoptimised graphs needed 4 KiB per row).
+inline void optimise_graph(std::vector<IrOp>& ops, uint32_t& num_intermediates, uint32_t& last_target) {
+  if (ops.empty()) return;
+  // ---- 1. store forwarding -----------------------------------------------------------------------
+  std::vector<uint32_t> alias(num_intermediates, 0xFFFFFFFFu);
+  auto resolve = [&](uint32_t src) {
+    while (is_inter(src) && alias[inter_idx(src)] != 0xFFFFFFFFu) src = alias[inter_idx(src)];
+    return src;
+  };
+  std::vector<IrOp> fwd;
+  for (size_t i = 0; i < ops.size(); i++) {
+    IrOp o = ops[i];
+    o.a = resolve(o.a);
+    o.b = resolve(o.b);
+    for (auto& p : o.parts) p = resolve(p);
+    bool last = (i + 1 == ops.size());
+    if (o.kind == OP_STORE && !last) { alias[o.target] = o.a; continue; }
+    fwd.push_back(o);
+  }
+  // ---- 2. Horner splitting ------------------------------------------------------------------------
+  // def_pos[t] = index in `fwd` of the op defining intermediate t
+  std::vector<IrOp> sched;
+  {
+    std::vector<int> def_pos(num_intermediates, -1);
+    for (size_t i = 0; i < fwd.size(); i++) def_pos[fwd[i].target] = (int)i;
+    // steps[i] = list of Horner steps to emit right after fwd[i]
+    std::vector<std::vector<IrOp>> after(fwd.size());
+    std::vector<bool> drop(fwd.size(), false);
+    for (size_t h = 0; h < fwd.size(); h++) {
+      const IrOp& H = fwd[h];
+      if (H.kind != OP_HORNER || H.parts.size() < 2) continue;
+      // the start value must be available before the first step: place steps no earlier than its definition
+      int pos = is_inter(H.a) ? def_pos[inter_idx(H.a)] : -1;
+      if (is_inter(H.b) && def_pos[inter_idx(H.b)] > pos) pos = def_pos[inter_idx(H.b)];
+      uint32_t acc = H.a;
+      bool ok = true;
+      std::vector<std::pair<int, IrOp>> steps;
+      for (size_t i = 0; i < H.parts.size(); i++) {
+        uint32_t pi = H.parts[i];
+        int dp = is_inter(pi) ? def_pos[inter_idx(pi)] : -1;
+        if (dp >= (int)h) { ok = false; break; }
+        if (dp > pos) pos = dp;
+        IrOp st;
+        st.kind = OP_HORNER; st.a = acc; st.b = H.b; st.parts = {pi};
+        bool final_step = (i + 1 == H.parts.size());
+        st.target = final_step ? H.target : num_intermediates++;
+        acc = vs_pack(VS_INTERMEDIATE, st.target, 0);
+        steps.push_back({pos, st});
+      }
+      if (!ok) continue;
+      drop[h] = true;
+      for (auto& ps : steps) {
+        // position -1 = before every other op: kept in after[0] with a marker bit
+        (ps.first < 0 ? after[0] : after[ps.first]).push_back(ps.second);
+        if (ps.first < 0) after[0].back().kind |= 0x100u;
+      }
+    }
+    for (size_t i = 0; i < fwd.size(); i++) {
+      // steps flagged 0x100 go BEFORE fwd[i] (only possible for i == 0)
+      for (auto& st : after[i]) if (st.kind & 0x100u) { IrOp c = st; c.kind &= 0xFFu; sched.push_back(c); }
+      if (!drop[i]) sched.push_back(fwd[i]);
+      for (auto& st : after[i]) if (!(st.kind & 0x100u)) sched.push_back(st);
+    }
+  }
+  // ---- 3. slot allocation by live range ----------------------------------------------------------------
+  std::vector<int> last_use(num_intermediates, -1);
+  auto use = [&](uint32_t src, int i) { if (is_inter(src)) last_use[inter_idx(src)] = i; };
+  for (size_t i = 0; i < sched.size(); i++) {
+    use(sched[i].a, (int)i); use(sched[i].b, (int)i);
+    for (auto p : sched[i].parts) use(p, (int)i);
+  }
+  uint32_t final_t = sched.back().target;
+  last_use[final_t] = (int)sched.size();               // the graph's result must survive
+  std::vector<uint32_t> slot_of(num_intermediates, 0xFFFFFFFFu), free_slots;
+  uint32_t n_slots = 0;
+  auto remap = [&](uint32_t src) { return is_inter(src) ? vs_pack(VS_INTERMEDIATE, slot_of[inter_idx(src)], 0) : src; };
+  for (size_t i = 0; i < sched.size(); i++) {
+    IrOp& o = sched[i];
+    uint32_t oa = o.a, ob = o.b;
+    std::vector<uint32_t> oparts = o.parts;
+    o.a = remap(o.a); o.b = remap(o.b);
+    for (auto& p : o.parts) p = remap(p);
+    // operands whose last use is this op release their slot before the target is allocated (in-place update)
+    auto release = [&](uint32_t src) {
+      if (is_inter(src) && last_use[inter_idx(src)] == (int)i && slot_of[inter_idx(src)] != 0xFFFFFFFFu) {
+        free_slots.push_back(slot_of[inter_idx(src)]);
+        last_use[inter_idx(src)] = -2;                  // released once
+      }
+    };
+    release(oa); release(ob);
+    for (auto p : oparts) release(p);
+    uint32_t sl;
+    if (!free_slots.empty()) { sl = free_slots.back(); free_slots.pop_back(); } else sl = n_slots++;
+    slot_of[o.target] = sl;
+    if (last_use[o.target] == -1) { /* dead value: its slot is reusable right away */ free_slots.push_back(sl); }
+    o.target = sl;
+  }
+  ops.swap(sched);
+  num_intermediates = n_slots ? n_slots : 1;
+  last_target = ops.back().target;
+}
+
 inline bool compile_graph(const zk_graph& g, const zk_evaluator_desc& d, CompiledEval& C, EvalGraph* out,
-                          std::set<std::pair<uint32_t, uint32_t>>& cols) {
+                          std::set<std::pair<uint32_t, uint32_t>>& cols, bool optimise) {
   if (g.n_rotations > (uint32_t)kMaxRot) { C.error = "graph uses more than 16 distinct rotations"; return false; }
   out->const_base = (uint32_t)C.consts.size();
   for (uint32_t i = 0; i < g.n_constants; i++) C.consts.push_back(g.constants[i]);
   out->rot_off = (uint32_t)C.code.size();
   out->n_rot = g.n_rotations;
   for (uint32_t i = 0; i < g.n_rotations; i++) C.code.push_back((uint32_t)g.rotations[i]);
-  out->code_off = (uint32_t)C.code.size();
-  out->n_calcs = g.n_calcs;
-  out->last_target = 0;
-  if (g.num_intermediates > C.max_intermediates) C.max_intermediates = g.num_intermediates;
+  std::vector<IrOp> ops;
   for (uint32_t i = 0; i < g.n_calcs; i++) {
     const zk_calculation& c = g.calcs[i];
     if (c.kind > ZK_CALC_STORE) { C.error = "unknown calculation kind"; return false; }
     if (c.target >= g.num_intermediates) { C.error = "calculation target out of range"; return false; }
-    uint32_t sa = 0, sb = 0;
-    if (!pack_source(c.a, g, d, &sa, cols, C.error)) return false;
+    IrOp o; o.kind = c.kind; o.target = c.target; o.a = 0; o.b = 0;
+    if (!pack_source(c.a, g, d, &o.a, cols, C.error)) return false;
     bool binary = c.kind == ZK_CALC_ADD || c.kind == ZK_CALC_SUB || c.kind == ZK_CALC_MUL || c.kind == ZK_CALC_HORNER;
-    if (binary && !pack_source(c.b, g, d, &sb, cols, C.error)) return false;
+    if (binary && !pack_source(c.b, g, d, &o.b, cols, C.error)) return false;
     uint32_t nparts = c.kind == ZK_CALC_HORNER ? c.parts_len : 0;
     if (nparts >= (1u << 24) || (nparts && (uint64_t)c.parts_off + nparts > g.n_horner_parts)) { C.error = "horner parts out of range"; return false; }
-    C.code.push_back(c.kind | (nparts << 8));
-    C.code.push_back(c.target);
-    C.code.push_back(sa);
-    C.code.push_back(sb);
     for (uint32_t p = 0; p < nparts; p++) {
       uint32_t sp = 0;
       if (!pack_source(g.horner_parts[c.parts_off + p], g, d, &sp, cols, C.error)) return false;
-      C.code.push_back(sp);
+      o.parts.push_back(sp);
     }
-    if (c.kind == ZK_CALC_MUL || c.kind == ZK_CALC_SQUARE) C.muls_per_row += 1;
-    if (c.kind == ZK_CALC_HORNER) C.muls_per_row += nparts;
-    out->last_target = c.target;
+    ops.push_back(o);
+  }
+  uint32_t n_inter = g.num_intermediates, last_target = ops.empty() ? 0 : ops.back().target;
+  if (optimise) optimise_graph(ops, n_inter, last_target);
+  out->code_off = (uint32_t)C.code.size();
+  out->n_calcs = (uint32_t)ops.size();
+  out->last_target = last_target;
+  if (n_inter > C.max_intermediates) C.max_intermediates = n_inter;
+  for (const IrOp& o : ops) {
+    C.code.push_back(o.kind | ((uint32_t)o.parts.size() << 8));
+    C.code.push_back(o.target);
+    C.code.push_back(o.a);
+    C.code.push_back(o.b);
+    for (auto p : o.parts) C.code.push_back(p);
+    if (o.kind == OP_MUL || o.kind == OP_SQUARE) C.muls_per_row += 1;
+    if (o.kind == OP_HORNER) C.muls_per_row += o.parts.size();
   }
   return true;
 }
 
 }  // namespace detail
 
-inline bool compile_program(const zk_evaluator_desc& d, CompiledEval& C) {
+inline bool compile_program(const zk_evaluator_desc& d, CompiledEval& C, bool optimise = true) {
   C = CompiledEval();
   EvalProgram& P = C.prog;
   memset(&P, 0, sizeof P);
@@ -116,9 +239,9 @@ inline bool compile_program(const zk_evaluator_desc& d, CompiledEval& C) {
   P.off_l0 = slot++; P.off_l_last = slot++; P.off_l_active = slot++;
   C.n_slots = slot;
   std::set<std::pair<uint32_t, uint32_t>> cols;
-  if (!detail::compile_graph(d.custom_gates, d, C, &P.gates, cols)) return false;
+  if (!detail::compile_graph(d.custom_gates, d, C, &P.gates, cols, optimise)) return false;
   for (uint32_t l = 0; l < d.n_lookups; l++)
-    if (!detail::compile_graph(d.lookups[l], d, C, &P.lookups[l], cols)) return false;
+    if (!detail::compile_graph(d.lookups[l], d, C, &P.lookups[l], cols, optimise)) return false;
   P.perm_cols_off = (uint32_t)C.code.size();
   for (uint32_t c = 0; c < d.n_perm_columns; c++) {
     const zk_column& col = d.perm_columns[c];

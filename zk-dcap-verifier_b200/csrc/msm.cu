@@ -22,6 +22,8 @@
 //   5. windows   with resident bases the table 2^(c*w) * G_i is precomputed once per SRS, so all
 //                windows share ONE bucket set and step 5 vanishes; otherwise the W window sums
 //                are combined by Horner with c doublings each.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ec.cuh"
 
@@ -92,23 +94,118 @@ __global__ void __launch_bounds__(1024) k_msm_scan(uint32_t* counts, uint32_t* s
 
 // ---- 3: bucket accumulation -------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint4* points, const uint32_t* entries,
-                                                        const uint32_t* starts, MsmPlan P, uint4* buckets) {
-  size_t vb = blockIdx.x * (size_t)blockDim.x + threadIdx.x;   // virtual bucket = bucket * S + lane
+// Load-balanced segmented accumulation.  The sorted entry list is cut into chunks of T entries, one
+// chunk per thread, REGARDLESS of bucket boundaries, so a bucket holding half of all entries (bit /
+// byte valued witness columns, a narrow top window) costs the same as a uniform distribution.
+// A run of equal-bucket entries that lies completely inside a chunk is that bucket's final sum and is
+// written to `buckets`; the (at most two) runs that continue into a neighbouring chunk go to the
+// thread's two partial slots, tagged with the bucket and with which side is still open.  The slot
+// array is again sorted by bucket, so the same reduction is applied to it (k_msm_acc_partials) until
+// one thread sees everything.  Empty buckets keep the zeroed (= identity) value.
+constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kOpenLeft = 0x80000000u, kOpenRight = 0x40000000u, kSlotIdMask = 0x3FFFFFFFu;
+
+__global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint4* points, const uint32_t* entries,
+                                                        const uint32_t* starts, MsmPlan P, uint32_t T,
+                                                        uint32_t nthreads, uint4* buckets, uint32_t* slot_ids,
+                                                        uint4* slot_pts) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t msm = blockIdx.y;
-  if (vb >= P.nb * P.S) return;
-  size_t b = vb / P.S;
-  uint32_t lane = (uint32_t)(vb % P.S);
+  if (t >= nthreads) return;
   const uint32_t* st = starts + msm * (P.nb + 1);
   const uint32_t* ent = entries + msm * P.ent_per_msm;
-  uint32_t lo = st[b], hi = st[b + 1];
-  XYZZ acc = XYZZ::identity();
-  for (uint32_t q = lo + lane; q < hi; q += P.S) {
-    uint32_t e = ent[q];
-    Affine pt = Affine::load(points + 4 * (size_t)(e & 0x7fffffffu)).cneg((e >> 31) != 0);
-    acc = acc.madd(pt);
+  uint32_t* sid = slot_ids + (msm * nthreads + t) * 2;
+  uint4* spt = slot_pts + 8 * ((msm * nthreads + t) * 2);
+  uint4* bk = buckets + 8 * (msm * P.nb);
+  const uint32_t total = st[P.nb];
+  uint32_t id0 = kSlotEmpty, id1 = kSlotEmpty;
+  const uint64_t q0 = (uint64_t)t * T;
+  if (q0 < total) {
+    const uint32_t q1 = (uint32_t)(q0 + T < total ? q0 + T : total);
+    // bucket holding entry q0: the last b with st[b] <= q0 (and st[b+1] > q0)
+    uint32_t lo = 0, hi = (uint32_t)P.nb;      // invariant: st[lo] <= q0 < st[hi]
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (st[mid] <= q0) lo = mid; else hi = mid;
+    }
+    // ONE flat loop of exactly q1 - q0 additions per thread: every lane of a warp stays in lockstep on the
+    // expensive madd; a bucket boundary only triggers a short (divergent) flush.
+    uint32_t b = lo, bend = st[b + 1];
+    bool open_l = st[b] < q0;
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t q = (uint32_t)q0; q < q1; q++) {
+      if (q == bend) {                       // bucket b ended inside the chunk
+        if (!open_l) acc.store(bk + 8 * (size_t)b);
+        else { id0 = b | kOpenLeft; acc.store(spt); }
+        acc = XYZZ::identity();
+        open_l = false;
+        b++;
+        while (st[b + 1] == q) b++;          // skip empty buckets
+        bend = st[b + 1];
+      }
+      uint32_t e = ent[q];
+      Affine pt = Affine::load(points + 4 * (size_t)(e & 0x7fffffffu)).cneg((e >> 31) != 0);
+      acc = acc.madd(pt);
+    }
+    bool open_r = bend > q1;
+    if (!open_l && !open_r) {
+      acc.store(bk + 8 * (size_t)b);
+    } else if (open_l) {
+      id0 = b | kOpenLeft | (open_r ? kOpenRight : 0u);
+      acc.store(spt);
+    } else {
+      id1 = b | kOpenRight;
+      acc.store(spt + 8);
+    }
   }
-  acc.store(buckets + 8 * (msm * P.nb * P.S + vb));
+  sid[0] = id0; sid[1] = id1;
+}
+
+// Next levels: the same reduction over the slot array (ids sorted, kSlotEmpty interspersed).
+__global__ void __launch_bounds__(128) k_msm_acc_partials(const uint32_t* in_ids, const uint4* in_pts, uint32_t n_in,
+                                                          uint32_t T, uint32_t nthreads, size_t nb, uint4* buckets,
+                                                          uint32_t* out_ids, uint4* out_pts) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t msm = blockIdx.y;
+  if (t >= nthreads) return;
+  const uint32_t* iid = in_ids + msm * n_in;
+  const uint4* ipt = in_pts + 8 * (msm * n_in);
+  uint32_t* sid = out_ids + (msm * nthreads + t) * 2;
+  uint4* spt = out_pts + 8 * ((msm * nthreads + t) * 2);
+  uint4* bk = buckets + 8 * (msm * nb);
+  uint32_t id0 = kSlotEmpty, id1 = kSlotEmpty;
+  uint64_t s0 = (uint64_t)t * T;
+  uint32_t s1 = (uint32_t)(s0 + T < n_in ? s0 + T : n_in);
+  uint32_t s = (uint32_t)s0;
+  while (s < s1) {
+    uint32_t raw = iid[s];
+    if (raw == kSlotEmpty) { s++; continue; }
+    uint32_t id = raw & kSlotIdMask;
+    bool open_l = (raw & kOpenLeft) != 0, open_r = (raw & kOpenRight) != 0;
+    XYZZ acc = XYZZ::load(ipt + 8 * (size_t)s);
+    s++;
+    // absorb the following slots of the same bucket that lie in this chunk
+    while (s < s1) {
+      uint32_t r2 = iid[s];
+      if (r2 == kSlotEmpty) { s++; continue; }
+      if ((r2 & kSlotIdMask) != id) break;
+      acc = acc.add(XYZZ::load(ipt + 8 * (size_t)s));
+      open_r = (r2 & kOpenRight) != 0;
+      s++;
+    }
+    // a run whose first slot is open to the left (last slot open to the right) continues outside this chunk,
+    // unless the matching neighbour slot is inside the chunk -- in which case it was absorbed above
+    if (!open_l && !open_r) {
+      acc.store(bk + 8 * (size_t)id);
+    } else if (open_l) {
+      id0 = id | kOpenLeft | (open_r ? kOpenRight : 0u);
+      acc.store(spt);
+    } else {
+      id1 = id | kOpenRight;
+      acc.store(spt + 8);
+    }
+  }
+  sid[0] = id0; sid[1] = id1;
 }
 
 // ---- 4: reduction -------------------------------------------------------------------------------------
@@ -219,18 +316,13 @@ MsmPlan make_plan(size_t n, size_t count, bool table, uint32_t table_c, size_t s
   P.B = 1u << (P.c - 1);
   P.nb = (size_t)P.G * P.B;
   P.ent_per_msm = n * P.W;
-  // enough threads to fill the chip: sm_count * 1024 virtual buckets over the whole batch
-  size_t want = (size_t)sm_count * 1024;
-  uint32_t S = 1;
-  while (S < 32 && P.nb * count * S < want) S <<= 1;
-  // a bucket holds n*W/nb entries on average: do not split below ~8 entries per thread
-  size_t avg = P.nb ? P.ent_per_msm / P.nb : 0;
-  while (S > 1 && avg / S < 8) S >>= 1;
-  P.S = S;
+  (void)sm_count;
+  P.S = 1;      // parallelism now comes from the chunked accumulation, not from splitting buckets
   return P;
 }
 
 uint32_t table_window_bits(uint32_t k) {
+  if (const char* v = getenv("ZK_MSM_C")) { int c = atoi(v); if (c >= 2 && c <= 22) return (uint32_t)c; }
   int c = (int)k - 3;
   if (c < 4) c = 4;
   if (c > 16) c = 16;
@@ -256,7 +348,7 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   const size_t ent_bytes = P.count * P.ent_per_msm * 4;
   const size_t bucket_bytes = P.count * P.nb * P.S * 128;
   // reduction levels
-  const uint32_t seg = 16;
+  const uint32_t seg = getenv("ZK_MSM_SEG") ? (uint32_t)atoi(getenv("ZK_MSM_SEG")) : 16;
   size_t vper = (size_t)P.B * P.S;
   uint32_t nseg1 = (uint32_t)((vper + seg - 1) / seg);
   size_t lvl1 = P.count * P.G * P.c * nseg1;            // points after level 1
@@ -264,7 +356,16 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t off_cnt = 0, off_st = off_cnt + align(cnt_bytes), off_ent = off_st + align(st_bytes);
   size_t off_bk = off_ent + align(ent_bytes), off_r1 = off_bk + align(bucket_bytes), off_r2 = off_r1 + align(red_bytes);
-  size_t total = off_r2 + align(red_bytes / seg + 128 * P.count * P.G * P.c);
+  // chunked accumulation: T0 entries per thread at level 0, T1 slots per thread afterwards
+  const uint32_t T0 = getenv("ZK_MSM_T0") ? (uint32_t)atoi(getenv("ZK_MSM_T0")) : 64;
+  const uint32_t T1 = getenv("ZK_MSM_T1") ? (uint32_t)atoi(getenv("ZK_MSM_T1")) : 8;   // short serial chains: these levels are latency bound
+  const uint32_t nth0 = (uint32_t)((P.ent_per_msm + T0 - 1) / T0);
+  const uint32_t nth1 = (2 * nth0 + T1 - 1) / T1;
+  const size_t slotA = (size_t)2 * nth0, slotB = (size_t)2 * nth1 + 2;
+  size_t off_sa_id = off_r2 + align(red_bytes / seg + 128 * P.count * P.G * P.c);
+  size_t off_sa_pt = off_sa_id + align(P.count * slotA * 4), off_sb_id = off_sa_pt + align(P.count * slotA * 128);
+  size_t off_sb_pt = off_sb_id + align(P.count * slotB * 4);
+  size_t total = off_sb_pt + align(P.count * slotB * 128);
   ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_work, total));
   char* w = (char*)ctx->msm_work.p;
   uint32_t* counts = (uint32_t*)(w + off_cnt);
@@ -279,8 +380,25 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   ZK_LAUNCH(ctx, "msm_digits_hist", k_msm_digits<false>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)nullptr, (uint32_t*)nullptr);
   ZK_LAUNCH(ctx, "msm_scan", k_msm_scan, (unsigned)P.count, 1024, 0, counts, starts, P.nb);
   ZK_LAUNCH(ctx, "msm_digits_scatter", k_msm_digits<true>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)starts, entries);
-  dim3 ga(zk_div_up(P.nb * P.S, 128), (unsigned)P.count);
-  ZK_LAUNCH(ctx, "msm_accumulate", k_msm_accumulate, ga, 128, 0, (const uint4*)d_points, (const uint32_t*)entries, (const uint32_t*)starts, P, buckets);
+  ZK_CUDA(ctx, cudaMemsetAsync(buckets, 0, bucket_bytes, ctx->stream));     // identity everywhere
+  {
+    uint32_t* ida = (uint32_t*)(w + off_sa_id); uint4* pta = (uint4*)(w + off_sa_pt);
+    uint32_t* idb = (uint32_t*)(w + off_sb_id); uint4* ptb = (uint4*)(w + off_sb_pt);
+    dim3 ga(zk_div_up(nth0, 128), (unsigned)P.count);
+    ZK_LAUNCH(ctx, "msm_accumulate", k_msm_accumulate, ga, 128, 0, (const uint4*)d_points, (const uint32_t*)entries,
+              (const uint32_t*)starts, P, T0, nth0, buckets, ida, pta);
+    uint32_t n_in = 2 * nth0;
+    for (;;) {
+      uint32_t nth = (n_in + T1 - 1) / T1;
+      dim3 gp(zk_div_up(nth, 128), (unsigned)P.count);
+      ZK_LAUNCH(ctx, "msm_acc_partials", k_msm_acc_partials, gp, 128, 0, (const uint32_t*)ida, (const uint4*)pta, n_in, T1,
+                nth, P.nb, buckets, idb, ptb);
+      if (nth == 1) break;     // one thread saw every slot: nothing is left open
+      uint32_t* ti = ida; ida = idb; idb = ti;
+      uint4* tp = pta; pta = ptb; ptb = tp;
+      n_in = 2 * nth;
+    }
+  }
   size_t rows = P.count * P.G * P.c;
   dim3 gr(zk_div_up((size_t)P.G * P.c * nseg1, 128), (unsigned)P.count);
   ZK_LAUNCH(ctx, "msm_reduce_bits", k_msm_reduce_bits, gr, 128, 0, (const uint4*)buckets, P, seg, nseg1, r1);

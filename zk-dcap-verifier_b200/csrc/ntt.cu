@@ -18,6 +18,8 @@
 // The inverse direction reuses the same table through omega^-e = -omega^(N/2-e).
 // Coset scaling (zeta^(i mod 3)), zero padding and the 1/N factor are fused into the first
 // pass's load and the last pass's store.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ff.cuh"
 
@@ -25,8 +27,18 @@ using namespace zk;
 
 namespace {
 
-constexpr int kTileLog = 11;      // 2^11 points = 64 KiB of shared memory per CTA
-constexpr int kMaxT = 8;          // stages per pass
+constexpr int kTileLogDefault = 10;   // 2^10 points = 32 KiB of shared memory per CTA (6 CTAs / SM)
+constexpr int kMaxTDefault = 8;       // stages per pass
+// tuning overrides (ZK_NTT_TILE_LOG in [6,12], ZK_NTT_MAX_T in [2,10]); read once
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+const int kTileLog = env_int("ZK_NTT_TILE_LOG", kTileLogDefault, 6, 12);
+const int kMaxT = env_int("ZK_NTT_MAX_T", kMaxTDefault, 2, 10) > kTileLog ? kTileLog
+                                                                           : env_int("ZK_NTT_MAX_T", kMaxTDefault, 2, 10);
 constexpr int kThreads = 256;
 
 struct PassConsts {
