@@ -2,6 +2,8 @@
 // transforms of the witness polynomials and the fused per-row kernel (evalh.cuh).
 // Reference: halo2_proofs plonk::evaluation::Evaluator::evaluate_h ([UPSTREAM] src/plonk/evaluation.rs
 // @ c254c75f), called from create_proof (circuits/src/sgx_dcap_verifier.rs:814).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "evalh_compile.hpp"
 
@@ -85,7 +87,7 @@ extern "C" int zk_pk_upload(zk_ctx* ctx, const zk_evaluator_desc* desc, const zk
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
   zk_pk* pk = new zk_pk();
   pk->ctx = ctx;
-  if (!compile_program(*desc, pk->C)) {
+  if (!compile_program(*desc, pk->C, getenv("ZK_EVALH_NOOPT") == nullptr)) {
     std::string e = pk->C.error;
     delete pk;
     ZK_FAIL(ctx, ZK_ERR_ARG, "zk_pk_upload: %s", e.c_str());
@@ -190,6 +192,10 @@ int launch_evalh(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr
   const uint4* tw = (const uint4*)zk_domain_twiddles(pk->dom);
   unsigned grid = zk_div_up(E, 128);
   uint32_t ni = pk->C.max_intermediates;
+  // measured on B200: the select-based register file (NI = 4) is slower than 16 L1-resident slots (21.5 vs 19.2 ms)
+  uint32_t ni_min = 16;
+  if (const char* v = getenv("ZK_EVALH_NI_MIN")) ni_min = (uint32_t)atoi(v);
+  if (ni < ni_min) ni = ni_min;
 #define EVALH_ARGS P, S, (const uint32_t*)pk->d_code, (const uint4* const*)pk->d_cols, (const uint4*)pk->d_consts, \
                    (const uint4*)pk->d_challenges, tw, (uint4*)d_out_ext
   if (ni <= 4) { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<4>, grid, 128, 0, EVALH_ARGS); }
