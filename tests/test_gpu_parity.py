@@ -207,3 +207,51 @@ def test_quotient_pipeline_roundtrip(ctx, orc):
     o = case["dom"]
     got = d.extended_to_coeff(d.divide_by_vanishing_poly(want))
     assert np.array_equal(got, o.extended_to_coeff(o.divide_by_vanishing_poly(want)))
+
+
+# ---- batched commitments and the batched-affine pairing round ------------------------------------------------
+def _commit_batch(ctx, params_n, scalars_list, which):
+    """zk_msm_batch_dev through the raw ABI with the library's own device-memory helpers"""
+    import ctypes as C
+    lib = ctx.lib
+    cnt = len(scalars_list)
+    n = params_n
+    flat = np.ascontiguousarray(np.stack(scalars_list)).reshape(cnt * n, 4)
+    d_s, d_o = C.c_void_p(), C.c_void_p()
+    ctx.check(lib.zk_dev_alloc(ctx.h, flat.nbytes, C.byref(d_s)))
+    ctx.check(lib.zk_dev_alloc(ctx.h, cnt * 96, C.byref(d_o)))
+    ctx.check(lib.zk_h2d(ctx.h, d_s, flat.ctypes.data_as(C.c_void_p), flat.nbytes))
+    ctx.check(lib.zk_msm_batch_dev(ctx.h, d_s, which, n, cnt, d_o))
+    out = np.empty((cnt, 12), dtype=np.uint64)
+    ctx.check(lib.zk_d2h(ctx.h, out.ctypes.data_as(C.c_void_p), d_o, out.nbytes))
+    ctx.check(lib.zk_dev_free(ctx.h, d_s)); ctx.check(lib.zk_dev_free(ctx.h, d_o))
+    return out
+
+
+@pytest.mark.parametrize("k,cnt", [(10, 5), (13, 3)])
+def test_commit_batch_vs_oracle(ctx, orc, k, cnt):
+    n = 1 << k
+    g, gl = orc.gen_points(900 + k, n), orc.gen_points(901 + k, n)
+    gl[7] = gl[6]                                  # equal neighbours in a bucket are likely for equal scalars
+    zk.ParamsKZG(k, g, gl, ctx, precompute=True)
+    rnd = random.Random(k)
+    cols = [orc.gen_scalars(50 + i, n) for i in range(cnt - 2)]
+    cols.append(pm.to_mont_limbs([rnd.choice([0, 1, 1, 2, rnd.getrandbits(8)]) for _ in range(n)], pm.R_MOD))
+    cols.append(pm.to_mont_limbs([1] * n, pm.R_MOD))
+    got = _commit_batch(ctx, n, cols, 2)
+    for i in range(cnt):
+        assert np.array_equal(affine(orc, got[i]), affine(orc, orc.best_multiexp(cols[i], gl))), i
+
+
+def test_batched_affine_round_forced():
+    """Re-runs the MSM parity tests with the batched-affine pairing round forced on (ZK_MSM_BA=1): it is otherwise
+    only taken for >= 2^24 bucket entries.  A fresh process is needed because the switch is read per call but the
+    default context is shared."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ZK_MSM_BA="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "(multiexp or commit or linearity) and not forced"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -105,7 +105,10 @@ __global__ void __launch_bounds__(1024) k_msm_scan(uint32_t* counts, uint32_t* s
 constexpr uint32_t kSlotEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kOpenLeft = 0x80000000u, kOpenRight = 0x40000000u, kSlotIdMask = 0x3FFFFFFFu;
 
-__global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint4* points, const uint32_t* entries,
+// DIRECT = false: entry q names a table point (index | sign << 31).  DIRECT = true: the q-th point of this
+// MSM's own point list (the output of the batched-affine pairing round) is used as it is.
+template <bool DIRECT>
+__global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint4* points, size_t pts_stride, const uint32_t* entries,
                                                         const uint32_t* starts, MsmPlan P, uint32_t T,
                                                         uint32_t nthreads, uint4* buckets, uint32_t* slot_ids,
                                                         uint4* slot_pts) {
@@ -143,8 +146,13 @@ __global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint4* points, 
         while (st[b + 1] == q) b++;          // skip empty buckets
         bend = st[b + 1];
       }
-      uint32_t e = ent[q];
-      Affine pt = Affine::load(points + 4 * (size_t)(e & 0x7fffffffu)).cneg((e >> 31) != 0);
+      Affine pt;
+      if (DIRECT) {
+        pt = Affine::load(points + 4 * (msm * pts_stride + q));
+      } else {
+        uint32_t e = ent[q];
+        pt = Affine::load(points + 4 * (size_t)(e & 0x7fffffffu)).cneg((e >> 31) != 0);
+      }
       acc = acc.madd(pt);
     }
     bool open_r = bend > q1;
@@ -161,18 +169,141 @@ __global__ void __launch_bounds__(128, 4) k_msm_accumulate(const uint4* points, 
   sid[0] = id0; sid[1] = id1;
 }
 
-// Next levels: the same reduction over the slot array (ids sorted, kSlotEmpty interspersed).
-__global__ void __launch_bounds__(128) k_msm_acc_partials(const uint32_t* in_ids, const uint4* in_pts, uint32_t n_in,
-                                                          uint32_t T, uint32_t nthreads, size_t nb, uint4* buckets,
-                                                          uint32_t* out_ids, uint4* out_pts) {
-  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+// ---- 3a: one batched-affine pairing round -----------------------------------------------------------------
+// Inside every bucket the entries are added in pairs (2j, 2j+1) as AFFINE points: lambda = dy / dx needs one
+// inversion per addition, and all additions of a round are independent, so the inversions are shared with
+// Montgomery's trick: every thread multiplies up the denominators of its M pairs, the 256 thread products of
+// a CTA are combined by a prefix / suffix product scan in shared memory, ONE field inversion (thread 0) serves
+// the whole CTA (256 * M additions), and the per-pair inverses are unwound backwards.  Cost per addition:
+// 1 (running product) + 2 (unwind) + 3 (lambda, lambda^2, y3) = 6 multiplications instead of 10 for the
+// inversion-free XYZZ mixed addition.  The round halves the entry list; its output (affine points, bucket
+// offsets ceil(m/2)) feeds the chunked XYZZ accumulation.  (0,0) encodes the identity, as in halo2curves.
+__global__ void k_pair_counts(const uint32_t* starts, size_t nb, uint32_t* out_counts) {
+  size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t msm = blockIdx.y;
-  if (t >= nthreads) return;
-  const uint32_t* iid = in_ids + msm * n_in;
-  const uint4* ipt = in_pts + 8 * (msm * n_in);
-  uint32_t* sid = out_ids + (msm * nthreads + t) * 2;
-  uint4* spt = out_pts + 8 * ((msm * nthreads + t) * 2);
-  uint4* bk = buckets + 8 * (msm * nb);
+  if (b >= nb) return;
+  const uint32_t* st = starts + msm * (nb + 1);
+  out_counts[msm * nb + b] = (st[b + 1] - st[b] + 1) >> 1;
+}
+
+struct PairCase { Affine p, q; Fq d; int kind; };   // kind: 0 add, 1 double, 2 result = p, 3 result = q, 4 identity
+__device__ __forceinline__ PairCase pair_load(const uint4* points, const uint32_t* ent, uint32_t q0, bool has_q) {
+  PairCase c;
+  uint32_t e0 = ent[q0];
+  c.p = Affine::load(points + 4 * (size_t)(e0 & 0x7fffffffu)).cneg((e0 >> 31) != 0);
+  c.d = Fq::one();
+  if (!has_q) { c.kind = 2; c.q = c.p; return c; }
+  uint32_t e1 = ent[q0 + 1];
+  c.q = Affine::load(points + 4 * (size_t)(e1 & 0x7fffffffu)).cneg((e1 >> 31) != 0);
+  if (c.q.is_identity()) { c.kind = 2; return c; }
+  if (c.p.is_identity()) { c.kind = 3; return c; }
+  Fq dx = c.q.x - c.p.x;
+  if (dx.is_zero()) {
+    if ((c.q.y - c.p.y).is_zero()) { c.kind = 1; c.d = c.p.y.dbl(); } else { c.kind = 4; }
+    return c;
+  }
+  c.kind = 0; c.d = dx;
+  return c;
+}
+
+constexpr uint32_t kPairThreads = 256;
+__global__ void __launch_bounds__(kPairThreads) k_pair_add(const uint4* points, const uint32_t* entries,
+                                                           const uint32_t* starts, const uint32_t* out_starts,
+                                                           MsmPlan P, uint32_t M, size_t out_cap, uint4* out_pts,
+                                                           uint4* scratch) {
+  __shared__ uint4 sm_pre[2 * kPairThreads];    // prefix products (two 16-byte halves per element)
+  __shared__ uint4 sm_suf[2 * kPairThreads];
+  __shared__ uint4 sm_inv[2];
+  const size_t msm = blockIdx.y;
+  const size_t gthreads = (size_t)gridDim.x * kPairThreads;
+  const size_t g = blockIdx.x * (size_t)kPairThreads + threadIdx.x;
+  const uint32_t* st = starts + msm * (P.nb + 1);
+  const uint32_t* ost = out_starts + msm * (P.nb + 1);
+  const uint32_t* ent = entries + msm * P.ent_per_msm;
+  uint4* out = out_pts + 4 * (msm * out_cap);
+  uint4* scr = scratch + 2 * (msm * (size_t)M * gthreads);
+  const uint32_t out_total = ost[P.nb];
+  const uint64_t o0 = (uint64_t)g * M;
+  const uint32_t o1 = (uint32_t)(o0 + M < out_total ? o0 + M : out_total);
+  // bucket of output slot o0
+  uint32_t b0 = 0;
+  if (o0 < out_total) {
+    uint32_t lo = 0, hi = (uint32_t)P.nb;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (ost[mid] <= o0) lo = mid; else hi = mid; }
+    b0 = lo;
+  }
+  // ---- phase 1: running product of the denominators ----------------------------------------------------
+  Fq acc = Fq::one();
+  {
+    uint32_t b = b0;
+    for (uint32_t o = (uint32_t)o0, i = 0; o < o1 && o0 < out_total; o++, i++) {
+      while (o >= ost[b + 1]) b++;
+      uint32_t j = o - ost[b], q0 = st[b] + 2 * j;
+      PairCase c = pair_load(points, ent, q0, q0 + 1 < st[b + 1]);
+      acc.store_raw(scr + 2 * ((size_t)i * gthreads + g));
+      acc = acc * c.d;
+    }
+  }
+  // ---- phase 2: CTA-wide product scans and one inversion -------------------------------------------------
+  auto put = [](uint4* a, uint32_t i, const Fq& v) {
+    a[2 * i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]); a[2 * i + 1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+  };
+  auto get = [](const uint4* a, uint32_t i) {
+    uint4 x = a[2 * i], y = a[2 * i + 1]; Fq v;
+    v.l[0] = x.x; v.l[1] = x.y; v.l[2] = x.z; v.l[3] = x.w; v.l[4] = y.x; v.l[5] = y.y; v.l[6] = y.z; v.l[7] = y.w;
+    return v;
+  };
+  const uint32_t t = threadIdx.x;
+  put(sm_pre, t, acc); put(sm_suf, t, acc);
+  __syncthreads();
+  for (uint32_t off = 1; off < kPairThreads; off <<= 1) {
+    Fq a = get(sm_pre, t), b = get(sm_suf, t);
+    bool hp = t >= off, hs = t + off < kPairThreads;
+    Fq pa = hp ? get(sm_pre, t - off) : Fq::one();
+    Fq sb = hs ? get(sm_suf, t + off) : Fq::one();
+    __syncthreads();
+    if (hp) put(sm_pre, t, a * pa);
+    if (hs) put(sm_suf, t, b * sb);
+    __syncthreads();
+  }
+  if (t == 0) { Fq gi = Fq::inv(get(sm_pre, kPairThreads - 1)); put(sm_inv, 0, gi); }
+  __syncthreads();
+  Fq inv_run = get(sm_inv, 0);
+  if (t > 0) inv_run = inv_run * get(sm_pre, t - 1);
+  if (t + 1 < kPairThreads) inv_run = inv_run * get(sm_suf, t + 1);
+  // ---- phase 3: unwind backwards, finish the additions ---------------------------------------------------
+  if (o0 < out_total) {
+    // bucket of the LAST slot, then walk down
+    uint32_t b = b0;
+    while (o1 - 1 >= ost[b + 1]) b++;
+    for (uint32_t o = o1; o-- > (uint32_t)o0;) {
+      while (o < ost[b]) b--;
+      uint32_t i = o - (uint32_t)o0;
+      uint32_t j = o - ost[b], q0 = st[b] + 2 * j;
+      PairCase c = pair_load(points, ent, q0, q0 + 1 < st[b + 1]);
+      Fq pv = Fq::load(scr + 2 * ((size_t)i * gthreads + g));
+      Fq inv_d = inv_run * pv;
+      inv_run = inv_run * c.d;
+      Affine r;
+      if (c.kind <= 1) {
+        Fq num, xq;
+        if (c.kind == 0) { num = c.q.y - c.p.y; xq = c.q.x; }
+        else { Fq xx = c.p.x.sqr(); num = xx.dbl() + xx; xq = c.p.x; }
+        Fq lam = num * inv_d;
+        r.x = lam.sqr() - c.p.x - xq;
+        r.y = lam * (c.p.x - r.x) - c.p.y;
+      } else if (c.kind == 2) { r = c.p; }
+      else if (c.kind == 3) { r = c.q; }
+      else { r = Affine::identity(); }
+      r.store(out + 4 * (size_t)o);
+    }
+  }
+}
+
+// Next levels: the same reduction over the slot array (ids sorted, kSlotEmpty interspersed).
+// One chunk of T slots -> complete runs into `bk`, at most two open partials into (sid, spt).
+__device__ __forceinline__ void partials_chunk(const uint32_t* iid, const uint4* ipt, uint32_t n_in, uint32_t T,
+                                               size_t t, uint4* bk, uint32_t* sid, uint4* spt) {
   uint32_t id0 = kSlotEmpty, id1 = kSlotEmpty;
   uint64_t s0 = (uint64_t)t * T;
   uint32_t s1 = (uint32_t)(s0 + T < n_in ? s0 + T : n_in);
@@ -193,8 +324,8 @@ __global__ void __launch_bounds__(128) k_msm_acc_partials(const uint32_t* in_ids
       open_r = (r2 & kOpenRight) != 0;
       s++;
     }
-    // a run whose first slot is open to the left (last slot open to the right) continues outside this chunk,
-    // unless the matching neighbour slot is inside the chunk -- in which case it was absorbed above
+    // a run whose first slot is open to the left (last slot open to the right) continues outside this chunk:
+    // a matching neighbour inside the chunk would have been absorbed above
     if (!open_l && !open_r) {
       acc.store(bk + 8 * (size_t)id);
     } else if (open_l) {
@@ -206,6 +337,38 @@ __global__ void __launch_bounds__(128) k_msm_acc_partials(const uint32_t* in_ids
     }
   }
   sid[0] = id0; sid[1] = id1;
+}
+
+__global__ void __launch_bounds__(128) k_msm_acc_partials(const uint32_t* in_ids, const uint4* in_pts, uint32_t n_in,
+                                                          uint32_t T, uint32_t nthreads, size_t nb, uint4* buckets,
+                                                          uint32_t* out_ids, uint4* out_pts, size_t in_stride,
+                                                          size_t out_stride) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t msm = blockIdx.y;
+  if (t >= nthreads) return;
+  partials_chunk(in_ids + msm * in_stride, in_pts + 8 * (msm * in_stride), n_in, T, t, buckets + 8 * (msm * nb),
+                 out_ids + msm * out_stride + 2 * t, out_pts + 8 * (msm * out_stride + 2 * t));
+}
+
+// Tail: once a level fits one CTA (n_in <= 2 * blockDim * T... here n_in <= kTailSlots) all remaining levels run
+// inside ONE launch, ping-ponging between the two slot arrays with a block barrier per level.
+constexpr uint32_t kTailThreads = 256, kTailT = 8, kTailSlots = kTailThreads * kTailT;
+__global__ void __launch_bounds__(kTailThreads) k_msm_acc_partials_tail(uint32_t* ids_a, uint4* pts_a, uint32_t* ids_b,
+                                                                        uint4* pts_b, uint32_t n_in, size_t nb,
+                                                                        uint4* buckets, size_t stride_a, size_t stride_b) {
+  size_t msm = blockIdx.x;
+  uint32_t* ia = ids_a + msm * stride_a; uint4* pa = pts_a + 8 * (msm * stride_a);
+  uint32_t* ib = ids_b + msm * stride_b; uint4* pb = pts_b + 8 * (msm * stride_b);
+  uint4* bk = buckets + 8 * (msm * nb);
+  for (;;) {
+    uint32_t nth = (n_in + kTailT - 1) / kTailT;
+    if (threadIdx.x < nth) partials_chunk(ia, pa, n_in, kTailT, threadIdx.x, bk, ib + 2 * threadIdx.x, pb + 8 * (2 * (size_t)threadIdx.x));
+    if (nth == 1) break;
+    __syncthreads();
+    uint32_t* ti = ia; ia = ib; ib = ti;
+    uint4* tp = pa; pa = pb; pb = tp;
+    n_in = 2 * nth;
+  }
 }
 
 // ---- 4: reduction -------------------------------------------------------------------------------------
@@ -242,23 +405,27 @@ __global__ void __launch_bounds__(128) k_xyzz_segsum(const uint4* in, size_t row
   for (uint32_t i = a; i < b; i++) acc = acc.add(XYZZ::load(in + 8 * (row * len + i)));
   acc.store(out + 8 * tid);
 }
-// final: per MSM, sums[g][k] -> sum_g 2^(c*g) * sum_k 2^k * sums[g][k]; writes a normalised G1
-__global__ void k_msm_final(const uint4* sums, MsmPlan P, uint4* out) {
-  size_t msm = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (msm >= P.count) return;
-  const uint4* s = sums + 8 * (msm * P.G * P.c);
-  XYZZ acc = XYZZ::identity();
-  for (int g = (int)P.G - 1; g >= 0; g--) {
-    if (g != (int)P.G - 1)
-      for (uint32_t i = 0; i < P.c; i++) acc = acc.dbl();
-    XYZZ win = XYZZ::identity();
-    for (int k = (int)P.c - 1; k >= 0; k--) {
-      win = win.dbl();
-      win = win.add(XYZZ::load(s + 8 * ((size_t)g * P.c + k)));
+// final: per MSM the G*c partial sums S_e (weight 2^e, e = g*c + k) are folded by a binary tree,
+// V[2j] += 2^(stride) * V[2j+1], so the serial chain is (items - 1) doublings + log2(items) additions instead
+// of items doublings + items additions; one CTA per MSM, the items live in shared memory.
+constexpr uint32_t kFinalMaxItems = 512;
+__global__ void __launch_bounds__(256) k_msm_final(const uint4* sums, MsmPlan P, uint4* out) {
+  extern __shared__ uint4 fsm[];
+  size_t msm = blockIdx.x;
+  const uint32_t items = P.G * P.c;
+  const uint4* s = sums + 8 * (msm * items);
+  for (uint32_t q = threadIdx.x; q < items * 8; q += blockDim.x) fsm[q] = s[q];
+  __syncthreads();
+  for (uint32_t stride = 1; stride < items; stride <<= 1) {
+    for (uint32_t j = threadIdx.x; (2 * j + 1) * stride < items; j += blockDim.x) {
+      XYZZ hi = XYZZ::load(fsm + 8 * ((2 * j + 1) * stride));
+      for (uint32_t d = 0; d < stride; d++) hi = hi.dbl();
+      XYZZ lo = XYZZ::load(fsm + 8 * (2 * j * stride));
+      lo.add(hi).store(fsm + 8 * (2 * j * stride));
     }
-    acc = acc.add(win);
+    __syncthreads();
   }
-  store_g1_normalised(out + 6 * msm, acc.to_affine());
+  if (threadIdx.x == 0) store_g1_normalised(out + 6 * msm, XYZZ::load(fsm).to_affine());
 }
 
 // ---- window table: table[w][i] = 2^(c*w) * base[i] ------------------------------------------------------
@@ -348,9 +515,11 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   const size_t ent_bytes = P.count * P.ent_per_msm * 4;
   const size_t bucket_bytes = P.count * P.nb * P.S * 128;
   // reduction levels
-  const uint32_t seg = getenv("ZK_MSM_SEG") ? (uint32_t)atoi(getenv("ZK_MSM_SEG")) : 16;
+  // short serial chains: these levels are latency bound, not throughput bound
+  const uint32_t seg1 = getenv("ZK_MSM_SEG") ? (uint32_t)atoi(getenv("ZK_MSM_SEG")) : 8, seg = 4;
   size_t vper = (size_t)P.B * P.S;
-  uint32_t nseg1 = (uint32_t)((vper + seg - 1) / seg);
+  uint32_t nseg1 = (uint32_t)((vper + seg1 - 1) / seg1);
+  if ((size_t)P.G * P.c > kFinalMaxItems) ZK_FAIL(ctx, ZK_ERR_ARG, "msm: %u window sums exceed the final stage", P.G * P.c);
   size_t lvl1 = P.count * P.G * P.c * nseg1;            // points after level 1
   const size_t red_bytes = lvl1 * 128;
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -360,12 +529,28 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   const uint32_t T0 = getenv("ZK_MSM_T0") ? (uint32_t)atoi(getenv("ZK_MSM_T0")) : 64;
   const uint32_t T1 = getenv("ZK_MSM_T1") ? (uint32_t)atoi(getenv("ZK_MSM_T1")) : 8;   // short serial chains: these levels are latency bound
   const uint32_t nth0 = (uint32_t)((P.ent_per_msm + T0 - 1) / T0);
-  const uint32_t nth1 = (2 * nth0 + T1 - 1) / T1;
+  const uint32_t Tmin = T1 < kTailT ? T1 : kTailT;
+  const uint32_t nth1 = (2 * nth0 + Tmin - 1) / Tmin;
   const size_t slotA = (size_t)2 * nth0, slotB = (size_t)2 * nth1 + 2;
   size_t off_sa_id = off_r2 + align(red_bytes / seg + 128 * P.count * P.G * P.c);
   size_t off_sa_pt = off_sa_id + align(P.count * slotA * 4), off_sb_id = off_sa_pt + align(P.count * slotA * 128);
   size_t off_sb_pt = off_sb_id + align(P.count * slotB * 4);
-  size_t total = off_sb_pt + align(P.count * slotB * 128);
+  // batched-affine pairing round (used for batches: the shared inversion needs >= ~16K additions per CTA)
+  const bool use_ba = getenv("ZK_MSM_BA") ? atoi(getenv("ZK_MSM_BA")) != 0 : (P.count * P.ent_per_msm >= ((size_t)1 << 24));
+  const size_t out_cap = (P.ent_per_msm + P.nb) / 2 + 1;
+  uint32_t baM = 8;
+  {
+    size_t want_ctas = (size_t)ctx->sm_count * 3;
+    while (baM < 128 && P.count * out_cap / ((size_t)kPairThreads * baM) > want_ctas) baM <<= 1;
+    if (getenv("ZK_MSM_BA_M")) baM = (uint32_t)atoi(getenv("ZK_MSM_BA_M"));
+  }
+  const unsigned ba_grid = zk_div_up(out_cap, (size_t)kPairThreads * baM);
+  const size_t ba_threads = (size_t)ba_grid * kPairThreads;
+  size_t off_ba_cnt = off_sb_pt + align(P.count * slotB * 128);
+  size_t off_ba_st = off_ba_cnt + align(use_ba ? cnt_bytes : 0);
+  size_t off_ba_pts = off_ba_st + align(use_ba ? st_bytes : 0);
+  size_t off_ba_scr = off_ba_pts + align(use_ba ? P.count * out_cap * 64 : 0);
+  size_t total = off_ba_scr + align(use_ba ? P.count * baM * ba_threads * 32 : 0);
   ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_work, total));
   char* w = (char*)ctx->msm_work.p;
   uint32_t* counts = (uint32_t*)(w + off_cnt);
@@ -385,23 +570,39 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
     uint32_t* ida = (uint32_t*)(w + off_sa_id); uint4* pta = (uint4*)(w + off_sa_pt);
     uint32_t* idb = (uint32_t*)(w + off_sb_id); uint4* ptb = (uint4*)(w + off_sb_pt);
     dim3 ga(zk_div_up(nth0, 128), (unsigned)P.count);
-    ZK_LAUNCH(ctx, "msm_accumulate", k_msm_accumulate, ga, 128, 0, (const uint4*)d_points, (const uint32_t*)entries,
-              (const uint32_t*)starts, P, T0, nth0, buckets, ida, pta);
+    if (use_ba) {
+      uint32_t* ocnt = (uint32_t*)(w + off_ba_cnt); uint32_t* ost = (uint32_t*)(w + off_ba_st);
+      uint4* opts = (uint4*)(w + off_ba_pts); uint4* scr = (uint4*)(w + off_ba_scr);
+      dim3 gc(zk_div_up(P.nb, 256), (unsigned)P.count);
+      ZK_LAUNCH(ctx, "msm_pair_counts", k_pair_counts, gc, 256, 0, (const uint32_t*)starts, P.nb, ocnt);
+      ZK_LAUNCH(ctx, "msm_scan", k_msm_scan, (unsigned)P.count, 1024, 0, ocnt, ost, P.nb);
+      dim3 gb(ba_grid, (unsigned)P.count);
+      ZK_LAUNCH(ctx, "msm_pair_add", k_pair_add, gb, kPairThreads, 0, (const uint4*)d_points, (const uint32_t*)entries,
+                (const uint32_t*)starts, (const uint32_t*)ost, P, baM, out_cap, opts, scr);
+      ZK_LAUNCH(ctx, "msm_accumulate", k_msm_accumulate<true>, ga, 128, 0, (const uint4*)opts, out_cap, (const uint32_t*)nullptr,
+                (const uint32_t*)ost, P, T0, nth0, buckets, ida, pta);
+    } else {
+      ZK_LAUNCH(ctx, "msm_accumulate", k_msm_accumulate<false>, ga, 128, 0, (const uint4*)d_points, (size_t)0,
+                (const uint32_t*)entries, (const uint32_t*)starts, P, T0, nth0, buckets, ida, pta);
+    }
     uint32_t n_in = 2 * nth0;
-    for (;;) {
+    size_t stride_in = slotA, stride_out = slotB;
+    while (n_in > kTailSlots) {
       uint32_t nth = (n_in + T1 - 1) / T1;
       dim3 gp(zk_div_up(nth, 128), (unsigned)P.count);
       ZK_LAUNCH(ctx, "msm_acc_partials", k_msm_acc_partials, gp, 128, 0, (const uint32_t*)ida, (const uint4*)pta, n_in, T1,
-                nth, P.nb, buckets, idb, ptb);
-      if (nth == 1) break;     // one thread saw every slot: nothing is left open
+                nth, P.nb, buckets, idb, ptb, stride_in, stride_out);
       uint32_t* ti = ida; ida = idb; idb = ti;
       uint4* tp = pta; pta = ptb; ptb = tp;
+      size_t ts = stride_in; stride_in = stride_out; stride_out = ts;
       n_in = 2 * nth;
     }
+    ZK_LAUNCH(ctx, "msm_acc_partials", k_msm_acc_partials_tail, (unsigned)P.count, kTailThreads, 0, ida, pta, idb, ptb, n_in,
+              P.nb, buckets, stride_in, stride_out);
   }
   size_t rows = P.count * P.G * P.c;
   dim3 gr(zk_div_up((size_t)P.G * P.c * nseg1, 128), (unsigned)P.count);
-  ZK_LAUNCH(ctx, "msm_reduce_bits", k_msm_reduce_bits, gr, 128, 0, (const uint4*)buckets, P, seg, nseg1, r1);
+  ZK_LAUNCH(ctx, "msm_reduce_bits", k_msm_reduce_bits, gr, 128, 0, (const uint4*)buckets, P, seg1, nseg1, r1);
   uint32_t len = nseg1;
   uint4 *src = r1, *dst = r2;
   while (len > 1) {
@@ -410,7 +611,11 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
     uint4* t = src; src = dst; dst = t;
     len = nseg;
   }
-  ZK_LAUNCH(ctx, "msm_final", k_msm_final, zk_div_up(P.count, 32), 32, 0, (const uint4*)src, P, (uint4*)d_out);
+  {
+    size_t fsmem = (size_t)P.G * P.c * 128;
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFinalMaxItems * 128)));
+    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)src, P, (uint4*)d_out);
+  }
   return ZK_OK;
 }
 
