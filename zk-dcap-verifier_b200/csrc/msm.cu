@@ -187,27 +187,54 @@ __global__ void k_pair_counts(const uint32_t* starts, size_t nb, uint32_t* out_c
 }
 
 struct PairCase { Affine p, q; Fq d; int kind; };   // kind: 0 add, 1 double, 2 result = p, 3 result = q, 4 identity
+// Table points and round outputs are stored canonically, so equality / identity are raw limb compares.
+__device__ __forceinline__ bool raw_eq(const Fq& a, const Fq& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.l[i] ^ b.l[i];
+  return o == 0;
+}
+__device__ __forceinline__ Fq load_y_signed(const uint4* points, uint32_t e) {
+  Fq y = Fq::load(points + 4 * (size_t)(e & 0x7fffffffu) + 2);
+  if (e >> 31) y = y.neg().reduce();
+  return y;
+}
+// Phase 1 needs only the denominator: read the two x coordinates (32 B each); y is touched only when the x's
+// coincide or one of them is zero (doubling / cancellation / identity), which is rare.
+__device__ __forceinline__ Fq pair_denominator(const uint4* points, const uint32_t* ent, uint32_t q0, bool has_q) {
+  if (!has_q) return Fq::one();
+  uint32_t e0 = ent[q0], e1 = ent[q0 + 1];
+  Fq xp = Fq::load(points + 4 * (size_t)(e0 & 0x7fffffffu)), xq = Fq::load(points + 4 * (size_t)(e1 & 0x7fffffffu));
+  bool same = raw_eq(xp, xq);
+  if (!same && !xp.is_zero_raw() && !xq.is_zero_raw()) return xq - xp;
+  Fq yp = load_y_signed(points, e0), yq = load_y_signed(points, e1);
+  if ((xp.is_zero_raw() && yp.is_zero_raw()) || (xq.is_zero_raw() && yq.is_zero_raw())) return Fq::one();   // identity operand
+  if (!same) return xq - xp;
+  if (raw_eq(yp, yq)) return yp.dbl();          // doubling
+  return Fq::one();                             // P = -Q
+}
 __device__ __forceinline__ PairCase pair_load(const uint4* points, const uint32_t* ent, uint32_t q0, bool has_q) {
   PairCase c;
   uint32_t e0 = ent[q0];
-  c.p = Affine::load(points + 4 * (size_t)(e0 & 0x7fffffffu)).cneg((e0 >> 31) != 0);
+  c.p = Affine::load(points + 4 * (size_t)(e0 & 0x7fffffffu));
+  if (e0 >> 31) c.p.y = c.p.y.neg().reduce();
   c.d = Fq::one();
   if (!has_q) { c.kind = 2; c.q = c.p; return c; }
   uint32_t e1 = ent[q0 + 1];
-  c.q = Affine::load(points + 4 * (size_t)(e1 & 0x7fffffffu)).cneg((e1 >> 31) != 0);
-  if (c.q.is_identity()) { c.kind = 2; return c; }
-  if (c.p.is_identity()) { c.kind = 3; return c; }
-  Fq dx = c.q.x - c.p.x;
-  if (dx.is_zero()) {
-    if ((c.q.y - c.p.y).is_zero()) { c.kind = 1; c.d = c.p.y.dbl(); } else { c.kind = 4; }
+  c.q = Affine::load(points + 4 * (size_t)(e1 & 0x7fffffffu));
+  if (e1 >> 31) c.q.y = c.q.y.neg().reduce();
+  if (c.q.x.is_zero_raw() && c.q.y.is_zero_raw()) { c.kind = 2; return c; }
+  if (c.p.x.is_zero_raw() && c.p.y.is_zero_raw()) { c.kind = 3; return c; }
+  if (raw_eq(c.p.x, c.q.x)) {
+    if (raw_eq(c.p.y, c.q.y)) { c.kind = 1; c.d = c.p.y.dbl(); } else { c.kind = 4; }
     return c;
   }
-  c.kind = 0; c.d = dx;
+  c.kind = 0; c.d = c.q.x - c.p.x;
   return c;
 }
 
 constexpr uint32_t kPairThreads = 256;
-__global__ void __launch_bounds__(kPairThreads) k_pair_add(const uint4* points, const uint32_t* entries,
+__global__ void __launch_bounds__(kPairThreads, 3) k_pair_add(const uint4* points, const uint32_t* entries,
                                                            const uint32_t* starts, const uint32_t* out_starts,
                                                            MsmPlan P, uint32_t M, size_t out_cap, uint4* out_pts,
                                                            uint4* scratch) {
@@ -239,9 +266,9 @@ __global__ void __launch_bounds__(kPairThreads) k_pair_add(const uint4* points, 
     for (uint32_t o = (uint32_t)o0, i = 0; o < o1 && o0 < out_total; o++, i++) {
       while (o >= ost[b + 1]) b++;
       uint32_t j = o - ost[b], q0 = st[b] + 2 * j;
-      PairCase c = pair_load(points, ent, q0, q0 + 1 < st[b + 1]);
+      Fq d = pair_denominator(points, ent, q0, q0 + 1 < st[b + 1]);
       acc.store_raw(scr + 2 * ((size_t)i * gthreads + g));
-      acc = acc * c.d;
+      acc = acc * d;
     }
   }
   // ---- phase 2: CTA-wide product scans and one inversion -------------------------------------------------
@@ -535,8 +562,11 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   size_t off_sa_id = off_r2 + align(red_bytes / seg + 128 * P.count * P.G * P.c);
   size_t off_sa_pt = off_sa_id + align(P.count * slotA * 4), off_sb_id = off_sa_pt + align(P.count * slotA * 128);
   size_t off_sb_pt = off_sb_id + align(P.count * slotB * 4);
-  // batched-affine pairing round (used for batches: the shared inversion needs >= ~16K additions per CTA)
-  const bool use_ba = getenv("ZK_MSM_BA") ? atoi(getenv("ZK_MSM_BA")) != 0 : (P.count * P.ent_per_msm >= ((size_t)1 << 24));
+  // Batched-affine pairing round: opt-in (ZK_MSM_BA=1).  Measured on B200 (k = 19, batch of 28, profiles/
+  // r1_pair_add.txt): 0.64 ms for the round + 0.63 ms XYZZ on the halved list = 1.27 ms, against 1.26 ms for XYZZ alone.
+  // The round saves 3.5 of 10 multiplications per addition but moves ~320 B of mostly randomly gathered DRAM
+  // traffic per addition (two passes around the shared inversion), which is what bounds it.
+  const bool use_ba = getenv("ZK_MSM_BA") ? atoi(getenv("ZK_MSM_BA")) != 0 : false;
   const size_t out_cap = (P.ent_per_msm + P.nb) / 2 + 1;
   uint32_t baM = 8;
   {
