@@ -30,6 +30,8 @@ struct zk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;   // H2D staging that overlaps compute inside one host-pointer call
+  cudaEvent_t copy_event = nullptr;
   int sm_count = 148;
   std::string err;
   uint64_t launches = 0;
@@ -112,6 +114,13 @@ static inline void zk_timing_end(zk_ctx* ctx) {
     if (_le != cudaSuccess)                                                          \
       ZK_FAIL(ctx, ZK_ERR_CUDA, "%s:%d: launch %s: %s", __FILE__, __LINE__, name, cudaGetErrorString(_le)); \
   } while (0)
+
+static inline int zk_copy_stream(zk_ctx* ctx) {
+  if (ctx->copy_stream) return ZK_OK;
+  ZK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  ZK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+  return ZK_OK;
+}
 
 static inline unsigned zk_div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

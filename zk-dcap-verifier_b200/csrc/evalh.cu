@@ -254,14 +254,17 @@ extern "C" int zk_evaluate_h(zk_pk* pk, const zk_fr* const* advice, const zk_fr*
   for (uint32_t i = 0; i < D.n_instance; i++) src.push_back(instance[i]);
   for (uint32_t i = 0; i < P.n_sets; i++) src.push_back(perm_product[i]);
   for (uint32_t i = 0; i < 3 * P.n_lookups; i++) src.push_back(lookup[i]);
+  // upload polynomial i+1 on the copy stream while polynomial i is being extended on the compute stream
   char* stage = (char*)pk->d_stage;
+  char* wit = (char*)pk->d_witness;
+  ZK_TRY(zk_copy_stream(ctx));
   for (size_t i = 0; i < src.size(); i++) {
     if (!src[i]) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_evaluate_h: null polynomial pointer");
-    ZK_CUDA(ctx, cudaMemcpyAsync(stage + i * n * 32, src[i], n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(stage + i * n * 32, src[i], n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    ZK_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->copy_stream));
+    ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_event, 0));
+    ZK_TRY(zk_coeff_to_extended_dev(pk->dom, (const zk_fr*)(stage + i * n * 32), (zk_fr*)(wit + i * E * 32), 1));
   }
-  // the staged polynomials are contiguous: one batched transform
-  if (!src.empty())
-    ZK_TRY(zk_coeff_to_extended_dev(pk->dom, (const zk_fr*)stage, (zk_fr*)pk->d_witness, src.size()));
   ZK_TRY(zk_scratch_reserve(ctx, ctx->misc, E * 32));
   ZK_TRY(launch_evalh(pk, challenges, y, beta, gamma, theta, (zk_fr*)ctx->misc.p));
   ZK_CUDA(ctx, cudaMemcpyAsync(out_ext, ctx->misc.p, E * 32, cudaMemcpyDeviceToHost, ctx->stream));

@@ -45,10 +45,11 @@ struct MsmPlan {
 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint4* scalars, MsmPlan P, uint32_t* counts,
-                                                   const uint32_t* starts, uint32_t* entries) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+                                                   const uint32_t* starts, uint32_t* entries, size_t i_begin,
+                                                   size_t i_end) {
+  size_t i = i_begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t msm = blockIdx.y;
-  if (i >= P.n) return;
+  if (i >= i_end) return;
   Fr s = Fr::load(scalars + 2 * (msm * P.n + i)).from_mont();
   uint32_t* cnt = counts + msm * P.nb;
   int carry = 0;
@@ -524,7 +525,10 @@ uint32_t table_window_bits(uint32_t k) {
 }
 
 // Runs the whole pipeline for `count` MSMs over the same point array.
-int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmPlan& P, void* d_out) {
+// `host_scalars` != nullptr: the scalars of a single MSM still live in host memory; they are uploaded into
+// d_scalars in chunks on the copy stream while the histogram of the previous chunk runs.
+int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmPlan& P, void* d_out,
+            const void* host_scalars = nullptr) {
   if (P.n == 0) {
     // empty sum = identity
     std::vector<zk_g1> ids(P.count);
@@ -592,9 +596,28 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
 
   ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, cnt_bytes, ctx->stream));
   dim3 gd(zk_div_up(P.n, 256), (unsigned)P.count);
-  ZK_LAUNCH(ctx, "msm_digits_hist", k_msm_digits<false>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)nullptr, (uint32_t*)nullptr);
+  if (host_scalars && P.count == 1 && P.n >= 4096) {
+    ZK_TRY(zk_copy_stream(ctx));
+    const size_t chunks = 4, per = (P.n + chunks - 1) / chunks;
+    for (size_t c = 0; c < chunks; c++) {
+      size_t lo = c * per, hi = lo + per < P.n ? lo + per : P.n;
+      if (lo >= hi) break;
+      ZK_CUDA(ctx, cudaMemcpyAsync((char*)d_scalars + lo * 32, (const char*)host_scalars + lo * 32, (hi - lo) * 32,
+                                   cudaMemcpyHostToDevice, ctx->copy_stream));
+      ZK_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->copy_stream));
+      ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_event, 0));
+      ZK_LAUNCH(ctx, "msm_digits_hist", k_msm_digits<false>, zk_div_up(hi - lo, 256), 256, 0, (const uint4*)d_scalars, P, counts,
+                (const uint32_t*)nullptr, (uint32_t*)nullptr, lo, hi);
+    }
+  } else {
+    if (host_scalars)
+      ZK_CUDA(ctx, cudaMemcpyAsync((void*)d_scalars, host_scalars, P.count * P.n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_LAUNCH(ctx, "msm_digits_hist", k_msm_digits<false>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)nullptr,
+              (uint32_t*)nullptr, (size_t)0, P.n);
+  }
   ZK_LAUNCH(ctx, "msm_scan", k_msm_scan, (unsigned)P.count, 1024, 0, counts, starts, P.nb);
-  ZK_LAUNCH(ctx, "msm_digits_scatter", k_msm_digits<true>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)starts, entries);
+  ZK_LAUNCH(ctx, "msm_digits_scatter", k_msm_digits<true>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)starts, entries,
+            (size_t)0, P.n);
   ZK_CUDA(ctx, cudaMemsetAsync(buckets, 0, bucket_bytes, ctx->stream));     // identity everywhere
   {
     uint32_t* ida = (uint32_t*)(w + off_sa_id); uint4* pta = (uint4*)(w + off_sa_pt);
@@ -738,14 +761,20 @@ extern "C" int zk_msm(zk_ctx* ctx, const zk_fr* scalars, const zk_g1_affine* bas
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
   ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_scalars, n * 32 + 32));
   ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_out, sizeof(zk_g1)));
-  ZK_CUDA(ctx, cudaMemcpyAsync(ctx->msm_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  const zk_g1_affine* d_bases = nullptr;
   if (which == ZK_BASES_HOST) {
+    ZK_CUDA(ctx, cudaMemcpyAsync(ctx->msm_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_bases, n * 64 + 64));
     ZK_CUDA(ctx, cudaMemcpyAsync(ctx->msm_bases.p, bases, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-    d_bases = (const zk_g1_affine*)ctx->msm_bases.p;
+    ZK_TRY(zk_msm_dev(ctx, (const zk_fr*)ctx->msm_scalars.p, (const zk_g1_affine*)ctx->msm_bases.p, which, n, (zk_g1*)ctx->msm_out.p));
+  } else {
+    if (which != ZK_BASES_G && which != ZK_BASES_G_LAGRANGE) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_msm: bad base selector");
+    zk_srs_set& s = which == ZK_BASES_G ? ctx->srs_g : ctx->srs_lagrange;
+    if (!s.bases) ZK_FAIL(ctx, ZK_ERR_STATE, "msm: no SRS uploaded (zk_srs_upload)");
+    if (n > ctx->srs_n) ZK_FAIL(ctx, ZK_ERR_ARG, "msm: n = %zu exceeds the SRS size %zu", n, ctx->srs_n);
+    bool table = s.table != nullptr;
+    MsmPlan P = make_plan(n, 1, table, (uint32_t)s.table_c, ctx->srs_n, ctx->sm_count);
+    ZK_TRY(run_msm(ctx, ctx->msm_scalars.p, table ? s.table : s.bases, P, ctx->msm_out.p, scalars));
   }
-  ZK_TRY(zk_msm_dev(ctx, (const zk_fr*)ctx->msm_scalars.p, d_bases, which, n, (zk_g1*)ctx->msm_out.p));
   ZK_CUDA(ctx, cudaMemcpyAsync(out, ctx->msm_out.p, sizeof(zk_g1), cudaMemcpyDeviceToHost, ctx->stream));
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ZK_OK;
