@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--k", type=int, default=19, help="log2 rows (19 = full-chain shape, 17 = QE3 shape)")
     ap.add_argument("--mode", default="proof", choices=["proof", "msm-sharded", "sweep"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--streams", type=int, default=3, help="1 = one stream, 3 = commitments on two streams + NTT/h(X) on a third")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-max", type=int, default=24)
     return ap.parse_args()
@@ -134,12 +135,24 @@ def rand_fr_host(rng, n):
 class Workload:
     """Everything one step needs, resident on one GPU."""
 
-    def __init__(self, zk, shapes, torch, device, k, seed, with_host=False):
+    def __init__(self, zk, shapes, torch, device, k, seed, with_host=False, streams=3):
         self.zk, self.torch, self.k, self.n = zk, torch, k, 1 << k
         self.h2 = __import__("importlib").import_module("zk-dcap-verifier_b200.halo2")
         dev = torch.device("cuda", device)
         self.dev = dev
         self.ctx = zk.Context(device, work_stream(torch, dev))
+        # Independent parts of a proof run on separate streams (one zk_ctx each): the latency- and atomic-bound
+        # stages of one MSM batch (digit sort, partial levels, bucket reduction) overlap the integer-pipe-bound
+        # stages of another, and the NTT / h(X) chain overlaps the commitments.  streams=1 serialises everything.
+        self.multi = streams > 1
+        self.sA = torch.cuda.current_stream(dev)
+        if self.multi:
+            self.sB, self.sC = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self.ctxB = zk.Context(device, self.sB.cuda_stream)
+            self.ctxC = zk.Context(device, self.sC.cuda_stream)
+        else:
+            self.ctxB = self.ctxC = self.ctx
+        self.ctxs = [self.ctx, self.ctxB, self.ctxC] if self.multi else [self.ctx]
         self.cs = shapes.full_chain_shape()
         self.counts = shapes.counts(self.cs)
         self.calls = shapes.hot_path_calls(self.cs)
@@ -152,13 +165,18 @@ class Workload:
         self.h2.fixed_base_mul_dev(self.ctx, G, sc.data_ptr(), 2 * n, pts.data_ptr())
         self.h2.srs_upload_dev(self.ctx, k, pts[:n].data_ptr(), pts[n:].data_ptr(), precompute=True)
         self.params = self.h2.ResidentParams(self.ctx, k)
+        torch.cuda.synchronize()
+        if self.multi:
+            self.ctxB.check(self.ctxB.lib.zk_ctx_share_srs(self.ctxB.h, self.ctx.h))
+        self.paramsB = self.h2.ResidentParams(self.ctxB, k)
         del sc, pts
         # proving key side of evaluate_h: random fixed / sigma / l0 / l_last / l_blind polynomials (coefficient form)
         rng = np.random.default_rng(seed)
         fixed = [rand_fr_host(rng, n) for _ in range(c["fixed"])]
         sigma = [rand_fr_host(rng, n) for _ in range(c["perm_columns"])]
         l0, l_last, l_blind = (rand_fr_host(rng, n) for _ in range(3))
-        self.pk = zk.ProvingKey(self.cs, k, fixed, sigma, l0, l_last, l_blind, coeff_form=True, ctx=self.ctx)
+        self.pk = zk.ProvingKey(self.cs, k, fixed, sigma, l0, l_last, l_blind, coeff_form=True, ctx=self.ctxC)
+        torch.cuda.synchronize()
         del fixed, sigma
         self.dom = self.pk.domain
         self.E = self.dom.ext_n
@@ -183,6 +201,8 @@ class Workload:
 
     # ---- one step, operands resident --------------------------------------------------------------------
     def step(self):
+        if self.multi:
+            return self.step_multi()
         h2, c, n = self.h2, self.counts, self.n
         A, Lk, P = c["advice"], c["lookups"], c["perm_sets"]
         w = self.work
@@ -215,6 +235,65 @@ class Workload:
         h2.commit_dev(self.params, self.h_coeff.data_ptr(), pieces, self.commits[ci].data_ptr(), lagrange=False); ci += pieces
         # SHPLONK: two more commitments of degree < n polynomials
         h2.commit_dev(self.params, w[1].data_ptr(), 2, self.commits[ci].data_ptr(), lagrange=False)
+
+    serialize = False
+
+    def _j(self):
+        """breakdown pass: force the three streams to run one call at a time so per-kernel timings do not overlap"""
+        if self.serialize:
+            for s_ in (self.sA, self.sB, self.sC):
+                for t_ in (self.sA, self.sB, self.sC):
+                    if s_ is not t_:
+                        t_.wait_stream(s_)
+
+    def step_multi(self):
+        """Same calls as step(), issued on three streams with events for the true data dependencies."""
+        torch, h2, c, n = self.torch, self.h2, self.counts, self.n
+        A, Lk, P = c["advice"], c["lookups"], c["perm_sets"]
+        sA, sB, sC = self.sA, self.sB, self.sC
+        lag, w = self.lag, self.work
+        sB.wait_stream(sA); sC.wait_stream(sA)
+        # stream C: coefficient forms, evaluate_h, quotient
+        with torch.cuda.stream(sC):
+            w.copy_(lag)
+        h2.lagrange_to_coeff_dev(self.dom, w.data_ptr(), self.n_lag)
+        self._j()
+        ev_coeff = torch.cuda.Event(); ev_coeff.record(sC)
+        # streams A / B: commit_lagrange of the Lagrange columns (read-only), split by group
+        offs, off = [], 0
+        for cnt in (A, 2 * Lk, P, Lk):
+            offs.append((off, cnt)); off += cnt
+        for i, (o, cnt) in enumerate(offs):
+            if cnt:
+                h2.commit_dev(self.params if i % 2 == 0 else self.paramsB, lag[o].data_ptr(), cnt,
+                              self.commits[o].data_ptr(), lagrange=True)
+                self._j()
+        adv = [w[i].data_ptr() for i in range(A)]
+        ins = [self.instance[i].data_ptr() for i in range(c["instance"])]
+        look = []
+        for l in range(Lk):
+            look += [w[A + 2 * Lk + P + l].data_ptr(), w[A + 2 * l].data_ptr(), w[A + 2 * l + 1].data_ptr()]
+        zs = [w[A + 2 * Lk + i].data_ptr() for i in range(P)]
+        ch = self.chal
+        h2.evaluate_h_dev(self.pk, adv, ins, ch[4:4 + self.cs.num_challenges], ch[0], ch[1], ch[2], ch[3], look, zs,
+                          self.h_ext.data_ptr())
+        self._j()
+        h2.divide_by_vanishing_poly_dev(self.dom, self.h_ext.data_ptr())
+        self._j()
+        h2.extended_to_coeff_dev(self.dom, self.h_ext.data_ptr(), self.h_coeff.data_ptr())
+        self._j()
+        ev_h = torch.cuda.Event(); ev_h.record(sC)
+        ci = self.n_lag
+        sA.wait_event(ev_coeff); sB.wait_event(ev_coeff)
+        h2.commit_dev(self.params, w[0].data_ptr(), 1, self.commits[ci].data_ptr(), lagrange=False); ci += 1
+        self._j()
+        pieces = c["degree"] - 1
+        h2.commit_dev(self.paramsB, w[1].data_ptr(), 2, self.commits[ci + pieces].data_ptr(), lagrange=False)
+        self._j()
+        sA.wait_event(ev_h)
+        h2.commit_dev(self.params, self.h_coeff.data_ptr(), pieces, self.commits[ci].data_ptr(), lagrange=False)
+        self._j()
+        sA.wait_stream(sB); sA.wait_stream(sC)
 
     # ---- one step through the host-pointer ABI (the drop-in boundary) ---------------------------------
     def step_e2e(self):
@@ -349,7 +428,8 @@ def main():
     config = {"workload": "full-chain DCAP shape: QE3 column set at k=%d (ext_k=%d), one create_proof hot path per step"
                           % (args.k, args.k + 2),
               "shape": None, "l2": "inputs (>= 1 GiB of witness columns per step) exceed the 126 MB L2",
-              "parallelism": "independent proofs per GPU (replicas)" if args.gpus > 1 else "1 GPU"}
+              "parallelism": "independent proofs per GPU (replicas)" if args.gpus > 1 else "1 GPU",
+              "streams": args.streams}
 
     if args.impl == "reference":
         if rank != 0:
@@ -389,7 +469,7 @@ def main():
     if args.mode == "msm-sharded":
         return msm_sharded(args, zk, torch, dist, dev, rank, local_rank, world)
 
-    wl = Workload(zk, shapes, torch, local_rank, args.k, seed=0xDCA90002 + rank, with_host=(rank == 0 and not args.no_e2e))
+    wl = Workload(zk, shapes, torch, local_rank, args.k, seed=0xDCA90002 + rank, with_host=(rank == 0 and not args.no_e2e), streams=args.streams)
     config["shape"] = wl.counts
     ctx = wl.ctx
     imad_peak = ctx.bench_imad(1, 2000) if rank == 0 else None
@@ -403,8 +483,7 @@ def main():
     for _ in range(args.warmup):
         wl.step()
     barrier()
-    ctx.timing(True); ctx.timing_reset()
-    launches0 = ctx.launch_count()
+    launches0 = sum(cx.launch_count() for cx in wl.ctxs)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -417,9 +496,25 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    kstats = ctx.timing_read()
-    ctx.timing(False)
-    launches = ctx.launch_count() - launches0
+    launches = sum(cx.launch_count() for cx in wl.ctxs) - launches0
+    # per-kernel breakdown: the same steps again with the streams forced to take turns, timed per launch with
+    # CUDA events by the library (overlapping kernels would inflate each other's durations)
+    for cx in wl.ctxs:
+        cx.timing(True); cx.timing_reset()
+    wl.serialize = True
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); s0.record()
+    for _ in range(args.steps):
+        wl.step()
+    s1.record(); barrier()
+    ms_serial = s0.elapsed_time(s1) / args.steps
+    wl.serialize = False
+    kstats = {}
+    for cx in wl.ctxs:
+        for name, (cnt, tot) in cx.timing_read().items():
+            c0, t0 = kstats.get(name, (0, 0.0))
+            kstats[name] = (c0 + cnt, t0 + tot)
+        cx.timing(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -477,7 +572,7 @@ def main():
         ach = bytes_step / launches_per_step / (per_launch_ms * 1e-3) / 1e9
         roof = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "avg_launch_ms": per_launch_ms, "share_of_step": d["ms_per_step"] / ms_per_step,
+                "avg_launch_ms": per_launch_ms, "share_of_step": d["ms_per_step"] / ms_serial,
                 "note": "integer-pipe bound kernel (254-bit modular arithmetic): the binding roofline is `int_pipe`"}
     # integer pipe: field multiplications per second against the measured register-resident peak
     msm_ms = sum(v["ms_per_step"] for kname, v in fam.items() if kname.startswith("msm"))
@@ -503,7 +598,8 @@ def main():
         except Exception as ex:          # the oracle is a checker; its absence must not hide the GPU number
             cpu = {"value": None, "unit": "proofs/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
     line = {"metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_step_one_stream": ms_serial,
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 limbs (254-bit modular)", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "int_pipe": int_pipe,
             "kernels": fam, "cpu_baseline": cpu}

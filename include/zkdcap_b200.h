@@ -108,6 +108,10 @@ int zk_srs_upload_dev(zk_ctx* ctx, uint32_t k, const zk_g1_affine* d_g,
 int zk_g1_fixed_base_mul_dev(zk_ctx* ctx, const zk_g1_affine* base, const zk_fr* d_scalars,
                              size_t n, zk_g1_affine* d_out);
 
+/* Lets `dst` (a second context = a second stream on the same device) commit
+ * against the SRS that `src` keeps resident; `src` must outlive `dst`'s use. */
+int zk_ctx_share_srs(zk_ctx* dst, const zk_ctx* src);
+
 /* ---- best_multiexp ------------------------------------------------------ */
 
 typedef enum { ZK_BASES_HOST = 0, ZK_BASES_G = 1, ZK_BASES_G_LAGRANGE = 2 } zk_bases;

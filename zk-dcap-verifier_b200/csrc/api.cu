@@ -37,12 +37,24 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   free_scratch(ctx->msm_scalars); free_scratch(ctx->msm_bases); free_scratch(ctx->msm_work);
   free_scratch(ctx->msm_out); free_scratch(ctx->ntt_buf); free_scratch(ctx->ntt_buf2); free_scratch(ctx->misc);
-  free_srs(ctx->srs_g); free_srs(ctx->srs_lagrange);
+  if (!ctx->srs_borrowed) { free_srs(ctx->srs_g); free_srs(ctx->srs_lagrange); }
   for (auto& t : ctx->twiddles) cudaFree(t.table);
   if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+// Lets `dst` (another stream on the same device) commit against the SRS that `src` holds resident.
+extern "C" int zk_ctx_share_srs(zk_ctx* dst, const zk_ctx* src) {
+  if (!dst || !src) return ZK_ERR_ARG;
+  if (dst->device != src->device) ZK_FAIL(dst, ZK_ERR_ARG, "zk_ctx_share_srs: contexts are on different devices");
+  if (!src->srs_g.bases) ZK_FAIL(dst, ZK_ERR_STATE, "zk_ctx_share_srs: source context holds no SRS");
+  if (!dst->srs_borrowed) { free_srs(dst->srs_g); free_srs(dst->srs_lagrange); }
+  dst->srs_g = src->srs_g; dst->srs_lagrange = src->srs_lagrange;
+  dst->srs_k = src->srs_k; dst->srs_n = src->srs_n;
+  dst->srs_borrowed = true;
+  return ZK_OK;
 }
 
 extern "C" const char* zk_last_error(const zk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }

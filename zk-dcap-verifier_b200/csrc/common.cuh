@@ -44,6 +44,7 @@ struct zk_ctx {
   uint32_t srs_k = 0;
   size_t srs_n = 0;
   zk_srs_set srs_g, srs_lagrange;
+  bool srs_borrowed = false;    // the base sets belong to another context (zk_ctx_share_srs)
   // grow-only scratch buffers, reused across calls on this context
   zk_scratch msm_scalars, msm_bases, msm_work, msm_out, ntt_buf, ntt_buf2, misc;
   // cached twiddle tables: key = (log_n, first 8 bytes of omega...) -> device table of omega^e, e < n/2

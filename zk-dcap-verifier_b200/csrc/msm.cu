@@ -695,15 +695,15 @@ extern "C" int zk_srs_upload(zk_ctx* ctx, uint32_t k, const zk_g1_affine* g, con
   zk_srs_set* sets[2] = {&ctx->srs_g, &ctx->srs_lagrange};
   const zk_g1_affine* src[2] = {g, g_lagrange};
   for (int i = 0; i < 2; i++) {
-    if (sets[i]->bases) cudaFree(sets[i]->bases);
-    if (sets[i]->table) cudaFree(sets[i]->table);
+    if (!ctx->srs_borrowed && sets[i]->bases) cudaFree(sets[i]->bases);
+    if (!ctx->srs_borrowed && sets[i]->table) cudaFree(sets[i]->table);
     *sets[i] = zk_srs_set();
     ZK_CUDA(ctx, cudaMalloc(&sets[i]->bases, n * 64));
     ZK_CUDA(ctx, cudaMemcpyAsync(sets[i]->bases, src[i], n * 64, cudaMemcpyHostToDevice, ctx->stream));
     if (precompute_windows) ZK_TRY(build_table(ctx, *sets[i], n, k));
   }
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->srs_k = k; ctx->srs_n = n;
+  ctx->srs_k = k; ctx->srs_n = n; ctx->srs_borrowed = false;
   return ZK_OK;
 }
 
@@ -717,15 +717,15 @@ extern "C" int zk_srs_upload_dev(zk_ctx* ctx, uint32_t k, const zk_g1_affine* d_
   zk_srs_set* sets[2] = {&ctx->srs_g, &ctx->srs_lagrange};
   const zk_g1_affine* src[2] = {d_g, d_g_lagrange};
   for (int i = 0; i < 2; i++) {
-    if (sets[i]->bases) cudaFree(sets[i]->bases);
-    if (sets[i]->table) cudaFree(sets[i]->table);
+    if (!ctx->srs_borrowed && sets[i]->bases) cudaFree(sets[i]->bases);
+    if (!ctx->srs_borrowed && sets[i]->table) cudaFree(sets[i]->table);
     *sets[i] = zk_srs_set();
     ZK_CUDA(ctx, cudaMalloc(&sets[i]->bases, n * 64));
     ZK_CUDA(ctx, cudaMemcpyAsync(sets[i]->bases, src[i], n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
     if (precompute_windows) ZK_TRY(build_table(ctx, *sets[i], n, k));
   }
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->srs_k = k; ctx->srs_n = n;
+  ctx->srs_k = k; ctx->srs_n = n; ctx->srs_borrowed = false;
   return ZK_OK;
 }
 
