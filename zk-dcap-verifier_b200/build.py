@@ -11,7 +11,7 @@ SOURCES = ["api.cu", "ntt.cu", "msm.cu", "evalh.cu"]
 HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", "evalh.cuh", "evalh_compile.hpp", os.path.join("..", "..", "include", "zkdcap_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("ZK_NVCC_EXTRA", "").split()
 
 
 def _stale(target, deps):

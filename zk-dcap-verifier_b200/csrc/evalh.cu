@@ -26,8 +26,11 @@ struct zk_pk {
 
 namespace {
 
+#ifndef ZK_EVALH_MIN_CTAS
+#define ZK_EVALH_MIN_CTAS 4
+#endif
 template <int NI>
-__global__ void __launch_bounds__(128) k_evalh(EvalProgram P, EvalScalars S, const uint32_t* code,
+__global__ void __launch_bounds__(128, ZK_EVALH_MIN_CTAS) k_evalh(EvalProgram P, EvalScalars S, const uint32_t* code,
                                                const uint4* const* cols, const uint4* consts,
                                                const uint4* challenges, const uint4* tw, uint4* out) {
   size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

@@ -86,6 +86,19 @@ struct EvalState<4> {
   }
 };
 
+// The evaluator multiplies at ~50 call sites; inlining the 165-instruction multiplier at each of them made the
+// kernel ~130 KB of code and instruction-fetch stalls its top stall reason (ncu: stalled_no_instruction 5.8 per
+// issue).  Field operations are therefore CALLED here, which keeps the whole kernel inside the instruction cache.
+#ifdef __CUDA_ARCH__
+#define ZK_EV_FN __device__ __noinline__
+#else
+#define ZK_EV_FN inline
+#endif
+ZK_EV_FN Fr ev_mul(Fr a, Fr b) { return a * b; }
+ZK_EV_FN Fr ev_add(Fr a, Fr b) { return a + b; }
+ZK_EV_FN Fr ev_sub(Fr a, Fr b) { return a - b; }
+ZK_EV_FN Fr ev_fma(Fr a, Fr b, Fr c) { return a * b + c; }      // a * b + c
+
 ZK_HD uint32_t rot_idx(size_t idx, int32_t rot, uint32_t rot_shift, size_t mask) {
   // (idx + rot * 2^rot_shift) mod 2^ext_k, rot may be negative
   int64_t v = (int64_t)idx + (int64_t)rot * ((int64_t)1 << rot_shift);
@@ -125,24 +138,24 @@ ZK_HD Fr graph_eval(const EvalProgram& P, const EvalGraph& G, const uint32_t* co
     uint32_t w0 = code[pc], target = code[pc + 1], sa = code[pc + 2], sb = code[pc + 3];
     uint32_t op = w0 & 0xFFu, nparts = w0 >> 8;
     pc += 4;
-    Fr a = vs_fetch<NI>(sa, P, G, cols, consts, challenges, S, st, prev), r;
-    switch (op) {
-      case OP_ADD: r = a + vs_fetch<NI>(sb, P, G, cols, consts, challenges, S, st, prev); break;
-      case OP_SUB: r = a - vs_fetch<NI>(sb, P, G, cols, consts, challenges, S, st, prev); break;
-      case OP_MUL: r = a * vs_fetch<NI>(sb, P, G, cols, consts, challenges, S, st, prev); break;
-      case OP_SQUARE: r = a.sqr(); break;
-      case OP_DOUBLE: r = a.dbl(); break;
-      case OP_NEGATE: r = a.neg(); break;
-      case OP_HORNER: {
-        Fr f = vs_fetch<NI>(sb, P, G, cols, consts, challenges, S, st, prev);
-        r = a;
-        for (uint32_t p = 0; p < nparts; p++)
-          r = r * f + vs_fetch<NI>(code[pc + p], P, G, cols, consts, challenges, S, st, prev);
-        pc += nparts;
-        break;
-      }
-      default: r = a; break;
+    // one inline copy of the operand fetch for `a`, one for `b` / the Horner parts (code size matters, see above)
+    Fr a = vs_fetch<NI>(sa, P, G, cols, consts, challenges, S, st, prev), r = a;
+    const bool binary = op <= OP_MUL || op == OP_HORNER;
+    const uint32_t nfetch = op == OP_HORNER ? nparts + 1 : (binary ? 1u : 0u);
+    Fr f = a;
+    for (uint32_t p = 0; p < nfetch; p++) {
+      // p == 0: operand b (the Horner factor); p >= 1: Horner part p-1
+      Fr b = vs_fetch<NI>(p == 0 ? sb : code[pc + p - 1], P, G, cols, consts, challenges, S, st, prev);
+      if (op == OP_HORNER) {
+        if (p == 0) f = b; else r = ev_fma(r, f, b);
+      } else if (op == OP_ADD) r = ev_add(a, b);
+      else if (op == OP_SUB) r = ev_sub(a, b);
+      else r = ev_mul(a, b);
     }
+    if (op == OP_HORNER) pc += nparts;
+    else if (op == OP_SQUARE) r = ev_mul(a, a);
+    else if (op == OP_DOUBLE) r = ev_add(a, a);
+    else if (op == OP_NEGATE) r = ev_sub(Fr::zero(), a);
     st.set(target, r);
   }
   return G.n_calcs ? st.get(G.last_target) : Fr::zero();
@@ -164,14 +177,14 @@ ZK_HD Fr evalh_row(const EvalProgram& P, const uint32_t* code, const uint4* cons
   if (P.n_sets) {
     size_t r_next = rot_idx(idx, 1, rot_shift, mask), r_last = rot_idx(idx, P.last_rotation, rot_shift, mask);
     Fr z0 = Fr::load(cols[P.off_z] + 2 * idx);
-    value = value * S.y + (S.one - z0) * l0;
+    value = ev_fma(value, S.y, ev_mul(ev_sub(S.one, z0), l0));
     Fr zl = Fr::load(cols[P.off_z + P.n_sets - 1] + 2 * idx);
-    value = value * S.y + (zl.sqr() - zl) * l_last;
+    value = ev_fma(value, S.y, ev_mul(ev_sub(ev_mul(zl, zl), zl), l_last));
     for (uint32_t s = 1; s < P.n_sets; s++) {
       Fr zi = Fr::load(cols[P.off_z + s] + 2 * idx), zp = Fr::load(cols[P.off_z + s - 1] + 2 * r_last);
-      value = value * S.y + (zi - zp) * l0;
+      value = ev_fma(value, S.y, ev_mul(ev_sub(zi, zp), l0));
     }
-    Fr current_delta = S.delta_start * beta_term;
+    Fr current_delta = ev_mul(S.delta_start, beta_term);
     for (uint32_t s = 0; s < P.n_sets; s++) {
       uint32_t c0 = s * P.chunk_len, c1 = c0 + P.chunk_len < P.n_perm_cols ? c0 + P.chunk_len : P.n_perm_cols;
       Fr left = Fr::load(cols[P.off_z + s] + 2 * r_next);
@@ -179,11 +192,11 @@ ZK_HD Fr evalh_row(const EvalProgram& P, const uint32_t* code, const uint4* cons
       for (uint32_t c = c0; c < c1; c++) {
         Fr v = Fr::load(cols[code[P.perm_cols_off + c]] + 2 * idx);
         Fr sg = Fr::load(cols[P.off_sigma + c] + 2 * idx);
-        left = left * (v + S.beta * sg + S.gamma);
-        right = right * (v + current_delta + S.gamma);
-        current_delta = current_delta * S.delta;
+        left = ev_mul(left, ev_add(ev_fma(S.beta, sg, v), S.gamma));
+        right = ev_mul(right, ev_add(ev_add(v, current_delta), S.gamma));
+        current_delta = ev_mul(current_delta, S.delta);
       }
-      value = value * S.y + (left - right) * l_active;
+      value = ev_fma(value, S.y, ev_mul(ev_sub(left, right), l_active));
     }
   }
   // lookup arguments
@@ -194,14 +207,15 @@ ZK_HD Fr evalh_row(const EvalProgram& P, const uint32_t* code, const uint4* cons
     const uint4* Ac = cols[P.off_lookup + 3 * l + 1];
     const uint4* Sc = cols[P.off_lookup + 3 * l + 2];
     Fr Z = Fr::load(Zc + 2 * idx), A = Fr::load(Ac + 2 * idx), Sv = Fr::load(Sc + 2 * idx);
-    Fr a_minus_s = A - Sv;
-    value = value * S.y + (S.one - Z) * l0;
-    value = value * S.y + (Z.sqr() - Z) * l_last;
+    Fr a_minus_s = ev_sub(A, Sv);
+    value = ev_fma(value, S.y, ev_mul(ev_sub(S.one, Z), l0));
+    value = ev_fma(value, S.y, ev_mul(ev_sub(ev_mul(Z, Z), Z), l_last));
     Fr Zn = Fr::load(Zc + 2 * r_next);
-    value = value * S.y + (Zn * (A + S.beta) * (Sv + S.gamma) - Z * table_value) * l_active;
-    value = value * S.y + a_minus_s * l0;
+    Fr t1 = ev_mul(ev_mul(Zn, ev_add(A, S.beta)), ev_add(Sv, S.gamma));
+    value = ev_fma(value, S.y, ev_mul(ev_sub(t1, ev_mul(Z, table_value)), l_active));
+    value = ev_fma(value, S.y, ev_mul(a_minus_s, l0));
     Fr Ap = Fr::load(Ac + 2 * r_prev);
-    value = value * S.y + a_minus_s * (A - Ap) * l_active;
+    value = ev_fma(value, S.y, ev_mul(ev_mul(a_minus_s, ev_sub(A, Ap)), l_active));
   }
   return value;
 }

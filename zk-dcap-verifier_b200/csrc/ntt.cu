@@ -69,7 +69,10 @@ __device__ __forceinline__ void sts_fr(uint4* p0, uint4* p1, uint32_t e, const F
   p1[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-__global__ void __launch_bounds__(kThreads) k_ntt_pass(PassArgs A, PassConsts K) {
+#ifndef ZK_NTT_MIN_CTAS
+#define ZK_NTT_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kThreads, ZK_NTT_MIN_CTAS) k_ntt_pass(PassArgs A, PassConsts K) {
   extern __shared__ uint4 smem[];
   const uint32_t t = A.t, logC = A.logC, C = 1u << logC, L = A.L, P = A.s0;
   const uint32_t rows = 1u << t, tile = rows << logC;
