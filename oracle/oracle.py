@@ -17,7 +17,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libzkoracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("zk_oracle.c", "field_tmpl.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("zk_oracle.c", "field_tmpl.h", "prover_tail.inc.h")]
     stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "libzkoracle.so"], stdout=subprocess.DEVNULL)
@@ -248,4 +248,75 @@ def evaluate_h(desc_struct, fixed_cosets, perm_cosets, l0, l_last, l_active,
                          tf, tp, _p(_u64(l0)), _p(_u64(l_last)), _p(_u64(l_active)),
                          ta, ti, _p(ch), _p(_u64(y)), _p(_u64(beta)), _p(_u64(gamma)), _p(_u64(theta)),
                          tl, tz, _p(out))
+    return out
+
+
+# ---- prover tail (oracle/prover_tail.inc.h) ---------------------------------------------------------
+def _table(arrs):
+    arrs = [_u64(a) for a in arrs]
+    t = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+    return t, arrs
+
+
+def eval_graph_rows(graph_struct, k, fixed, advice, instance, challenges, theta, threads=None):
+    """graph (ctypes zk_graph, plain data) evaluated on the n Lagrange rows, rot_scale = 1."""
+    tf, kf = _table(fixed)
+    ta, ka = _table(advice)
+    ti, ki = _table(instance)
+    ch = _u64(challenges) if len(challenges) else np.zeros((1, 4), dtype=np.uint64)
+    out = np.empty((1 << k, 4), dtype=np.uint64)
+    lib().orc_eval_graph_rows(C.byref(graph_struct), C.c_int(threads or cpu_threads()), C.c_uint32(k), tf, ta, ti,
+                              _p(ch), _p(_u64(theta)), _p(out))
+    return out
+
+
+def permute_expression_pair(inp, tab, usable):
+    inp, tab = _u64(inp), _u64(tab)
+    a = np.empty((usable, 4), dtype=np.uint64)
+    s = np.empty((usable, 4), dtype=np.uint64)
+    rc = lib().orc_permute_expression_pair(_p(inp), _p(tab), C.c_size_t(usable), _p(a), _p(s))
+    if rc != 0:
+        raise ValueError("ConstraintSystemFailure: lookup input not in table")
+    return a, s
+
+
+def permutation_product(k, values, sigma, beta, gamma, omega, deltaomega0, last_z, threads=None):
+    tv, kv = _table(values)
+    ts, ks = _table(sigma)
+    out = np.empty((1 << k, 4), dtype=np.uint64)
+    lib().orc_permutation_product(C.c_uint32(k), C.c_int(threads or cpu_threads()), C.c_uint32(len(values)), tv, ts,
+                                  _p(_u64(beta)), _p(_u64(gamma)), _p(_u64(omega)), _p(_u64(deltaomega0)),
+                                  _p(_u64(last_z)), _p(out))
+    return out
+
+
+def lookup_product(k, cin, ctab, pin, ptab, beta, gamma):
+    out = np.empty((1 << k, 4), dtype=np.uint64)
+    lib().orc_lookup_product(C.c_uint32(k), _p(_u64(cin)), _p(_u64(ctab)), _p(_u64(pin)), _p(_u64(ptab)),
+                             _p(_u64(beta)), _p(_u64(gamma)), _p(out))
+    return out
+
+
+def kate_division(a, z):
+    a = _u64(a).reshape(-1, 4)
+    out = np.empty((a.shape[0] - 1, 4), dtype=np.uint64)
+    lib().orc_kate_division(_p(a), C.c_size_t(a.shape[0]), _p(_u64(z)), _p(out))
+    return out
+
+
+def poly_lincomb(polys, scalars, threads=None):
+    tp, kp = _table(polys)
+    n = kp[0].size // 4
+    sc = _u64(np.stack([_u64(s) for s in scalars]))
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib().orc_poly_lincomb(C.c_size_t(n), C.c_int(threads or cpu_threads()), C.c_size_t(len(polys)), tp, _p(sc), _p(out))
+    return out
+
+
+def permutation_sigma(k, mapping, omega):
+    """mapping: (ncols, n, 2) uint32 of (column', row') -> (ncols, n, 4) sigma values in Lagrange form"""
+    mapping = np.ascontiguousarray(mapping, dtype=np.uint32)
+    ncols = mapping.shape[0]
+    out = np.empty((ncols, 1 << k, 4), dtype=np.uint64)
+    lib().orc_permutation_sigma(C.c_uint32(k), C.c_uint32(ncols), _p(mapping), _p(_u64(omega)), _p(out))
     return out

@@ -770,3 +770,6 @@ void orc_gen_points(u64 seed, size_t n, int threads, zk_g1_affine* out) {
   genp_job j = {seed, out};
   parallel_for(n, threads, genp_fn, &j);
 }
+
+/* prover tail: lookup / permutation products, kate division (test infrastructure) */
+#include "prover_tail.inc.h"

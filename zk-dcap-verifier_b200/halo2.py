@@ -298,6 +298,9 @@ class ConstraintSystem:
         self.permutation_columns = []   # list of (column_type, index); _abi.COL_*
         self.minimum_degree = None
         self.num_advice_queries = [0] * num_advice
+        # cs.{advice,fixed,instance}_queries: (column index, rotation) in first-query order.  They fix the order of
+        # the evaluations in the proof (plonk/prover.rs) and, through num_advice_queries, blinding_factors().
+        self.advice_queries, self.fixed_queries, self.instance_queries = [], [], []
 
     def create_gate(self, polys):
         for p in polys:
@@ -310,23 +313,25 @@ class ConstraintSystem:
             self._count_queries(e)
 
     def enable_equality(self, column_type, index):
+        # ConstraintSystem::enable_equality: query_any_index(column, Rotation::cur()) + permutation.add_column
+        self._query({_abi.COL_ADVICE: "Advice", _abi.COL_FIXED: "Fixed", _abi.COL_INSTANCE: "Instance"}[column_type], index, 0)
         if (column_type, index) not in self.permutation_columns:
             self.permutation_columns.append((column_type, index))
 
-    def _count_queries(self, e, seen=None):
-        # num_advice_queries counts DISTINCT (column, rotation) queries per advice column
-        if not hasattr(self, "_advice_q"):
-            self._advice_q = set()
-        stack = [e]
-        while stack:
-            x = stack.pop()
-            if x.tag == "Advice":
-                if (x.args[0], x.args[1]) not in self._advice_q:
-                    self._advice_q.add((x.args[0], x.args[1]))
-                    self.num_advice_queries[x.args[0]] += 1
-            for a in x.args:
-                if isinstance(a, Expression):
-                    stack.append(a)
+    def _query(self, tag, column, rotation):
+        lst = {"Advice": self.advice_queries, "Fixed": self.fixed_queries, "Instance": self.instance_queries}[tag]
+        if (column, rotation) not in lst:
+            lst.append((column, rotation))
+            if tag == "Advice":
+                self.num_advice_queries[column] += 1
+
+    def _count_queries(self, e):
+        # left-to-right walk of the expression: the order in which the closure would have called meta.query_*
+        if e.tag in ("Advice", "Fixed", "Instance"):
+            self._query(e.tag, e.args[0], e.args[1])
+        for a in e.args:
+            if isinstance(a, Expression):
+                self._count_queries(a)
 
     def degree(self):
         degree = 3                                          # permutation::Argument::required_degree()
@@ -504,6 +509,45 @@ class Evaluator:
         d.perm_columns, d.n_perm_columns = C.cast(pc, C.POINTER(_abi.zk_column)), len(cs.permutation_columns)
         keep += [lk, pc]
         return d, keep
+
+
+class Circuit:
+    """What keygen / create_proof need to know about one circuit: the ConstraintSystem, k, the Evaluator image
+    (zk_evaluator_desc) and, per lookup argument, the graphs of the theta-compressed input and table expressions
+    that lookup::Argument::commit_permuted evaluates over the n Lagrange rows (plonk/lookup/prover.rs)."""
+
+    def __init__(self, cs, k, transcript_repr=0):
+        self.cs, self.k = cs, k
+        self.transcript_repr = transcript_repr % R_MOD
+        self.ev = Evaluator.new(cs)
+        self.desc, self._keep = self.ev.describe(cs, k)
+        self.lookup_input_graphs, self.lookup_table_graphs = [], []
+        for inputs, tables in cs.lookups:
+            for exprs, dst in ((inputs, self.lookup_input_graphs), (tables, self.lookup_table_graphs)):
+                g = GraphEvaluator()
+                parts = tuple(g.add_expression(e) for e in exprs)
+                g.add_calculation(("Horner", (_abi.VS_CONSTANT, 0, 0), parts, (_abi.VS_THETA, 0, 0)))
+                cg, keep = g.to_c()
+                dst.append(cg)
+                self._keep.append(keep)
+
+    def to_c(self):
+        """-> zk_circuit_desc (ctypes) for zk_keygen"""
+        nl = len(self.cs.lookups)
+        d = _abi.zk_circuit_desc()
+        d.ev = self.desc
+        li = (_abi.zk_graph * max(1, nl))(*self.lookup_input_graphs)
+        lt = (_abi.zk_graph * max(1, nl))(*self.lookup_table_graphs)
+        aq = (_abi.zk_query * max(1, len(self.cs.advice_queries)))(*[_abi.zk_query(c, r) for c, r in self.cs.advice_queries])
+        fq = (_abi.zk_query * max(1, len(self.cs.fixed_queries)))(*[_abi.zk_query(c, r) for c, r in self.cs.fixed_queries])
+        d.lookup_inputs, d.lookup_tables = C.cast(li, C.POINTER(_abi.zk_graph)), C.cast(lt, C.POINTER(_abi.zk_graph))
+        d.advice_queries, d.n_advice_queries = C.cast(aq, C.POINTER(_abi.zk_query)), len(self.cs.advice_queries)
+        d.fixed_queries, d.n_fixed_queries = C.cast(fq, C.POINTER(_abi.zk_query)), len(self.cs.fixed_queries)
+        tr = self.transcript_repr * _MONT_R % R_MOD
+        for i in range(4):
+            d.transcript_repr.l[i] = (tr >> (64 * i)) & 0xFFFFFFFFFFFFFFFF
+        self._keep += [li, lt, aq, fq]
+        return d
 
 
 def _ptr_table(arrs):

@@ -108,3 +108,120 @@ def hot_path_calls(cs):
     A, L, P, I, d = c["advice"], c["lookups"], c["perm_sets"], c["instance"], c["degree"]
     return {"msm_lagrange": A + 3 * L + P, "msm_coeff": 1 + (d - 1) + 2, "intt_n": A + 3 * L + P,
             "coset_ntt_ext": A + I + P + 3 * L, "intt_ext": 1}
+
+
+# ---- synthetic satisfying assignment of the QE3 / full-chain shape ----------------------------------------
+# BASELINE configs 1/2 ask for "synthetic witnesses of the named circuit shapes" (SURVEY.md 8d).  The assignment
+# below satisfies every gate, lookup and copy constraint of qe3_shape(), so the proof it leads to verifies.  It is
+# workload generation, not part of the prover: the field arithmetic it needs (out = a + b*c on the enabled rows) is
+# done by the `fops` object the caller passes (device field ops in bench.py, the oracle's in the tests).
+def _rand_fr(rng, shape_n):
+    import numpy as np
+    v = rng.integers(0, 1 << 63, size=(shape_n, 4), dtype=np.uint64) * np.uint64(2) + \
+        rng.integers(0, 2, size=(shape_n, 4), dtype=np.uint64)
+    v[:, 3] %= np.uint64(0x30644e72e131a029)      # < r: every such limb vector is a valid Montgomery residue
+    return v
+
+
+def synth_qe3_witness(cs, k, seed, fops):
+    """-> (fixed_values [21 x (n,4)], advice_values [28 x (n,4)], mapping (18, n, 2) uint32).
+    fops: object with mul(a, b), add(a, b), to_mont(raw) on (m, 4) uint64 arrays."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    n = 1 << k
+    bf = cs.blinding_factors()
+    usable = n - (bf + 1)
+    BIT0, ENC, DEC, DECNG, FP_GATE, FP_LOOKUP, RG_GATE, RG_LOOKUP, SHA = 0, 12, 13, 14, 15, 19, 20, 23, 24
+    TAB, RT_FP, RT_RG, SPREAD_T, CONST, QSEL, QDEC = 0, 7, 8, 9, 11, 13, 20
+    zero = np.zeros((n, 4), dtype=np.uint64)
+
+    def small(vals):                               # canonical small integers -> Montgomery column
+        raw = np.zeros((n, 4), dtype=np.uint64)
+        raw[:len(vals), 0] = np.asarray(vals, dtype=np.uint64)
+        return fops.to_mont(raw)
+    one = small([1] * n)
+    fixed = [zero.copy() for _ in range(21)]
+    advice = [_rand_fr(rng, n) for _ in range(28)]
+    # lookup tables: the seven bit-table columns all hold t for t < 256 (then the default row 0), see SURVEY 8d
+    tab_rows = min(256, usable)
+    tvals = np.arange(n, dtype=np.uint64)
+    tvals[tab_rows:] = 0
+    tcol = small(tvals)
+    for j in range(7):
+        fixed[TAB + j] = tcol.copy()
+    range_rows = min(1 << max(k - 1, 1), usable)
+    rvals = np.arange(n, dtype=np.uint64)
+    rvals[range_rows:] = 0
+    fixed[RT_FP] = small(rvals)
+    fixed[RT_RG] = fixed[RT_FP].copy()
+    # spread table: dense t, spread(t) = bits of t interleaved with zeros
+    srows = min(1 << min(k - 1, 16), usable)
+    dense = np.arange(n, dtype=np.uint64)
+    dense[srows:] = 0
+    spread = np.zeros(n, dtype=np.uint64)
+    for b in range(20):
+        spread |= ((dense >> np.uint64(b)) & np.uint64(1)) << np.uint64(2 * b)
+    fixed[SPREAD_T], fixed[SPREAD_T + 1] = small(dense), small(spread)
+    fixed[CONST], fixed[CONST + 1] = _rand_fr(rng, n), _rand_fr(rng, n)
+    # complex selector q on ~3/4 of the usable rows; looked-up cells take one table row per witness row
+    qdec = (rng.integers(0, 4, size=n) != 0)
+    qdec[usable:] = False
+    fixed[QDEC][qdec] = one[qdec]
+    trow = rng.integers(0, tab_rows, size=n)
+    for c in list(range(BIT0, BIT0 + 12)) + [ENC, DEC]:
+        advice[c][qdec] = tcol[trow][qdec]
+    advice[FP_LOOKUP][:usable] = fixed[RT_FP][rng.integers(0, range_rows, size=usable)]
+    advice[RG_LOOKUP][:usable] = fixed[RT_RG][rng.integers(0, range_rows, size=usable)]
+    for i in range(2):
+        t = rng.integers(0, srows, size=usable)
+        advice[SHA + 2 * i][:usable] = fixed[SPREAD_T][t]
+        advice[SHA + 2 * i + 1][:usable] = fixed[SPREAD_T + 1][t]
+    # vertical basic gates q * (a + b*c - out) on rows 4g .. 4g+3, wired together by copy constraints
+    pcol = {col: i for i, col in enumerate(cs.permutation_columns)}
+    mapping = np.empty((len(cs.permutation_columns), n, 2), dtype=np.uint32)
+    mapping[:, :, 0] = np.arange(len(cs.permutation_columns), dtype=np.uint32)[:, None]
+    mapping[:, :, 1] = np.arange(n, dtype=np.uint32)[None, :]
+
+    def tie(ca, ra, cb, rb):                        # 2-cycles between distinct cells (vectorised)
+        mapping[ca, ra, 0], mapping[ca, ra, 1] = cb, rb
+        mapping[cb, rb, 0], mapping[cb, rb, 1] = ca, ra
+    groups = usable // 4
+    gate_cols = [(FP_GATE + i, QSEL + i, FP_LOOKUP) for i in range(4)] + [(RG_GATE + i, QSEL + 4 + i, RG_LOOKUP) for i in range(3)]
+    even, odd = np.arange(0, groups, 2), np.arange(1, groups, 2)
+    lk_free = {FP_LOOKUP: rng.permutation(usable), RG_LOOKUP: rng.permutation(usable)}
+    const_free = [rng.permutation(usable), rng.permutation(usable)]
+    used = {FP_LOOKUP: 0, RG_LOOKUP: 0, "c0": 0, "c1": 0}
+    for gi, (col, sel, lcol) in enumerate(gate_cols):
+        fixed[sel][4 * np.arange(groups)] = one[:groups]
+        # b cells of every 4th group come from a constant column, c cells of every 4th group from the lookup column
+        gb = np.arange(1, groups, 4)
+        cc = gi % 2
+        rows_c = const_free[cc][used["c%d" % cc]:used["c%d" % cc] + len(gb)]
+        used["c%d" % cc] += len(gb)
+        advice[col][4 * gb + 1] = fixed[CONST + cc][rows_c]
+        tie(pcol[(_abi.COL_ADVICE, col)], 4 * gb + 1, pcol[(_abi.COL_FIXED, CONST + cc)], rows_c)
+        gc = np.arange(2, groups, 4)
+        rows_l = lk_free[lcol][used[lcol]:used[lcol] + len(gc)]
+        used[lcol] += len(gc)
+        advice[col][4 * gc + 2] = advice[lcol][rows_l]
+        tie(pcol[(_abi.COL_ADVICE, col)], 4 * gc + 2, pcol[(_abi.COL_ADVICE, lcol)], rows_l)
+    # even groups first (free a), then odd groups take a = out of a random even group of the previous gate column
+    for col, _, _ in gate_cols:
+        r = 4 * even
+        advice[col][r + 3] = fops.add(advice[col][r], fops.mul(advice[col][r + 1], advice[col][r + 2]))
+    for gi, (col, _, _) in enumerate(gate_cols):
+        src_col = gate_cols[(gi + 1) % len(gate_cols)][0]
+        src = rng.permutation(even)[:len(odd)]
+        r = 4 * odd[:len(src)]
+        advice[col][r] = advice[src_col][4 * src + 3]
+        tie(pcol[(_abi.COL_ADVICE, col)], r, pcol[(_abi.COL_ADVICE, src_col)], 4 * src + 3)
+        r = 4 * odd
+        advice[col][r + 3] = fops.add(advice[col][r], fops.mul(advice[col][r + 1], advice[col][r + 2]))
+    # DECNG mirrors DEC on a random third of the rows; the SHA dense columns are tied pairwise on a few rows
+    rows = rng.permutation(usable)[:usable // 3]
+    dst = rng.permutation(usable)[:usable // 3]
+    advice[DECNG][dst] = advice[DEC][rows]
+    tie(pcol[(_abi.COL_ADVICE, DECNG)], dst, pcol[(_abi.COL_ADVICE, DEC)], rows)
+    rows = rng.permutation(usable)[:usable // 8]
+    advice[ENC][rows] = advice[ENC][rows]          # ENC stays unconstrained by copies (kept for clarity)
+    return fixed, advice, mapping
