@@ -268,6 +268,57 @@ int zk_evaluate_h_dev(zk_pk* pk,
                       const zk_fr* const* d_lookup_polys, const zk_fr* const* d_perm_product_polys,
                       zk_fr* d_out_ext);
 
+/* ---- keygen_pk / create_proof (plonk/keygen.rs, plonk/prover.rs) -------------- */
+/* the prover's n-sized loops between the MSM / FFT /
+ * evaluate_h calls (lookup compression + permutation, grand products, polynomial
+ * evaluation, SHPLONK quotients) run on the device too, so that one proof needs
+ * one upload of the advice columns and one download of the proof bytes.
+ * Replaces halo2_proofs::plonk::{keygen_vk, keygen_pk, create_proof} as called at
+ * circuits/src/sgx_dcap_verifier.rs:803, :807, :814-822 for
+ * KZGCommitmentScheme<Bn256> + ProverSHPLONK + Blake2bWrite/Challenge255, one
+ * circuit instance, first-phase advice columns. */
+
+typedef struct { uint32_t column; int32_t rotation; } zk_query;
+
+typedef struct {
+  zk_evaluator_desc ev;              /* Evaluator image + column counts + permutation columns */
+  const zk_graph* lookup_inputs;     /* ev.n_lookups graphs: theta-compressed input expressions, */
+  const zk_graph* lookup_tables;     /*   resp. table expressions, evaluated on the n Lagrange rows */
+  const zk_query* advice_queries; uint32_t n_advice_queries;   /* cs.advice_queries, in order */
+  const zk_query* fixed_queries;  uint32_t n_fixed_queries;    /* cs.fixed_queries, in order */
+  zk_fr transcript_repr;             /* vk.transcript_repr: upstream hashes the Debug string of the pinned
+                                        vk, which only Rust can produce -- supplied by the caller */
+} zk_circuit_desc;
+
+typedef struct zk_pkey zk_pkey;
+
+/* keygen_vk + keygen_pk.  fixed_values: ev.n_fixed host columns of n Lagrange values (after selector
+ * compression); perm_mapping: ev.n_perm_columns x n pairs (column', row') -- cell (i, j) of the i-th
+ * permutation column is mapped to cell (column', row') by the copy-constraint cycles (identity when
+ * unconstrained), as permutation::keygen::Assembly holds it.  The SRS must have been uploaded to ctx.
+ * Everything create_proof needs stays resident in HBM. */
+int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* circuit, const zk_fr* const* fixed_values,
+              const uint32_t* perm_mapping, zk_pkey** out);
+void zk_pkey_destroy(zk_pkey* pk);
+/* vk.fixed_commitments (n_fixed) and vk.permutation.commitments (n_perm_columns), affine. */
+int zk_pkey_vk_commitments(const zk_pkey* pk, zk_g1_affine* fixed_commitments, zk_g1_affine* perm_commitments);
+/* The evaluate_h side of the key (for zk_evaluate_h* / zk_pk_program_stats). */
+zk_pk* zk_pkey_pk(zk_pkey* pk);
+/* Number of Fr::random draws one create_proof makes for this circuit. */
+size_t zk_proof_randoms(const zk_pkey* pk);
+/* Upper bound of the proof size in bytes. */
+size_t zk_proof_max_bytes(const zk_pkey* pk);
+
+/* create_proof.  advice_values: ev.n_advice host columns of n Lagrange values as `synthesize` left
+ * them (the last blinding_factors+1 rows are overwritten with randoms here, as upstream);
+ * instance_values / instance_lens: ev.n_instance public-input columns; randoms: the caller's RNG
+ * pre-drawn -- element i is the i-th Fr::random(&mut rng) upstream would make (zk_proof_randoms of them).
+ * proof receives the transcript bytes (Blake2bWrite::finalize). */
+int zk_create_proof(zk_pkey* pk, const zk_fr* const* advice_values,
+                    const zk_fr* const* instance_values, const uint32_t* instance_lens,
+                    const zk_fr* randoms, size_t n_randoms,
+                    uint8_t* proof, size_t proof_cap, size_t* proof_len);
+
 /* ---- element-wise field arithmetic (parity self-test of the device field) --- */
 /* op: 0 add, 1 sub, 2 mul, 3 neg, 4 invert, 5 square, 6 to Montgomery form,
  * 7 from Montgomery form (to_repr), 8 double.  field: 0 = Fr, 1 = Fq.

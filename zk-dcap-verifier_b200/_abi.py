@@ -44,6 +44,18 @@ class zk_evaluator_desc(C.Structure):
                 ("perm_columns", C.POINTER(zk_column)), ("n_perm_columns", C.c_uint32)]
 
 
+class zk_query(C.Structure):
+    _fields_ = [("column", C.c_uint32), ("rotation", C.c_int32)]
+
+
+class zk_circuit_desc(C.Structure):
+    _fields_ = [("ev", zk_evaluator_desc),
+                ("lookup_inputs", C.POINTER(zk_graph)), ("lookup_tables", C.POINTER(zk_graph)),
+                ("advice_queries", C.POINTER(zk_query)), ("n_advice_queries", C.c_uint32),
+                ("fixed_queries", C.POINTER(zk_query)), ("n_fixed_queries", C.c_uint32),
+                ("transcript_repr", zk_fr)]
+
+
 class zk_kernel_stat(C.Structure):
     _fields_ = [("name", C.c_char * 40), ("launches", C.c_uint64), ("total_ms", C.c_double)]
 
@@ -70,6 +82,8 @@ SYMBOLS = [
     "zk_divide_by_vanishing_poly_dev",
     "zk_pk_upload", "zk_pk_destroy", "zk_pk_domain", "zk_pk_program_stats",
     "zk_evaluate_h", "zk_evaluate_h_dev",
+    "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_proof_randoms", "zk_proof_max_bytes",
+    "zk_create_proof",
     "zk_field_op", "zk_bench_modmul", "zk_bench_imad",
 ]
 
@@ -132,6 +146,13 @@ def load():
         "zk_pk_program_stats": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "zk_evaluate_h": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "zk_evaluate_h_dev": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "zk_keygen": (i32, [vp, C.POINTER(zk_circuit_desc), vp, vp, C.POINTER(vp)]),
+        "zk_pkey_destroy": (None, [vp]),
+        "zk_pkey_vk_commitments": (i32, [vp, vp, vp]),
+        "zk_pkey_pk": (vp, [vp]),
+        "zk_proof_randoms": (sz, [vp]),
+        "zk_proof_max_bytes": (sz, [vp]),
+        "zk_create_proof": (i32, [vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz)]),
         "zk_field_op": (i32, [vp, i32, i32, vp, vp, vp, sz]),
         "zk_bench_modmul": (i32, [vp, i32, u32, C.POINTER(C.c_double)]),
         "zk_bench_imad": (i32, [vp, i32, u32, C.POINTER(C.c_double)]),

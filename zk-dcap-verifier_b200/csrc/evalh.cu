@@ -140,7 +140,7 @@ extern "C" int zk_pk_upload(zk_ctx* ctx, const zk_evaluator_desc* desc, const zk
     PK_CUDA(cudaMalloc(&stage, n * 32));
     for (size_t i = 0; i < src.size(); i++) {
       if (!src[i]) { cudaFree(stage); zk_pk_destroy(pk); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_pk_upload: null column pointer"); }
-      PK_CUDA(cudaMemcpyAsync(stage, src[i], n * 32, cudaMemcpyHostToDevice, ctx->stream));
+      PK_CUDA(cudaMemcpyAsync(stage, src[i], n * 32, cudaMemcpyDefault, ctx->stream));   // host or device source
       int rr = zk_coeff_to_extended_dev(pk->dom, (const zk_fr*)stage, (zk_fr*)(res + i * E * 32), 1);
       if (rr != ZK_OK) { cudaFree(stage); zk_pk_destroy(pk); return rr; }
       PK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,899 @@
+// prover.cu -- keygen_pk and create_proof with every n-sized loop on the device.
+//
+// Restates the ORDER of halo2_proofs plonk/prover.rs `create_proof`, plonk/keygen.rs `keygen_vk`/`keygen_pk`,
+// plonk/{lookup,permutation,vanishing}/prover.rs and poly/kzg/multiopen/shplonk/prover.rs ([UPSTREAM] @ c254c75f,
+// Cargo.lock:1314-1316; called at circuits/src/sgx_dcap_verifier.rs:803, :807, :814-822): RNG draw order
+// (SURVEY.md A.7), transcript order (3.2, A.8), query order and SHPLONK set construction (A.5).  Field and group
+// results are canonical, so HOW each vector is computed is free: commitments are the Pippenger MSM of msm.cu,
+// transforms the NTT of ntt.cu, h(X) the fused kernel of evalh.cu, and the loops in between the kernels of
+// prover_kernels.cuh.  The host only hashes (Blake2b transcript) and does O(#columns) scalar arithmetic.
+#include <stdlib.h>
+
+#include <algorithm>
+#include <map>
+#include <set>
+
+#include "common.cuh"
+#include "evalh_compile.hpp"
+#include "prover_kernels.cuh"
+#include "transcript.hpp"
+
+using namespace zk;
+
+// entry points of the other translation units
+extern "C" int zk_lagrange_to_coeff_dev(zk_domain* d, zk_fr* d_a, size_t count);
+extern "C" int zk_extended_to_coeff_dev(zk_domain* d, zk_fr* d_a_ext, zk_fr* d_out);
+extern "C" int zk_divide_by_vanishing_poly_dev(zk_domain* d, zk_fr* d_a_ext);
+extern "C" int zk_msm_batch_dev(zk_ctx* ctx, const zk_fr* d_scalars, int which, size_t n, size_t count, zk_g1* d_out);
+const void* zk_domain_twiddles(const zk_domain* d);
+size_t zk_domain_ext_n(const zk_domain* d);
+
+struct zk_pkey {
+  zk_ctx* ctx = nullptr;
+  zk_pk* pk = nullptr;             // evaluate_h side (cosets, compiled program); owns its own domain
+  zk_domain* dom = nullptr;
+  uint32_t k = 0, degree = 0, bf = 0, n_fixed = 0, n_advice = 0, n_instance = 0, n_challenges = 0, n_lookups = 0;
+  uint32_t n_perm = 0, n_sets = 0, chunk = 0;
+  size_t n = 0, ext_n = 0;
+  std::vector<zk_column> perm_columns;
+  std::vector<zk_query> advice_queries, fixed_queries;
+  Fr transcript_repr;
+  Fr omega, omega_inv;
+  // resident key material (Lagrange values and coefficient forms; the cosets live in `pk`)
+  char *d_fixed_values = nullptr, *d_fixed_polys = nullptr, *d_sigma_values = nullptr, *d_sigma_polys = nullptr;
+  std::vector<zk_g1_affine> fixed_commitments, perm_commitments;
+  // lookup compression program: graphs 2l (inputs) and 2l+1 (tables) of lookup l
+  CompiledEval CL;
+  uint32_t* d_lcode = nullptr;
+  void* d_lconsts = nullptr;
+  const void** d_lcols = nullptr;
+  void* d_challenges = nullptr;
+  // per-proof work area, allocated once
+  char *d_advice = nullptr, *d_instance = nullptr, *d_instance_polys = nullptr, *d_lookup = nullptr, *d_perm_z = nullptr;
+  char *d_random = nullptr, *d_hext = nullptr, *d_hpieces = nullptr, *d_hpoly = nullptr, *d_hx = nullptr, *d_lx = nullptr;
+  char *d_w0 = nullptr, *d_w1 = nullptr, *d_w2 = nullptr;      // n-element scratch vectors
+  char *d_tables = nullptr;                                    // pow tables: slot s at d_tables + s*n*32
+  uint32_t n_table_slots = 0;
+  std::vector<char*> d_setacc;                                 // sum_j y^j P_ij per rotation set
+  char *d_scan_totals = nullptr, *d_seed = nullptr;
+  char *d_keys_a = nullptr, *d_keys_t = nullptr, *d_sk_a = nullptr, *d_sk_t = nullptr;
+  uint32_t *d_idx[4] = {nullptr, nullptr, nullptr, nullptr}, *d_hist = nullptr, *d_u32[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint32_t* d_flags = nullptr;                                  // [0] failure bits, [1..2] totals, [8..15] diff mask
+  char *d_points = nullptr, *d_ptrs = nullptr, *d_scalars = nullptr, *d_partial = nullptr, *d_evals = nullptr;
+  uint32_t max_list = 0, eval_chunks = 1;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+Fr fr_canon_words(const uint32_t c[8]) { Fr v; memcpy(v.l, c, 32); return v.to_mont(); }
+Fr fr_delta() {
+  const uint32_t c[8] = {0xe533e9a2u, 0x870e56bbu, 0x5e963f25u, 0x5b5f898eu, 0xd4c86e71u, 0x64ec26aau, 0x22c6f0cau, 0x09226b6eu};
+  return fr_canon_words(c);
+}
+Fr fr_small(uint64_t x) { Fr v = Fr::zero(); v.l[0] = (uint32_t)x; v.l[1] = (uint32_t)(x >> 32); return v.to_mont(); }
+bool fr_less(const Fr& a, const Fr& b) {        // Fr: Ord = numeric order of the canonical value
+  Fr x = a.from_mont(), y = b.from_mont();
+  for (int i = 7; i >= 0; i--) if (x.l[i] != y.l[i]) return x.l[i] < y.l[i];
+  return false;
+}
+bool fr_same(const Fr& a, const Fr& b) { return (a - b).is_zero(); }
+
+template <class T>
+int dev_alloc(zk_pkey* K, T** p, size_t bytes) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, bytes ? bytes : 32);
+  if (e != cudaSuccess) {
+    K->ctx->err = std::string("zk_keygen: cudaMalloc: ") + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? ZK_ERR_OOM : ZK_ERR_CUDA;
+  }
+  K->allocs.push_back(q);
+  *p = (T*)q;
+  return ZK_OK;
+}
+
+unsigned blocks_for(size_t n, unsigned per) { return zk_div_up(n, per); }
+
+// ---- scans ----------------------------------------------------------------------------------------------------
+template <class M>
+int run_scan(zk_pkey* K, const char* name, const void* in, void* out, size_t n, int reverse, int exclusive, const void* d_seed) {
+  zk_ctx* ctx = K->ctx;
+  unsigned tiles = blocks_for(n, kScanTile);
+  ZK_LAUNCH(ctx, name, k_scan_tiles<M>, tiles, kScanThreads, 0, in, n, reverse, (void*)K->d_scan_totals);
+  ZK_LAUNCH(ctx, name, k_scan_totals<M>, 1, kScanThreads, 0, (void*)K->d_scan_totals, (size_t)tiles, d_seed);
+  ZK_LAUNCH(ctx, name, k_scan_apply<M>, tiles, kScanThreads, 0, in, out, n, reverse, exclusive, (const void*)K->d_scan_totals);
+  return ZK_OK;
+}
+
+int batch_invert(zk_pkey* K, char* v, char* scratch, size_t n) {
+  zk_ctx* ctx = K->ctx;
+  ZK_LAUNCH(ctx, "batch_invert", k_batch_invert, blocks_for(blocks_for(n, kInvChunk), 128), 128, 0, (uint4*)v, (uint4*)scratch, n);
+  return ZK_OK;
+}
+
+// ---- pow tables --------------------------------------------------------------------------------------------------
+char* table_slot(zk_pkey* K, uint32_t slot) { return K->d_tables + (size_t)slot * K->n * 32; }
+int build_pow_table(zk_pkey* K, const Fr& z, uint32_t slot) {
+  zk_ctx* ctx = K->ctx;
+  ZK_LAUNCH(ctx, "pow_table", k_pow_table, blocks_for(blocks_for(K->n, kPowChunk), 128), 128, 0, z, (uint4*)table_slot(K, slot), K->n);
+  return ZK_OK;
+}
+
+// ---- lists of device pointers / scalars ------------------------------------------------------------------------------
+int upload_list(zk_pkey* K, const std::vector<const void*>& ptrs, const std::vector<Fr>* scalars) {
+  zk_ctx* ctx = K->ctx;
+  if (ptrs.size() > K->max_list) ZK_FAIL(ctx, ZK_ERR_ARG, "prover: pointer list of %zu exceeds %u", ptrs.size(), K->max_list);
+  ZK_CUDA(ctx, cudaMemcpyAsync(K->d_ptrs, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  if (scalars) {
+    std::vector<zk_fr> s(scalars->size());
+    for (size_t i = 0; i < s.size(); i++) f_to_abi((*scalars)[i], &s[i]);
+    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_scalars, s.data(), s.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // pageable sources are staged before the call returns
+  return ZK_OK;
+}
+// out = sum_j scalars[j] * polys[j]
+int lincomb(zk_pkey* K, const std::vector<const void*>& polys, const std::vector<Fr>& scalars, char* out) {
+  zk_ctx* ctx = K->ctx;
+  ZK_TRY(upload_list(K, polys, &scalars));
+  ZK_LAUNCH(ctx, "poly_lincomb", k_lincomb, blocks_for(K->n, 256), 256, 0, (const uint4* const*)K->d_ptrs, (const uint4*)K->d_scalars,
+            (uint32_t)polys.size(), (uint4*)out, K->n);
+  return ZK_OK;
+}
+// evaluations of `polys` at the point whose pow table sits in `slot`; results appended to `out` (host, after sync)
+int eval_list(zk_pkey* K, const std::vector<const void*>& polys, uint32_t slot, std::vector<Fr>* out) {
+  zk_ctx* ctx = K->ctx;
+  if (polys.empty()) return ZK_OK;
+  ZK_TRY(upload_list(K, polys, nullptr));
+  dim3 grid(K->eval_chunks, (unsigned)polys.size());
+  ZK_LAUNCH(ctx, "eval_polynomial", k_eval_partial, grid, kEvalThreads, 0, (const uint4* const*)K->d_ptrs, (const uint4*)table_slot(K, slot),
+            K->n, (uint4*)K->d_partial, K->eval_chunks);
+  ZK_LAUNCH(ctx, "eval_polynomial", k_eval_final, blocks_for(polys.size(), 64), 64, 0, (const uint4*)K->d_partial, K->eval_chunks,
+            (uint4*)K->d_evals, (uint32_t)polys.size());
+  std::vector<zk_fr> h(polys.size());
+  ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), K->d_evals, polys.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& e : h) out->push_back(f_from_abi<Fr>(&e));
+  return ZK_OK;
+}
+// a <- a / (X - z) with the pow tables of z in slot_z and of 1/z in slot_zinv (kate_division; remainder dropped)
+int kate_divide(zk_pkey* K, char* a, uint32_t slot_z, uint32_t slot_zinv) {
+  zk_ctx* ctx = K->ctx;
+  size_t n = K->n;
+  ZK_LAUNCH(ctx, "kate_division", k_mul_vec, blocks_for(n, 256), 256, 0, (const uint4*)a, (const uint4*)table_slot(K, slot_z), (uint4*)K->d_w1, n);
+  ZK_TRY(run_scan<FrAddMonoid>(K, "kate_division", K->d_w1, K->d_w2, n, 1, 0, nullptr));
+  ZK_LAUNCH(ctx, "kate_division", k_kate_finish, blocks_for(n, 256), 256, 0, (const uint4*)K->d_w2, (const uint4*)table_slot(K, slot_zinv), (uint4*)a, n);
+  return ZK_OK;
+}
+
+// commitments: `count` contiguous polynomials -> affine points on the host (normalised Jacobian from the MSM)
+struct HostPoint { Fq x, y; bool identity; };
+int commit(zk_pkey* K, const char* d_polys, size_t count, int which, std::vector<HostPoint>* out) {
+  zk_ctx* ctx = K->ctx;
+  ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, count, (zk_g1*)K->d_points));
+  std::vector<zk_g1> h(count);
+  ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), K->d_points, count * sizeof(zk_g1), cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& p : h) {
+    HostPoint q;
+    q.x = f_from_abi<Fq>(&p.x); q.y = f_from_abi<Fq>(&p.y);
+    q.identity = f_from_abi<Fq>(&p.z).is_zero();
+    out->push_back(q);
+  }
+  return ZK_OK;
+}
+
+// ---- lookup: permute_expression_pair on the device -----------------------------------------------------------
+int radix_sort(zk_pkey* K, const char* keys, uint32_t*& idx, uint32_t*& idx_alt, size_t n, const std::vector<uint32_t>& digits) {
+  zk_ctx* ctx = K->ctx;
+  unsigned nb = blocks_for(n, kRadixTile);
+  for (uint32_t d : digits) {
+    ZK_LAUNCH(ctx, "lookup_sort", k_radix_hist, nb, kRadixThreads, 0, (const uint32_t*)keys, idx, n, d, K->d_hist);
+    ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_sort", K->d_hist, K->d_hist, (size_t)256 * nb, 0, 1, nullptr));
+    ZK_LAUNCH(ctx, "lookup_sort", k_radix_scatter, nb, kRadixThreads, 0, (const uint32_t*)keys, idx, idx_alt, n, d, K->d_hist);
+    std::swap(idx, idx_alt);
+  }
+  return ZK_OK;
+}
+// sorts canonical keys of `vals[0..n)`; leaves the order in idx (returned) and the sorted keys in sk
+int sort_values(zk_pkey* K, const char* vals, char* keys, char* sk, uint32_t*& idx, uint32_t*& idx_alt, size_t n) {
+  zk_ctx* ctx = K->ctx;
+  ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, blocks_for(n, 256), 256, 0, (const uint4*)vals, (uint4*)keys, idx, n);
+  ZK_CUDA(ctx, cudaMemsetAsync(K->d_flags + 8, 0, 32, ctx->stream));
+  ZK_LAUNCH(ctx, "lookup_sort", k_key_diff_mask, 148 * 2, 256, 0, (const uint32_t*)keys, n, K->d_flags + 8);
+  uint32_t mask[8];
+  ZK_CUDA(ctx, cudaMemcpyAsync(mask, K->d_flags + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> varying;                                   // digit indices, least significant first
+  for (uint32_t d = 0; d < 32; d++) if ((mask[d >> 2] >> (8 * (d & 3))) & 0xFFu) varying.push_back(d);
+  // theta-compressed values look uniform: the top 8 varying digits (64 bits) order them unless two distinct
+  // values agree on all of those digits.  Sort by them first and verify; fall back to every varying digit.
+  const size_t kTop = 8;
+  bool partial = varying.size() > kTop;
+  std::vector<uint32_t> first = partial ? std::vector<uint32_t>(varying.end() - kTop, varying.end()) : varying;
+  ZK_TRY(radix_sort(K, keys, idx, idx_alt, n, first));
+  ZK_LAUNCH(ctx, "lookup_sort", k_gather_keys, blocks_for(n, 256), 256, 0, (const uint4*)keys, idx, (uint4*)sk, n);
+  if (partial) {
+    ZK_CUDA(ctx, cudaMemsetAsync(K->d_flags + 3, 0, 4, ctx->stream));
+    ZK_LAUNCH(ctx, "lookup_sort", k_check_sorted, blocks_for(n, 256), 256, 0, (const uint32_t*)sk, n, K->d_flags + 3);
+    uint32_t bad = 0;
+    ZK_CUDA(ctx, cudaMemcpyAsync(&bad, K->d_flags + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad) {
+      std::vector<uint32_t> rest(varying.begin(), varying.end() - kTop);
+      // LSD needs the low digits first: redo from the identity order over every varying digit
+      ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, blocks_for(n, 256), 256, 0, (const uint4*)vals, (uint4*)keys, idx, n);
+      ZK_TRY(radix_sort(K, keys, idx, idx_alt, n, varying));
+      ZK_LAUNCH(ctx, "lookup_sort", k_gather_keys, blocks_for(n, 256), 256, 0, (const uint4*)keys, idx, (uint4*)sk, n);
+    }
+  }
+  return ZK_OK;
+}
+// (input, table)[0..usable) -> (A', S')[0..usable)
+int permute_expression_pair(zk_pkey* K, const char* input, const char* table, char* pin, char* ptab, size_t usable) {
+  zk_ctx* ctx = K->ctx;
+  uint32_t *ia = K->d_idx[0], *ia2 = K->d_idx[1], *it = K->d_idx[2], *it2 = K->d_idx[3];
+  ZK_TRY(sort_values(K, input, K->d_keys_a, K->d_sk_a, ia, ia2, usable));
+  ZK_TRY(sort_values(K, table, K->d_keys_t, K->d_sk_t, it, it2, usable));
+  uint32_t *rep = K->d_u32[0], *left = K->d_u32[1], *rrank = K->d_u32[2], *lrank = K->d_u32[3], *rpos = K->d_u32[4];
+  unsigned g = blocks_for(usable, 256);
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_flags, g, 256, 0, (const uint32_t*)K->d_sk_a, (const uint32_t*)K->d_sk_t, usable, rep, left, K->d_flags);
+  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", rep, rrank, usable, 0, 1, nullptr));
+  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", left, lrank, usable, 0, 1, nullptr));
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_totals, 1, 32, 0, rep, rrank, left, lrank, usable, K->d_flags + 1, K->d_flags);
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_rpos, g, 256, 0, rep, rrank, rpos, usable);
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_write, g, 256, 0, (const uint4*)input, (const uint4*)table, ia, it, rep, left, lrank, rpos,
+            K->d_flags + 1, (uint4*)pin, (uint4*)ptab, usable);
+  return ZK_OK;
+}
+
+// lookup compression: graph `gi` of the compress program over the n Lagrange rows
+int eval_rows(zk_pkey* K, uint32_t gi, const EvalScalars& S, char* out) {
+  zk_ctx* ctx = K->ctx;
+  uint32_t ni = K->CL.max_intermediates;
+  unsigned grid = blocks_for(K->n, 128);
+#define ROWS_ARGS K->CL.prog, S, gi, (const uint32_t*)K->d_lcode, (const uint4* const*)K->d_lcols, (const uint4*)K->d_lconsts, \
+                  (const uint4*)K->d_challenges, (uint4*)out, K->n
+  if (ni <= 16) { ZK_LAUNCH(ctx, "lookup_compress", k_eval_rows<16>, grid, 128, 0, ROWS_ARGS); }
+  else if (ni <= 128) { ZK_LAUNCH(ctx, "lookup_compress", k_eval_rows<128>, grid, 128, 0, ROWS_ARGS); }
+  else { ZK_LAUNCH(ctx, "lookup_compress", k_eval_rows<512>, grid, 128, 0, ROWS_ARGS); }
+#undef ROWS_ARGS
+  return ZK_OK;
+}
+
+// ---- host-side helpers of SHPLONK ----------------------------------------------------------------------------------
+// coefficients (low -> high) of the polynomial of degree < m through (points, evals)
+std::vector<Fr> lagrange_interpolate(const std::vector<Fr>& pts, const std::vector<Fr>& evals) {
+  size_t m = pts.size();
+  std::vector<Fr> out(m, Fr::zero());
+  for (size_t j = 0; j < m; j++) {
+    std::vector<Fr> num(1, Fr::one());
+    Fr den = Fr::one();
+    for (size_t i = 0; i < m; i++) {
+      if (i == j) continue;
+      std::vector<Fr> nxt(num.size() + 1, Fr::zero());
+      for (size_t t = 0; t < num.size(); t++) {
+        nxt[t] = nxt[t] - num[t] * pts[i];
+        nxt[t + 1] = nxt[t + 1] + num[t];
+      }
+      num.swap(nxt);
+      den = den * (pts[j] - pts[i]);
+    }
+    Fr f = evals[j] * Fr::inv(den);
+    for (size_t t = 0; t < num.size(); t++) out[t] = out[t] + num[t] * f;
+  }
+  return out;
+}
+Fr eval_small(const std::vector<Fr>& c, const Fr& x) {
+  Fr acc = Fr::zero();
+  for (size_t i = c.size(); i-- > 0;) acc = acc * x + c[i];
+  return acc;
+}
+
+struct Query { const void* poly; uint32_t point; Fr eval; };      // point = index into the list of opening points
+struct RotationSet {
+  std::vector<uint32_t> points;                                    // ascending by field value
+  std::vector<const void*> polys;
+  std::vector<std::vector<Fr>> evals;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" void zk_pkey_destroy(zk_pkey* K) {
+  if (!K) return;
+  cudaSetDevice(K->ctx->device);
+  cudaStreamSynchronize(K->ctx->stream);
+  for (void* p : K->allocs) cudaFree(p);
+  for (char* p : K->d_setacc) cudaFree(p);
+  if (K->pk) zk_pk_destroy(K->pk);
+  if (K->dom) zk_domain_destroy(K->dom);
+  delete K;
+}
+extern "C" zk_pk* zk_pkey_pk(zk_pkey* K) { return K ? K->pk : nullptr; }
+extern "C" size_t zk_proof_randoms(const zk_pkey* K) {
+  if (!K) return 0;
+  size_t a = K->n_advice, l = K->n_lookups, bf = K->bf;
+  return a * (bf + 1) + a + l * (2 * (bf + 1) + 2) + (size_t)K->n_sets * (bf + 1) + l * (bf + 1) + K->n + 1 + (K->degree - 1);
+}
+extern "C" size_t zk_proof_max_bytes(const zk_pkey* K) {
+  if (!K) return 0;
+  size_t points = K->n_advice + 2 * (size_t)K->n_lookups + K->n_sets + K->n_lookups + 1 + (K->degree - 1) + 2;
+  size_t scalars = K->advice_queries.size() + K->fixed_queries.size() + 1 + K->n_perm + 3 * (size_t)K->n_sets + 5 * (size_t)K->n_lookups;
+  return 32 * (points + scalars);
+}
+extern "C" int zk_pkey_vk_commitments(const zk_pkey* K, zk_g1_affine* fixed_commitments, zk_g1_affine* perm_commitments) {
+  if (!K) return ZK_ERR_ARG;
+  if (fixed_commitments && !K->fixed_commitments.empty()) memcpy(fixed_commitments, K->fixed_commitments.data(), K->fixed_commitments.size() * sizeof(zk_g1_affine));
+  if (perm_commitments && !K->perm_commitments.empty()) memcpy(perm_commitments, K->perm_commitments.data(), K->perm_commitments.size() * sizeof(zk_g1_affine));
+  return ZK_OK;
+}
+
+extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* const* fixed_values, const uint32_t* perm_mapping,
+                         zk_pkey** out) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!cd || !out || (cd->ev.n_fixed && !fixed_values) || (cd->ev.n_perm_columns && !perm_mapping) ||
+      (cd->ev.n_lookups && (!cd->lookup_inputs || !cd->lookup_tables)) || (cd->n_advice_queries && !cd->advice_queries) ||
+      (cd->n_fixed_queries && !cd->fixed_queries))
+    ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: bad argument");
+  const zk_evaluator_desc& D = cd->ev;
+  if (D.degree < 3) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: cs.degree() must be >= 3");
+  if (D.n_lookups * 2 > (uint32_t)kMaxLookups) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: more than %d lookup arguments", kMaxLookups / 2);
+  if (D.degree - 2 > 8) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: permutation chunk of %u columns exceeds 8", D.degree - 2);
+  if (ctx->srs_k < D.k || !ctx->srs_g.bases || !ctx->srs_lagrange.bases) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_keygen: upload an SRS with k >= %u first", D.k);
+  if (ctx->srs_k != D.k) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_keygen: the resident SRS has k = %u, the circuit k = %u (g_lagrange is per k)", ctx->srs_k, D.k);
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  zk_pkey* K = new zk_pkey();
+  K->ctx = ctx;
+#define KG(expr) do { int _r = (expr); if (_r != ZK_OK) { zk_pkey_destroy(K); return _r; } } while (0)
+#define KG_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { ctx->err = std::string("zk_keygen: ") + #expr + ": " + cudaGetErrorString(_e); zk_pkey_destroy(K); return _e == cudaErrorMemoryAllocation ? ZK_ERR_OOM : ZK_ERR_CUDA; } } while (0)
+  K->k = D.k; K->degree = D.degree; K->bf = D.blinding_factors;
+  K->n_fixed = D.n_fixed; K->n_advice = D.n_advice; K->n_instance = D.n_instance; K->n_challenges = D.n_challenges;
+  K->n_lookups = D.n_lookups; K->n_perm = D.n_perm_columns; K->chunk = D.degree - 2;
+  K->n_sets = K->n_perm ? (K->n_perm + K->chunk - 1) / K->chunk : 0;
+  K->n = (size_t)1 << D.k;
+  if (K->n < (size_t)K->bf + 3) { zk_pkey_destroy(K); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: not enough rows (n = %zu, minimum_rows = %u)", (size_t)1 << D.k, D.blinding_factors + 3); }
+  K->perm_columns.assign(D.perm_columns, D.perm_columns + D.n_perm_columns);
+  K->advice_queries.assign(cd->advice_queries, cd->advice_queries + cd->n_advice_queries);
+  K->fixed_queries.assign(cd->fixed_queries, cd->fixed_queries + cd->n_fixed_queries);
+  for (auto& q : K->advice_queries) if (q.column >= D.n_advice) { zk_pkey_destroy(K); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: advice query column out of range"); }
+  for (auto& q : K->fixed_queries) if (q.column >= D.n_fixed) { zk_pkey_destroy(K); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: fixed query column out of range"); }
+  K->transcript_repr = f_from_abi<Fr>(&cd->transcript_repr);
+  KG(zk_domain_create(ctx, D.degree, D.k, &K->dom));
+  K->ext_n = zk_domain_ext_n(K->dom);
+  zk_fr dc[8];
+  zk_domain_constants(K->dom, dc);
+  K->omega = f_from_abi<Fr>(&dc[0]); K->omega_inv = f_from_abi<Fr>(&dc[1]);
+  const size_t n = K->n, nb = n * 32;
+
+  // ---- lookup compression program: slots = fixed | advice | instance Lagrange columns -----------------------------
+  {
+    CompiledEval& C = K->CL;
+    C = CompiledEval();
+    EvalProgram& P = C.prog;
+    memset(&P, 0, sizeof P);
+    P.k = D.k; P.ext_k = D.k;
+    P.off_fixed = 0; P.off_advice = D.n_fixed; P.off_instance = D.n_fixed + D.n_advice;
+    C.n_slots = D.n_fixed + D.n_advice + D.n_instance;
+    std::set<std::pair<uint32_t, uint32_t>> cols;
+    for (uint32_t l = 0; l < D.n_lookups; l++) {
+      if (!detail::compile_graph(cd->lookup_inputs[l], D, C, &P.lookups[2 * l], cols, true) ||
+          !detail::compile_graph(cd->lookup_tables[l], D, C, &P.lookups[2 * l + 1], cols, true)) {
+        std::string e = C.error; zk_pkey_destroy(K); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: lookup %u: %s", l, e.c_str());
+      }
+    }
+    if (C.max_intermediates > 512) { zk_pkey_destroy(K); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: lookup graph needs more than 512 intermediates"); }
+    if (C.consts.empty()) { zk_fr z; memset(&z, 0, sizeof z); C.consts.push_back(z); }
+    if (C.code.empty()) C.code.push_back(0);
+    KG(dev_alloc(K, &K->d_lcode, C.code.size() * 4));
+    KG(dev_alloc(K, &K->d_lconsts, C.consts.size() * 32));
+    KG(dev_alloc(K, &K->d_lcols, (C.n_slots + 1) * sizeof(void*)));
+    KG(dev_alloc(K, &K->d_challenges, (D.n_challenges + 1) * 32));
+    KG_CUDA(cudaMemcpyAsync(K->d_lcode, C.code.data(), C.code.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    KG_CUDA(cudaMemcpyAsync(K->d_lconsts, C.consts.data(), C.consts.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+
+  // ---- buffers ---------------------------------------------------------------------------------------------------------
+  KG(dev_alloc(K, &K->d_fixed_values, D.n_fixed * nb)); KG(dev_alloc(K, &K->d_fixed_polys, D.n_fixed * nb));
+  KG(dev_alloc(K, &K->d_sigma_values, K->n_perm * nb)); KG(dev_alloc(K, &K->d_sigma_polys, K->n_perm * nb));
+  KG(dev_alloc(K, &K->d_advice, D.n_advice * nb));
+  KG(dev_alloc(K, &K->d_instance, D.n_instance * nb)); KG(dev_alloc(K, &K->d_instance_polys, D.n_instance * nb));
+  KG(dev_alloc(K, &K->d_lookup, (size_t)D.n_lookups * 5 * nb));
+  KG(dev_alloc(K, &K->d_perm_z, K->n_sets * nb));
+  KG(dev_alloc(K, &K->d_random, nb)); KG(dev_alloc(K, &K->d_hext, K->ext_n * 32));
+  KG(dev_alloc(K, &K->d_hpieces, (size_t)(D.degree - 1) * nb));
+  KG(dev_alloc(K, &K->d_hpoly, nb)); KG(dev_alloc(K, &K->d_hx, nb)); KG(dev_alloc(K, &K->d_lx, nb));
+  KG(dev_alloc(K, &K->d_w0, nb)); KG(dev_alloc(K, &K->d_w1, nb)); KG(dev_alloc(K, &K->d_w2, nb));
+  // opening points: one per distinct rotation (+ u), each with a table of powers and of inverse powers
+  {
+    std::set<int32_t> rots = {0, 1, -1, -(int32_t)(K->bf + 1)};
+    for (auto& q : K->advice_queries) rots.insert(q.rotation);
+    for (auto& q : K->fixed_queries) rots.insert(q.rotation);
+    K->n_table_slots = 2 * ((uint32_t)rots.size() + 1);
+  }
+  KG(dev_alloc(K, &K->d_tables, (size_t)K->n_table_slots * nb));
+  size_t scan_tiles = std::max<size_t>(blocks_for(std::max(n, (size_t)256 * blocks_for(n, kRadixTile)), kScanTile), 1);
+  KG(dev_alloc(K, &K->d_scan_totals, scan_tiles * 32)); KG(dev_alloc(K, &K->d_seed, 32));
+  KG(dev_alloc(K, &K->d_keys_a, nb)); KG(dev_alloc(K, &K->d_keys_t, nb)); KG(dev_alloc(K, &K->d_sk_a, nb)); KG(dev_alloc(K, &K->d_sk_t, nb));
+  for (int i = 0; i < 4; i++) KG(dev_alloc(K, &K->d_idx[i], n * 4));
+  for (int i = 0; i < 5; i++) KG(dev_alloc(K, &K->d_u32[i], n * 4));
+  KG(dev_alloc(K, &K->d_hist, (size_t)256 * blocks_for(n, kRadixTile) * 4));
+  KG(dev_alloc(K, &K->d_flags, 64));
+  K->max_list = D.n_advice + D.n_fixed + D.n_instance + K->n_perm + K->n_sets + 3 * D.n_lookups + D.degree + 16;
+  K->eval_chunks = (uint32_t)std::min<size_t>(std::max<size_t>(n / 4096, 1), 64);
+  KG(dev_alloc(K, &K->d_points, (size_t)K->max_list * sizeof(zk_g1)));
+  KG(dev_alloc(K, &K->d_ptrs, (size_t)K->max_list * sizeof(void*)));
+  KG(dev_alloc(K, &K->d_scalars, (size_t)K->max_list * 32));
+  KG(dev_alloc(K, &K->d_partial, (size_t)K->max_list * K->eval_chunks * 32));
+  KG(dev_alloc(K, &K->d_evals, (size_t)K->max_list * 32));
+
+  // ---- fixed columns: values, coefficient forms ----------------------------------------------------------------------------
+  for (uint32_t i = 0; i < D.n_fixed; i++) {
+    if (!fixed_values[i]) { zk_pkey_destroy(K); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: null fixed column"); }
+    KG_CUDA(cudaMemcpyAsync(K->d_fixed_values + i * nb, fixed_values[i], nb, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  KG_CUDA(cudaMemcpyAsync(K->d_fixed_polys, K->d_fixed_values, D.n_fixed * nb, cudaMemcpyDeviceToDevice, ctx->stream));
+  KG(zk_lagrange_to_coeff_dev(K->dom, (zk_fr*)K->d_fixed_polys, D.n_fixed));
+  // ---- permutation: sigma_i[j] = delta^(i') * omega^(j') ----------------------------------------------------------------------
+  const uint4* tw = (const uint4*)zk_domain_twiddles(K->dom);
+  const uint32_t tw_shift = zk_domain_extended_k(K->dom) - D.k;
+  const size_t half_ext = K->ext_n >> 1;
+  if (K->n_perm) {
+    for (size_t i = 0; i < (size_t)K->n_perm * n; i++)
+      if (perm_mapping[2 * i] >= K->n_perm || perm_mapping[2 * i + 1] >= n) { zk_pkey_destroy(K); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: permutation mapping out of range"); }
+    std::vector<zk_fr> dp(K->n_perm);
+    Fr cur = Fr::one(), delta = fr_delta();
+    for (uint32_t i = 0; i < K->n_perm; i++) { f_to_abi(cur, &dp[i]); cur = cur * delta; }
+    KG_CUDA(cudaMemcpyAsync(K->d_scalars, dp.data(), dp.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+    // the mapping is staged through the (still unused) sigma polynomial buffer: 8 bytes per cell
+    KG_CUDA(cudaMemcpyAsync(K->d_sigma_polys, perm_mapping, (size_t)K->n_perm * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    zk_timing_begin(ctx, "keygen_sigma");
+    k_sigma<<<blocks_for((size_t)K->n_perm * n, 256), 256, 0, ctx->stream>>>((const uint2*)K->d_sigma_polys, (const uint4*)K->d_scalars, tw, tw_shift,
+                                                                           half_ext, (uint4*)K->d_sigma_values, (size_t)K->n_perm * n);
+    zk_timing_end(ctx);
+    KG_CUDA(cudaGetLastError());
+    KG_CUDA(cudaMemcpyAsync(K->d_sigma_polys, K->d_sigma_values, K->n_perm * nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    KG(zk_lagrange_to_coeff_dev(K->dom, (zk_fr*)K->d_sigma_polys, K->n_perm));
+  }
+  // ---- l0, l_last, l_blind --------------------------------------------------------------------------------------------------------
+  {
+    char* ind = K->d_w0;   // three indicator columns need 3n: use w0, w1, w2
+    char* cols3[3] = {K->d_w0, K->d_w1, K->d_w2};
+    (void)ind;
+    size_t lo[3] = {0, n - K->bf - 1, n - K->bf}, hi[3] = {1, n - K->bf, n};
+    for (int i = 0; i < 3; i++) {
+      zk_timing_begin(ctx, "keygen_indicator");
+      k_indicator<<<blocks_for(n, 256), 256, 0, ctx->stream>>>((uint4*)cols3[i], n, lo[i], hi[i]);
+      zk_timing_end(ctx);
+      KG(zk_lagrange_to_coeff_dev(K->dom, (zk_fr*)cols3[i], 1));
+    }
+    std::vector<const zk_fr*> fx(D.n_fixed + 1), sg(K->n_perm + 1);
+    for (uint32_t i = 0; i < D.n_fixed; i++) fx[i] = (const zk_fr*)(K->d_fixed_polys + i * nb);
+    for (uint32_t i = 0; i < K->n_perm; i++) sg[i] = (const zk_fr*)(K->d_sigma_polys + i * nb);
+    // coefficient forms (device pointers; the copies inside are cudaMemcpyDefault) -> cosets, l_active_row
+    KG(zk_pk_upload(ctx, &D, fx.data(), sg.data(), (const zk_fr*)K->d_w0, (const zk_fr*)K->d_w1, (const zk_fr*)K->d_w2, 1, &K->pk));
+  }
+  // ---- keygen_vk: commitments of the fixed and permutation columns ------------------------------------------------------------------
+  {
+    std::vector<HostPoint> pts;
+    if (D.n_fixed) KG(commit(K, K->d_fixed_values, D.n_fixed, ZK_BASES_G_LAGRANGE, &pts));
+    if (K->n_perm) KG(commit(K, K->d_sigma_values, K->n_perm, ZK_BASES_G_LAGRANGE, &pts));
+    for (size_t i = 0; i < pts.size(); i++) {
+      zk_g1_affine a; memset(&a, 0, sizeof a);
+      if (!pts[i].identity) { f_to_abi(pts[i].x, &a.x); f_to_abi(pts[i].y, &a.y); }
+      (i < D.n_fixed ? K->fixed_commitments : K->perm_commitments).push_back(a);
+    }
+  }
+  KG_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef KG
+#undef KG_CUDA
+  *out = K;
+  return ZK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, const zk_fr* const* instance_values,
+                               const uint32_t* instance_lens, const zk_fr* randoms, size_t n_randoms, uint8_t* proof,
+                               size_t proof_cap, size_t* proof_len) {
+  if (!K) return ZK_ERR_ARG;
+  zk_ctx* ctx = K->ctx;
+  if (!proof || !proof_len || !randoms || (K->n_advice && !advice_values) || (K->n_instance && (!instance_values || !instance_lens)))
+    ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: bad argument");
+  if (n_randoms < zk_proof_randoms(K)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: %zu randoms supplied, %zu needed", n_randoms, zk_proof_randoms(K));
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = K->n, nb = n * 32;
+  const uint32_t bf = K->bf, A = K->n_advice, L = K->n_lookups;
+  const size_t usable = n - (bf + 1);
+  size_t rpos = 0;                                    // cursor in `randoms`
+  auto draw_to = [&](char* dst, size_t count) -> int {
+    ZK_CUDA(ctx, cudaMemcpyAsync(dst, randoms + rpos, count * 32, cudaMemcpyHostToDevice, ctx->stream));
+    rpos += count;
+    return ZK_OK;
+  };
+  TranscriptWrite tr;
+  auto write_points = [&](const std::vector<HostPoint>& pts) -> int {
+    for (auto& p : pts)
+      if (!tr.write_point(p.x, p.y, p.identity)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: cannot write points at infinity to the transcript");
+    return ZK_OK;
+  };
+  zk_domain* dom = K->dom;
+  const uint4* tw = (const uint4*)zk_domain_twiddles(dom);
+  const uint32_t tw_shift = zk_domain_extended_k(dom) - K->k;
+  const size_t half_ext = K->ext_n >> 1;
+
+  // vk.hash_into; instances (KZG: the values are absorbed as scalars)
+  tr.common_scalar(K->transcript_repr);
+  for (uint32_t i = 0; i < K->n_instance; i++) {
+    if (instance_lens[i] > usable) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: InstanceTooLarge");
+    ZK_CUDA(ctx, cudaMemsetAsync(K->d_instance + i * nb, 0, nb, ctx->stream));
+    if (instance_lens[i]) {
+      if (!instance_values[i]) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: null instance column");
+      ZK_CUDA(ctx, cudaMemcpyAsync(K->d_instance + i * nb, instance_values[i], (size_t)instance_lens[i] * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (uint32_t j = 0; j < instance_lens[i]; j++) tr.common_scalar(f_from_abi<Fr>(&instance_values[i][j]));
+  }
+  if (K->n_instance) {
+    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_instance_polys, K->d_instance, K->n_instance * nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)K->d_instance_polys, K->n_instance));
+  }
+
+  // ---- advice: upload, blind, commit ---------------------------------------------------------------------------------
+  for (uint32_t i = 0; i < A; i++) {
+    if (!advice_values[i]) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: null advice column");
+    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_advice + i * nb, advice_values[i], usable * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  for (uint32_t i = 0; i < A; i++) ZK_TRY(draw_to(K->d_advice + i * nb + usable * 32, bf + 1));
+  rpos += A;                                           // one Blind per column: drawn, unused by KZG
+  {
+    std::vector<HostPoint> pts;
+    if (A) ZK_TRY(commit(K, K->d_advice, A, ZK_BASES_G_LAGRANGE, &pts));
+    ZK_TRY(write_points(pts));
+  }
+  std::vector<Fr> challenges(K->n_challenges);
+  for (auto& c : challenges) c = tr.squeeze_challenge();
+  if (K->n_challenges) {
+    std::vector<zk_fr> ch(K->n_challenges);
+    for (uint32_t i = 0; i < K->n_challenges; i++) f_to_abi(challenges[i], &ch[i]);
+    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_challenges, ch.data(), ch.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  Fr theta = tr.squeeze_challenge();
+
+  // ---- lookups: compress, permute, commit A' and S' ---------------------------------------------------------------------
+  auto lk = [&](uint32_t l, int which) { return K->d_lookup + ((size_t)l * 5 + which) * nb; };   // 0 cin 1 ctab 2 pin 3 ptab 4 z
+  if (L) {
+    std::vector<const void*> cols(K->CL.n_slots);
+    for (uint32_t i = 0; i < K->n_fixed; i++) cols[K->CL.prog.off_fixed + i] = K->d_fixed_values + i * nb;
+    for (uint32_t i = 0; i < A; i++) cols[K->CL.prog.off_advice + i] = K->d_advice + i * nb;
+    for (uint32_t i = 0; i < K->n_instance; i++) cols[K->CL.prog.off_instance + i] = K->d_instance + i * nb;
+    ZK_CUDA(ctx, cudaMemcpyAsync((void*)K->d_lcols, cols.data(), cols.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    EvalScalars S;
+    S.beta = Fr::zero(); S.gamma = Fr::zero(); S.y = Fr::zero(); S.theta = theta;
+    S.delta_start = Fr::zero(); S.delta = Fr::zero(); S.one = Fr::one();
+    ZK_CUDA(ctx, cudaMemsetAsync(K->d_flags, 0, 64, ctx->stream));
+    for (uint32_t l = 0; l < L; l++) {
+      ZK_TRY(eval_rows(K, 2 * l, S, lk(l, 0)));
+      ZK_TRY(eval_rows(K, 2 * l + 1, S, lk(l, 1)));
+      ZK_TRY(permute_expression_pair(K, lk(l, 0), lk(l, 1), lk(l, 2), lk(l, 3), usable));
+      ZK_TRY(draw_to(lk(l, 2) + usable * 32, bf + 1));
+      ZK_TRY(draw_to(lk(l, 3) + usable * 32, bf + 1));
+      rpos += 2;                                       // the two Blinds of commit_values
+    }
+    uint32_t flags = 0;
+    ZK_CUDA(ctx, cudaMemcpyAsync(&flags, K->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flags & 6u) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: ConstraintSystemFailure (a lookup input is not in its table)");
+    for (uint32_t l = 0; l < L; l++) {
+      std::vector<HostPoint> pts;
+      ZK_TRY(commit(K, lk(l, 2), 2, ZK_BASES_G_LAGRANGE, &pts));      // pin and ptab are adjacent
+      ZK_TRY(write_points(pts));
+    }
+  }
+  Fr beta = tr.squeeze_challenge();
+  Fr gamma = tr.squeeze_challenge();
+
+  // ---- permutation.commit --------------------------------------------------------------------------------------------------
+  auto column_values = [&](const zk_column& c) -> const char* {
+    return c.column_type == ZK_COL_ADVICE ? K->d_advice + c.index * nb : c.column_type == ZK_COL_FIXED ? K->d_fixed_values + c.index * nb
+                                                                                                      : K->d_instance + c.index * nb;
+  };
+  if (K->n_sets) {
+    Fr delta = fr_delta(), dpow = Fr::one();
+    zk_fr one_h; f_to_abi(Fr::one(), &one_h);
+    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_seed, &one_h, 32, cudaMemcpyHostToDevice, ctx->stream));     // last_z = 1
+    for (uint32_t s = 0; s < K->n_sets; s++) {
+      uint32_t c0 = s * K->chunk, c1 = std::min(c0 + K->chunk, K->n_perm);
+      PermCols C; memset(&C, 0, sizeof C);
+      PermNum D;
+      C.ncols = c1 - c0;
+      for (uint32_t c = c0; c < c1; c++) {
+        C.values[c - c0] = (const uint4*)column_values(K->perm_columns[c]);
+        C.sigma[c - c0] = (const uint4*)(K->d_sigma_values + c * nb);
+        D.dbeta[c - c0] = dpow * beta;
+        dpow = dpow * delta;
+      }
+      for (uint32_t c = C.ncols; c < 8; c++) D.dbeta[c] = Fr::zero();
+      char* z = K->d_perm_z + s * nb;
+      ZK_LAUNCH(ctx, "permutation_product", k_perm_den, blocks_for(n, 256), 256, 0, C, beta, gamma, (uint4*)K->d_w0, n);
+      ZK_TRY(batch_invert(K, K->d_w0, K->d_w1, n));
+      ZK_LAUNCH(ctx, "permutation_product", k_perm_num, blocks_for(n, 256), 256, 0, C, D, gamma, tw, tw_shift, half_ext, (uint4*)K->d_w0, n);
+      ZK_TRY(run_scan<FrMulMonoid>(K, "permutation_product", K->d_w0, z, n, 0, 1, K->d_seed));
+      ZK_TRY(draw_to(z + (n - bf) * 32, bf));
+      ZK_CUDA(ctx, cudaMemcpyAsync(K->d_seed, z + usable * 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));   // last_z
+      rpos += 1;
+    }
+    std::vector<HostPoint> pts;
+    ZK_TRY(commit(K, K->d_perm_z, K->n_sets, ZK_BASES_G_LAGRANGE, &pts));
+    ZK_TRY(write_points(pts));
+    ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)K->d_perm_z, K->n_sets));
+  }
+
+  // ---- lookups: commit_product -------------------------------------------------------------------------------------------------
+  for (uint32_t l = 0; l < L; l++) {
+    char* z = lk(l, 4);
+    ZK_LAUNCH(ctx, "lookup_product", k_lookup_den, blocks_for(n, 256), 256, 0, (const uint4*)lk(l, 2), (const uint4*)lk(l, 3), beta, gamma, (uint4*)K->d_w0, n);
+    ZK_TRY(batch_invert(K, K->d_w0, K->d_w1, n));
+    ZK_LAUNCH(ctx, "lookup_product", k_lookup_num, blocks_for(n, 256), 256, 0, (const uint4*)lk(l, 0), (const uint4*)lk(l, 1), beta, gamma, (uint4*)K->d_w0, n);
+    ZK_TRY(run_scan<FrMulMonoid>(K, "lookup_product", K->d_w0, z, n, 0, 1, nullptr));
+    ZK_TRY(draw_to(z + (n - bf) * 32, bf));
+    rpos += 1;
+  }
+  for (uint32_t l = 0; l < L; l++) {
+    std::vector<HostPoint> pts;
+    ZK_TRY(commit(K, lk(l, 4), 1, ZK_BASES_G_LAGRANGE, &pts));
+    ZK_TRY(write_points(pts));
+    ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)lk(l, 2), 3));      // pin, ptab, z -> coefficient form
+  }
+
+  // ---- vanishing.commit: random polynomial ------------------------------------------------------------------------------------
+  ZK_TRY(draw_to(K->d_random, n));
+  rpos += 1;
+  {
+    std::vector<HostPoint> pts;
+    ZK_TRY(commit(K, K->d_random, 1, ZK_BASES_G, &pts));
+    ZK_TRY(write_points(pts));
+  }
+  Fr y = tr.squeeze_challenge();
+
+  // ---- h(X) ----------------------------------------------------------------------------------------------------------------------
+  if (A) ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)K->d_advice, A));
+  {
+    std::vector<const zk_fr*> ap(A + 1), ip(K->n_instance + 1), lp(3 * L + 1), zp(K->n_sets + 1);
+    for (uint32_t i = 0; i < A; i++) ap[i] = (const zk_fr*)(K->d_advice + i * nb);
+    for (uint32_t i = 0; i < K->n_instance; i++) ip[i] = (const zk_fr*)(K->d_instance_polys + i * nb);
+    for (uint32_t l = 0; l < L; l++) { lp[3 * l] = (const zk_fr*)lk(l, 4); lp[3 * l + 1] = (const zk_fr*)lk(l, 2); lp[3 * l + 2] = (const zk_fr*)lk(l, 3); }
+    for (uint32_t s = 0; s < K->n_sets; s++) zp[s] = (const zk_fr*)(K->d_perm_z + s * nb);
+    std::vector<zk_fr> ch(K->n_challenges + 1);
+    for (uint32_t i = 0; i < K->n_challenges; i++) f_to_abi(challenges[i], &ch[i]);
+    zk_fr yh, bh, gh, th;
+    f_to_abi(y, &yh); f_to_abi(beta, &bh); f_to_abi(gamma, &gh); f_to_abi(theta, &th);
+    ZK_TRY(zk_evaluate_h_dev(K->pk, ap.data(), ip.data(), ch.data(), &yh, &bh, &gh, &th, lp.data(), zp.data(), (zk_fr*)K->d_hext));
+  }
+  // vanishing.construct
+  ZK_TRY(zk_divide_by_vanishing_poly_dev(dom, (zk_fr*)K->d_hext));
+  ZK_TRY(zk_extended_to_coeff_dev(dom, (zk_fr*)K->d_hext, (zk_fr*)K->d_hpieces));
+  const uint32_t n_pieces = K->degree - 1;
+  rpos += n_pieces;
+  {
+    std::vector<HostPoint> pts;
+    ZK_TRY(commit(K, K->d_hpieces, n_pieces, ZK_BASES_G, &pts));
+    ZK_TRY(write_points(pts));
+  }
+  Fr x = tr.squeeze_challenge();
+  Fr xn = Fr::pow_u64(x, (uint64_t)n);
+
+  // ---- opening points and their power tables -----------------------------------------------------------------------------------
+  std::vector<int32_t> rot_of;                        // point index -> rotation
+  std::vector<Fr> pt_val;
+  auto point_of = [&](int32_t r) -> uint32_t {
+    for (uint32_t i = 0; i < rot_of.size(); i++) if (rot_of[i] == r) return i;
+    rot_of.push_back(r);
+    Fr v = x * (r >= 0 ? Fr::pow_u64(K->omega, (uint64_t)r) : Fr::pow_u64(K->omega_inv, (uint64_t)(-(int64_t)r)));
+    pt_val.push_back(v);
+    return (uint32_t)rot_of.size() - 1;
+  };
+  struct EvalReq { const void* poly; uint32_t point; };
+  std::vector<EvalReq> reqs;
+  auto req = [&](const void* poly, int32_t r) { reqs.push_back({poly, point_of(r)}); };
+  for (auto& q : K->advice_queries) req(K->d_advice + q.column * nb, q.rotation);
+  for (auto& q : K->fixed_queries) req(K->d_fixed_polys + q.column * nb, q.rotation);
+  // vanishing.evaluate: h(X) = sum_i xn^i h_i(X) (opened, not written); random_eval
+  {
+    std::vector<const void*> pp; std::vector<Fr> sc;
+    Fr cur = Fr::one();
+    for (uint32_t i = 0; i < n_pieces; i++) { pp.push_back(K->d_hpieces + i * nb); sc.push_back(cur); cur = cur * xn; }
+    ZK_TRY(lincomb(K, pp, sc, K->d_hpoly));
+  }
+  req(K->d_random, 0);
+  for (uint32_t i = 0; i < K->n_perm; i++) req(K->d_sigma_polys + i * nb, 0);
+  const int32_t last_rot = -(int32_t)(bf + 1);
+  for (uint32_t s = 0; s < K->n_sets; s++) {
+    req(K->d_perm_z + s * nb, 0); req(K->d_perm_z + s * nb, 1);
+    if (s + 1 < K->n_sets) req(K->d_perm_z + s * nb, last_rot);
+  }
+  for (uint32_t l = 0; l < L; l++) {
+    req(lk(l, 4), 0); req(lk(l, 4), 1); req(lk(l, 2), 0); req(lk(l, 2), -1); req(lk(l, 3), 0);
+  }
+  const size_t n_written = reqs.size();
+  req(K->d_hpoly, 0);                                  // the prover's own evaluation of h (ProverQuery::get_eval)
+  if (2 * (rot_of.size() + 1) > K->n_table_slots) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: opening point tables");
+  for (uint32_t p = 0; p < rot_of.size(); p++) ZK_TRY(build_pow_table(K, pt_val[p], 2 * p));
+  std::vector<Fr> evals(reqs.size());
+  for (uint32_t p = 0; p < rot_of.size(); p++) {
+    std::vector<const void*> polys; std::vector<size_t> where;
+    for (size_t i = 0; i < reqs.size(); i++) if (reqs[i].point == p) { polys.push_back(reqs[i].poly); where.push_back(i); }
+    for (size_t off = 0; off < polys.size(); off += K->max_list) {
+      size_t cnt = std::min<size_t>(K->max_list, polys.size() - off);
+      std::vector<const void*> part(polys.begin() + off, polys.begin() + off + cnt);
+      std::vector<Fr> got;
+      ZK_TRY(eval_list(K, part, 2 * p, &got));
+      for (size_t i = 0; i < cnt; i++) evals[where[off + i]] = got[i];
+    }
+  }
+  for (size_t i = 0; i < n_written; i++) tr.write_scalar(evals[i]);
+
+  // ---- queries in create_proof's order ---------------------------------------------------------------------------------------------
+  std::vector<Query> queries;
+  {
+    size_t e = 0;
+    std::vector<Fr> adv_e(evals.begin(), evals.begin() + K->advice_queries.size()); e += K->advice_queries.size();
+    std::vector<Fr> fix_e(evals.begin() + e, evals.begin() + e + K->fixed_queries.size()); e += K->fixed_queries.size();
+    Fr random_eval = evals[e++];
+    std::vector<Fr> sig_e(evals.begin() + e, evals.begin() + e + K->n_perm); e += K->n_perm;
+    struct PE { Fr x, next, last; };
+    std::vector<PE> pe(K->n_sets);
+    for (uint32_t s = 0; s < K->n_sets; s++) { pe[s].x = evals[e++]; pe[s].next = evals[e++]; if (s + 1 < K->n_sets) pe[s].last = evals[e++]; }
+    std::vector<std::vector<Fr>> le(L);
+    for (uint32_t l = 0; l < L; l++) { le[l].assign(evals.begin() + e, evals.begin() + e + 5); e += 5; }
+    Fr h_eval = evals[e++];
+    const uint32_t p0 = point_of(0);
+    for (size_t i = 0; i < K->advice_queries.size(); i++)
+      queries.push_back({K->d_advice + K->advice_queries[i].column * nb, point_of(K->advice_queries[i].rotation), adv_e[i]});
+    for (uint32_t s = 0; s < K->n_sets; s++) {
+      queries.push_back({K->d_perm_z + s * nb, p0, pe[s].x});
+      queries.push_back({K->d_perm_z + s * nb, point_of(1), pe[s].next});
+    }
+    for (uint32_t s = K->n_sets; s-- > 0;) if (s + 1 < K->n_sets) queries.push_back({K->d_perm_z + s * nb, point_of(last_rot), pe[s].last});
+    for (uint32_t l = 0; l < L; l++) {
+      queries.push_back({lk(l, 4), p0, le[l][0]}); queries.push_back({lk(l, 2), p0, le[l][2]}); queries.push_back({lk(l, 3), p0, le[l][4]});
+      queries.push_back({lk(l, 2), point_of(-1), le[l][3]}); queries.push_back({lk(l, 4), point_of(1), le[l][1]});
+    }
+    for (size_t i = 0; i < K->fixed_queries.size(); i++)
+      queries.push_back({K->d_fixed_polys + K->fixed_queries[i].column * nb, point_of(K->fixed_queries[i].rotation), fix_e[i]});
+    for (uint32_t i = 0; i < K->n_perm; i++) queries.push_back({K->d_sigma_polys + i * nb, p0, sig_e[i]});
+    queries.push_back({K->d_hpoly, p0, h_eval});
+    queries.push_back({K->d_random, p0, random_eval});
+  }
+
+  // ---- ProverSHPLONK::create_proof --------------------------------------------------------------------------------------------------
+  // construct_intermediate_sets: points are compared / ordered by their field value
+  std::vector<uint32_t> pt_rank(pt_val.size());      // rank of point p in ascending field order
+  {
+    std::vector<uint32_t> ord(pt_val.size());
+    for (uint32_t i = 0; i < ord.size(); i++) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return fr_less(pt_val[a], pt_val[b]); });
+    for (uint32_t i = 0; i < ord.size(); i++) pt_rank[ord[i]] = i;
+    for (uint32_t i = 0; i + 1 < ord.size(); i++)
+      if (fr_same(pt_val[ord[i]], pt_val[ord[i + 1]])) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: two rotations give the same opening point");
+  }
+  std::vector<std::pair<const void*, std::set<uint32_t>>> commitment_sets;          // (poly, ranks of its points)
+  for (auto& q : queries) {
+    bool found = false;
+    for (auto& cs_ : commitment_sets) if (cs_.first == q.poly) { cs_.second.insert(pt_rank[q.point]); found = true; break; }
+    if (!found) commitment_sets.push_back({q.poly, {pt_rank[q.point]}});
+  }
+  std::vector<uint32_t> by_rank(pt_val.size());
+  for (uint32_t p = 0; p < pt_val.size(); p++) by_rank[pt_rank[p]] = p;
+  std::vector<RotationSet> sets;
+  {
+    std::vector<std::set<uint32_t>> keys;
+    for (auto& cs_ : commitment_sets) {
+      size_t si = 0;
+      for (; si < keys.size(); si++) if (keys[si] == cs_.second) break;
+      if (si == keys.size()) {
+        keys.push_back(cs_.second);
+        RotationSet rs;
+        for (uint32_t r : cs_.second) rs.points.push_back(by_rank[r]);               // ascending
+        sets.push_back(rs);
+      }
+      std::vector<Fr> ev;
+      for (uint32_t p : sets[si].points) {
+        bool ok = false;
+        for (auto& q : queries) if (q.poly == cs_.first && q.point == p) { ev.push_back(q.eval); ok = true; break; }
+        if (!ok) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: missing query evaluation");
+      }
+      sets[si].polys.push_back(cs_.first);
+      sets[si].evals.push_back(ev);
+    }
+  }
+  Fr ys = tr.squeeze_challenge();
+  Fr v = tr.squeeze_challenge();
+  while (K->d_setacc.size() < sets.size()) {
+    void* p = nullptr;
+    ZK_CUDA(ctx, cudaMalloc(&p, nb));
+    K->d_setacc.push_back((char*)p);
+  }
+  // inverse power tables of the opening points (kate_division by suffix sums)
+  for (uint32_t p = 0; p < rot_of.size(); p++) {
+    if (pt_val[p].is_zero()) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: opening point is zero");
+    ZK_TRY(build_pow_table(K, Fr::inv(pt_val[p]), 2 * p + 1));
+  }
+  std::vector<std::vector<Fr>> ypow(sets.size());
+  std::vector<std::vector<std::vector<Fr>>> rpoly(sets.size());
+  {
+    Fr vpow = Fr::one();
+    for (size_t i = 0; i < sets.size(); i++) {
+      RotationSet& rs = sets[i];
+      std::vector<Fr> pts;
+      for (uint32_t p : rs.points) pts.push_back(pt_val[p]);
+      Fr cur = Fr::one();
+      for (size_t j = 0; j < rs.polys.size(); j++) { ypow[i].push_back(cur); cur = cur * ys; }
+      for (size_t off = 0; off < rs.polys.size(); off += K->max_list - 1) {         // sum_j y^j P_ij, in slices
+        size_t cnt = std::min<size_t>(K->max_list - 1, rs.polys.size() - off);
+        std::vector<const void*> pp(rs.polys.begin() + off, rs.polys.begin() + off + cnt);
+        std::vector<Fr> sc(ypow[i].begin() + off, ypow[i].begin() + off + cnt);
+        if (off) { pp.push_back(K->d_setacc[i]); sc.push_back(Fr::one()); }
+        ZK_TRY(lincomb(K, pp, sc, K->d_setacc[i]));
+      }
+      LowPoly low; memset(&low, 0, sizeof low);
+      low.m = (uint32_t)pts.size();
+      if (low.m > 8) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: a polynomial is opened at more than 8 points");
+      for (uint32_t t = 0; t < 8; t++) low.c[t] = Fr::zero();
+      for (size_t j = 0; j < rs.polys.size(); j++) {
+        rpoly[i].push_back(lagrange_interpolate(pts, rs.evals[j]));                  // low_degree_equivalent
+        for (uint32_t t = 0; t < low.m; t++) low.c[t] = low.c[t] + ypow[i][j] * rpoly[i][j][t];
+      }
+      ZK_CUDA(ctx, cudaMemcpyAsync(K->d_w0, K->d_setacc[i], nb, cudaMemcpyDeviceToDevice, ctx->stream));
+      ZK_LAUNCH(ctx, "shplonk", k_sub_low, 1, 32, 0, (uint4*)K->d_w0, low);
+      for (uint32_t p : rs.points) ZK_TRY(kate_divide(K, K->d_w0, 2 * p, 2 * p + 1));  // div_by_vanishing
+      if (i == 0) {
+        ZK_CUDA(ctx, cudaMemcpyAsync(K->d_hx, K->d_w0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+      } else {
+        ZK_TRY(lincomb(K, {K->d_hx, K->d_w0}, {Fr::one(), vpow}, K->d_hx));
+      }
+      vpow = vpow * v;
+    }
+  }
+  {
+    std::vector<HostPoint> pts;
+    ZK_TRY(commit(K, K->d_hx, 1, ZK_BASES_G, &pts));
+    ZK_TRY(write_points(pts));
+  }
+  Fr u = tr.squeeze_challenge();
+  {
+    std::vector<const void*> pp; std::vector<Fr> sc;
+    Fr vpow = Fr::one(), c0 = Fr::zero(), z0_diff = Fr::one();
+    for (size_t i = 0; i < sets.size(); i++) {
+      Fr z_i = Fr::one();                              // evaluate_vanishing_polynomial(super_point_set \ points, u)
+      for (uint32_t p = 0; p < pt_val.size(); p++)
+        if (std::find(sets[i].points.begin(), sets[i].points.end(), p) == sets[i].points.end()) z_i = z_i * (u - pt_val[p]);
+      if (i == 0) z0_diff = z_i;
+      Fr r_u = Fr::zero();
+      for (size_t j = 0; j < sets[i].polys.size(); j++) r_u = r_u + ypow[i][j] * eval_small(rpoly[i][j], u);
+      pp.push_back(K->d_setacc[i]); sc.push_back(vpow * z_i);
+      c0 = c0 + vpow * z_i * r_u;
+      vpow = vpow * v;
+    }
+    Fr zt = Fr::one();
+    for (auto& p : pt_val) zt = zt * (u - p);
+    pp.push_back(K->d_hx); sc.push_back(zt.neg());
+    ZK_TRY(lincomb(K, pp, sc, K->d_lx));
+    LowPoly low; memset(&low, 0, sizeof low);
+    low.m = 1; low.c[0] = c0;
+    for (uint32_t t = 1; t < 8; t++) low.c[t] = Fr::zero();
+    ZK_LAUNCH(ctx, "shplonk", k_sub_low, 1, 32, 0, (uint4*)K->d_lx, low);
+    if (u.is_zero() || z0_diff.is_zero()) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: degenerate challenge u");
+    uint32_t su = 2 * (uint32_t)rot_of.size();
+    ZK_TRY(build_pow_table(K, u, su));
+    ZK_TRY(build_pow_table(K, Fr::inv(u), su + 1));
+    ZK_TRY(kate_divide(K, K->d_lx, su, su + 1));
+    ZK_LAUNCH(ctx, "shplonk", k_scale, blocks_for(n, 256), 256, 0, (uint4*)K->d_lx, Fr::inv(z0_diff), n);
+    std::vector<HostPoint> pts;
+    ZK_TRY(commit(K, K->d_lx, 1, ZK_BASES_G, &pts));
+    ZK_TRY(write_points(pts));
+  }
+  if (rpos != zk_proof_randoms(K)) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: drew %zu randoms, expected %zu", rpos, zk_proof_randoms(K));
+  if (tr.proof.size() > proof_cap) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: proof needs %zu bytes, buffer holds %zu", tr.proof.size(), proof_cap);
+  memcpy(proof, tr.proof.data(), tr.proof.size());
+  *proof_len = tr.proof.size();
+  return ZK_OK;
+}

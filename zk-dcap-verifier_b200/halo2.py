@@ -602,6 +602,61 @@ class ProvingKey:
         return out
 
 
+# ---- plonk/keygen.rs + plonk/prover.rs ------------------------------------------------------------------
+class ProverKey:
+    """keygen_vk + keygen_pk (circuits/src/sgx_dcap_verifier.rs:803, :807): the whole ProvingKey resident in HBM,
+    together with the per-proof work area.  `params` must hold the SRS of the circuit's k on the same context."""
+
+    def __init__(self, params, circuit, fixed_values, perm_mapping):
+        self.ctx, self.circuit, self.params = params.ctx, circuit, params
+        cs, k = circuit.cs, circuit.k
+        n = 1 << k
+        if len(fixed_values) != cs.num_fixed_columns:
+            raise AssertionError("keygen: fixed column count")
+        self._cd = circuit.to_c()
+        tf, kf = _ptr_table([_u64(f, (n, 4)) for f in fixed_values])
+        mp = np.ascontiguousarray(perm_mapping, dtype=np.uint32).reshape(len(cs.permutation_columns), n, 2)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.zk_keygen(self.ctx.h, C.byref(self._cd), tf, _ptr(mp), C.byref(h)))
+        self.h = h
+        self.randoms_needed = int(self.ctx.lib.zk_proof_randoms(h))
+        self.max_proof_bytes = int(self.ctx.lib.zk_proof_max_bytes(h))
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.zk_pkey_destroy(self.h)
+        except Exception:
+            pass
+
+    def vk_commitments(self):
+        """(vk.fixed_commitments, vk.permutation.commitments) as (count, 8) G1Affine arrays"""
+        cs = self.circuit.cs
+        fc = np.zeros((max(1, cs.num_fixed_columns), 8), dtype=np.uint64)
+        pc = np.zeros((max(1, len(cs.permutation_columns)), 8), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.zk_pkey_vk_commitments(self.h, _ptr(fc), _ptr(pc)))
+        return fc[:cs.num_fixed_columns], pc[:len(cs.permutation_columns)]
+
+    def create_proof(self, advice_values, instances, randoms):
+        """create_proof(params, pk, &[circuit], &[instances], rng, Blake2bWrite) -> transcript.finalize()
+        (sgx_dcap_verifier.rs:814-823).  advice_values: Lagrange columns left by synthesize; instances: one (len, 4)
+        array per instance column; randoms: (count, 4) -- the RNG's Fr::random outputs in draw order."""
+        cs = self.circuit.cs
+        n = 1 << self.circuit.k
+        if len(advice_values) != cs.num_advice_columns or len(instances) != cs.num_instance_columns:
+            raise AssertionError("create_proof: column counts")
+        ta, ka = _ptr_table([_u64(a, (n, 4)) for a in advice_values])
+        inst = [_u64(i, (-1, 4)) for i in instances]
+        ti, ki = _ptr_table(inst)
+        lens = (C.c_uint32 * max(1, len(inst)))(*[i.shape[0] for i in inst])
+        rnd = _u64(randoms, (-1, 4))
+        out = np.empty(self.max_proof_bytes, dtype=np.uint8)
+        ln = C.c_size_t()
+        self.ctx.check(self.ctx.lib.zk_create_proof(self.h, ta, ti, lens, _ptr(rnd), rnd.shape[0], _ptr(out), out.size,
+                                                    C.byref(ln)))
+        return out[:ln.value].tobytes()
+
+
 # ---- device-pointer variants (operands already resident in HBM; asynchronous on the context stream) -----
 def _vp(x):
     return C.c_void_p(int(x)) if x else None

@@ -114,7 +114,7 @@ def hot_path_calls(cs):
 # BASELINE configs 1/2 ask for "synthetic witnesses of the named circuit shapes" (SURVEY.md 8d).  The assignment
 # below satisfies every gate, lookup and copy constraint of qe3_shape(), so the proof it leads to verifies.  It is
 # workload generation, not part of the prover: the field arithmetic it needs (out = a + b*c on the enabled rows) is
-# done by the `fops` object the caller passes (device field ops in bench.py, the oracle's in the tests).
+# done by the `fops` object the caller passes (the device field ops in bench.py).
 def _rand_fr(rng, shape_n):
     import numpy as np
     v = rng.integers(0, 1 << 63, size=(shape_n, 4), dtype=np.uint64) * np.uint64(2) + \
@@ -225,3 +225,67 @@ def synth_qe3_witness(cs, k, seed, fops):
     rows = rng.permutation(usable)[:usable // 8]
     advice[ENC][rows] = advice[ENC][rows]          # ENC stays unconstrained by copies (kept for clarity)
     return fixed, advice, mapping
+
+
+def toy_prover_shape():
+    """Small satisfiable circuit that exercises what the QE3 shape does not: an instance column (also in the
+    permutation), a fixed column in the permutation, a rotation -1 query and a lookup with gated inputs."""
+    cs = ConstraintSystem(num_fixed=4, num_advice=3, num_instance=1)
+    _flex_gate(cs, 0, 0)                                            # F0 * (a + a[1]*a[2] - a[3])
+    cs.create_gate([E.Fixed(1) * (E.Advice(1) - E.Instance(0))])    # F1 * (b - instance)
+    cs.create_gate([E.Fixed(1) * (E.Advice(2, -1) - E.Advice(2, -1)) * 7])   # vanishes identically; queries c at -1
+    q = E.Fixed(1)
+    cs.lookup([q * E.Advice(1), q * E.Advice(2) + (E.Constant(1) - q) * E.Constant(5)], [E.Fixed(2), E.Fixed(3)])
+    cs.enable_equality(_abi.COL_ADVICE, 0)
+    cs.enable_equality(_abi.COL_ADVICE, 1)
+    cs.enable_equality(_abi.COL_FIXED, 2)
+    cs.enable_equality(_abi.COL_INSTANCE, 0)
+    return cs
+
+
+def synth_toy_witness(cs, k, seed, fops, n_instance=5):
+    """-> (fixed_values, advice_values, mapping, instances [one (len, 4) array]) for toy_prover_shape()"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    n = 1 << k
+    usable = n - (cs.blinding_factors() + 1)
+    zero = np.zeros((n, 4), dtype=np.uint64)
+
+    def small(vals):
+        raw = np.zeros((n, 4), dtype=np.uint64)
+        raw[:len(vals), 0] = np.asarray(vals, dtype=np.uint64)
+        return fops.to_mont(raw)
+    one = small([1] * n)
+    fixed = [zero.copy() for _ in range(4)]
+    advice = [_rand_fr(rng, n) for _ in range(3)]
+    trows = min(usable, 16)
+    t0 = _rand_fr(rng, n); t1 = _rand_fr(rng, n)
+    t0[0] = 0; t1[0] = small([5])[0]
+    t0[trows:] = t0[0]; t1[trows:] = t1[0]
+    fixed[2], fixed[3] = t0, t1
+    n_instance = min(n_instance, usable, trows - 1)
+    rows = np.arange(n_instance)
+    pick = 1 + rng.integers(0, trows - 1, size=n_instance)
+    fixed[1][rows] = one[rows]
+    instance = t0[pick].copy()
+    advice[1][rows] = t0[pick]
+    advice[2][rows] = t1[pick]
+    groups = usable // 4
+    g = np.arange(groups)
+    fixed[0][4 * g] = one[:groups]
+    pcol = {col: i for i, col in enumerate(cs.permutation_columns)}
+    mapping = np.empty((len(cs.permutation_columns), n, 2), dtype=np.uint32)
+    mapping[:, :, 0] = np.arange(len(cs.permutation_columns), dtype=np.uint32)[:, None]
+    mapping[:, :, 1] = np.arange(n, dtype=np.uint32)[None, :]
+
+    def tie(ca, ra, cb, rb):
+        mapping[ca, ra, 0], mapping[ca, ra, 1] = cb, rb
+        mapping[cb, rb, 0], mapping[cb, rb, 1] = ca, ra
+    # a-cells of the first gates come from table cells (fixed column in the permutation)
+    m = min(groups, trows)
+    advice[0][4 * np.arange(m)] = t0[np.arange(m)]
+    tie(pcol[(_abi.COL_ADVICE, 0)], 4 * np.arange(m), pcol[(_abi.COL_FIXED, 2)], np.arange(m))
+    advice[0][4 * g + 3] = fops.add(advice[0][4 * g], fops.mul(advice[0][4 * g + 1], advice[0][4 * g + 2]))
+    # instance cells are tied to the b cells they equal
+    tie(pcol[(_abi.COL_INSTANCE, 0)], rows, pcol[(_abi.COL_ADVICE, 1)], rows)
+    return fixed, advice, mapping, [instance]
