@@ -313,7 +313,8 @@ size_t zk_proof_max_bytes(const zk_pkey* pk);
  * them (the last blinding_factors+1 rows are overwritten with randoms here, as upstream);
  * instance_values / instance_lens: ev.n_instance public-input columns; randoms: the caller's RNG
  * pre-drawn -- element i is the i-th Fr::random(&mut rng) upstream would make (zk_proof_randoms of them).
- * proof receives the transcript bytes (Blake2bWrite::finalize). */
+ * proof receives the transcript bytes (Blake2bWrite::finalize).  The advice columns and `randoms` may also be
+ * DEVICE pointers (operands already resident in HBM); instance values must be host memory. */
 int zk_create_proof(zk_pkey* pk, const zk_fr* const* advice_values,
                     const zk_fr* const* instance_values, const uint32_t* instance_lens,
                     const zk_fr* randoms, size_t n_randoms,

@@ -506,7 +506,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   const size_t usable = n - (bf + 1);
   size_t rpos = 0;                                    // cursor in `randoms`
   auto draw_to = [&](char* dst, size_t count) -> int {
-    ZK_CUDA(ctx, cudaMemcpyAsync(dst, randoms + rpos, count * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(dst, randoms + rpos, count * 32, cudaMemcpyDefault, ctx->stream));
     rpos += count;
     return ZK_OK;
   };
@@ -540,7 +540,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   // ---- advice: upload, blind, commit ---------------------------------------------------------------------------------
   for (uint32_t i = 0; i < A; i++) {
     if (!advice_values[i]) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: null advice column");
-    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_advice + i * nb, advice_values[i], usable * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_advice + i * nb, advice_values[i], usable * 32, cudaMemcpyDefault, ctx->stream));
   }
   for (uint32_t i = 0; i < A; i++) ZK_TRY(draw_to(K->d_advice + i * nb + usable * 32, bf + 1));
   rpos += A;                                           // one Blind per column: drawn, unused by KZG

@@ -657,6 +657,20 @@ class ProverKey:
         return out[:ln.value].tobytes()
 
 
+    def create_proof_raw(self, advice_ptrs, randoms_ptr, n_randoms):
+        """Same with raw addresses (pinned host memory or device memory) for the advice columns and the randoms;
+        circuits without instance columns."""
+        if len(advice_ptrs) != self.circuit.cs.num_advice_columns or self.circuit.cs.num_instance_columns:
+            raise AssertionError("create_proof_raw: column counts")
+        ta = (C.c_void_p * max(1, len(advice_ptrs)))(*[int(p) for p in advice_ptrs])
+        if not hasattr(self, "_proof_buf"):
+            self._proof_buf = np.empty(self.max_proof_bytes, dtype=np.uint8)
+        ln = C.c_size_t()
+        self.ctx.check(self.ctx.lib.zk_create_proof(self.h, ta, None, None, C.c_void_p(int(randoms_ptr)), n_randoms,
+                                                    _ptr(self._proof_buf), self._proof_buf.size, C.byref(ln)))
+        return self._proof_buf[:ln.value].tobytes()
+
+
 # ---- device-pointer variants (operands already resident in HBM; asynchronous on the context stream) -----
 def _vp(x):
     return C.c_void_p(int(x)) if x else None
