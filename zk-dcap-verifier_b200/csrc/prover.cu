@@ -56,8 +56,12 @@ struct zk_pkey {
   uint32_t n_table_slots = 0;
   std::vector<char*> d_setacc;                                 // sum_j y^j P_ij per rotation set
   char *d_scan_totals = nullptr, *d_seed = nullptr;
-  char *d_keys_a = nullptr, *d_keys_t = nullptr, *d_sk_a = nullptr, *d_sk_t = nullptr;
-  uint32_t *d_idx[4] = {nullptr, nullptr, nullptr, nullptr}, *d_hist = nullptr, *d_u32[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  char *d_keys = nullptr, *d_sk = nullptr;                      // canonical keys / sorted keys of the 2L sorts
+  uint32_t *d_idx[2] = {nullptr, nullptr}, *d_hist = nullptr, *d_u32[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint32_t *d_masks = nullptr, *d_digits = nullptr, *d_totals = nullptr;
+  char *d_permcols = nullptr, *d_permnum = nullptr, *d_seeds = nullptr;
+  size_t scan_cap = 0;
+  uint64_t sort_fallbacks = 0;
   uint32_t* d_flags = nullptr;                                  // [0] failure bits, [1..2] totals, [8..15] diff mask
   char *d_points = nullptr, *d_ptrs = nullptr, *d_scalars = nullptr, *d_partial = nullptr, *d_evals = nullptr;
   uint32_t max_list = 0, eval_chunks = 1;
@@ -96,12 +100,16 @@ unsigned blocks_for(size_t n, unsigned per) { return zk_div_up(n, per); }
 
 // ---- scans ----------------------------------------------------------------------------------------------------
 template <class M>
-int run_scan(zk_pkey* K, const char* name, const void* in, void* out, size_t n, int reverse, int exclusive, const void* d_seed) {
+int run_scan(zk_pkey* K, const char* name, const void* in, void* out, size_t n, int reverse, int exclusive, const void* d_seeds,
+             unsigned nseg = 1, size_t stride_in = 0, size_t stride_out = 0) {
   zk_ctx* ctx = K->ctx;
   unsigned tiles = blocks_for(n, kScanTile);
-  ZK_LAUNCH(ctx, name, k_scan_tiles<M>, tiles, kScanThreads, 0, in, n, reverse, (void*)K->d_scan_totals);
-  ZK_LAUNCH(ctx, name, k_scan_totals<M>, 1, kScanThreads, 0, (void*)K->d_scan_totals, (size_t)tiles, d_seed);
-  ZK_LAUNCH(ctx, name, k_scan_apply<M>, tiles, kScanThreads, 0, in, out, n, reverse, exclusive, (const void*)K->d_scan_totals);
+  if ((size_t)tiles * nseg > K->scan_cap) ZK_FAIL(ctx, ZK_ERR_STATE, "prover: scan of %zu x %u elements exceeds the scratch", n, nseg);
+  dim3 grid(tiles, nseg);
+  ZK_LAUNCH(ctx, name, k_scan_tiles<M>, grid, kScanThreads, 0, in, n, stride_in, reverse, (void*)K->d_scan_totals);
+  ZK_LAUNCH(ctx, name, k_scan_totals<M>, nseg, kScanThreads, 0, (void*)K->d_scan_totals, (size_t)tiles, d_seeds);
+  ZK_LAUNCH(ctx, name, k_scan_apply<M>, grid, kScanThreads, 0, in, out, n, stride_in, stride_out, reverse, exclusive,
+            (const void*)K->d_scan_totals);
   return ZK_OK;
 }
 
@@ -183,67 +191,78 @@ int commit(zk_pkey* K, const char* d_polys, size_t count, int which, std::vector
   return ZK_OK;
 }
 
-// ---- lookup: permute_expression_pair on the device -----------------------------------------------------------
-int radix_sort(zk_pkey* K, const char* keys, uint32_t*& idx, uint32_t*& idx_alt, size_t n, const std::vector<uint32_t>& digits) {
+// ---- lookup: permute_expression_pair on the device, all lookup arguments at once --------------------------------------
+// Sort s in [0, L) = compressed inputs of lookup s, [L, 2L) = compressed tables: planes 0 and 1 of d_lookup.
+int radix_passes(zk_pkey* K, size_t usable, unsigned nsorts, const std::vector<std::vector<uint32_t>>& digits) {
   zk_ctx* ctx = K->ctx;
-  unsigned nb = blocks_for(n, kRadixTile);
-  for (uint32_t d : digits) {
-    ZK_LAUNCH(ctx, "lookup_sort", k_radix_hist, nb, kRadixThreads, 0, (const uint32_t*)keys, idx, n, d, K->d_hist);
-    ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_sort", K->d_hist, K->d_hist, (size_t)256 * nb, 0, 1, nullptr));
-    ZK_LAUNCH(ctx, "lookup_sort", k_radix_scatter, nb, kRadixThreads, 0, (const uint32_t*)keys, idx, idx_alt, n, d, K->d_hist);
-    std::swap(idx, idx_alt);
+  size_t passes = 0;
+  for (auto& d : digits) passes = std::max(passes, d.size());
+  unsigned nb = blocks_for(usable, kRadixTile);
+  dim3 grid(nb, nsorts);
+  std::vector<uint32_t> tab(passes * nsorts);
+  for (size_t p = 0; p < passes; p++)
+    for (unsigned s_ = 0; s_ < nsorts; s_++) tab[p * nsorts + s_] = p < digits[s_].size() ? digits[s_][p] : kNullDigit;
+  if (tab.size() > 32 * 2 * (size_t)kMaxLookups) ZK_FAIL(ctx, ZK_ERR_STATE, "prover: digit table");
+  ZK_CUDA(ctx, cudaMemcpyAsync(K->d_digits, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  uint32_t *idx = K->d_idx[0], *alt = K->d_idx[1];
+  for (size_t p = 0; p < passes; p++) {
+    const uint32_t* dg = K->d_digits + p * nsorts;
+    ZK_LAUNCH(ctx, "lookup_sort", k_radix_hist, grid, kRadixThreads, 0, (const uint32_t*)K->d_keys, idx, usable, K->n, dg, K->d_hist);
+    ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_sort", K->d_hist, K->d_hist, (size_t)256 * nb * nsorts, 0, 1, nullptr));
+    ZK_LAUNCH(ctx, "lookup_sort", k_radix_scatter, grid, kRadixThreads, 0, (const uint32_t*)K->d_keys, idx, alt, usable, K->n, dg, K->d_hist);
+    std::swap(idx, alt);
   }
+  K->d_idx[0] = idx; K->d_idx[1] = alt;          // d_idx[0] always holds the current order
   return ZK_OK;
 }
-// sorts canonical keys of `vals[0..n)`; leaves the order in idx (returned) and the sorted keys in sk
-int sort_values(zk_pkey* K, const char* vals, char* keys, char* sk, uint32_t*& idx, uint32_t*& idx_alt, size_t n) {
+int permute_expression_pairs(zk_pkey* K, size_t usable) {
   zk_ctx* ctx = K->ctx;
-  ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, blocks_for(n, 256), 256, 0, (const uint4*)vals, (uint4*)keys, idx, n);
-  ZK_CUDA(ctx, cudaMemsetAsync(K->d_flags + 8, 0, 32, ctx->stream));
-  ZK_LAUNCH(ctx, "lookup_sort", k_key_diff_mask, 148 * 2, 256, 0, (const uint32_t*)keys, n, K->d_flags + 8);
-  uint32_t mask[8];
-  ZK_CUDA(ctx, cudaMemcpyAsync(mask, K->d_flags + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  const uint32_t L = K->n_lookups;
+  const unsigned nsorts = 2 * L;
+  const size_t n = K->n;
+  char* vals = K->d_lookup;                      // planes 0 (cin) and 1 (ctab) are adjacent: 2L columns
+  dim3 g256(blocks_for(usable, 256), nsorts);
+  ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, g256, 256, 0, (const uint4*)vals, (uint4*)K->d_keys, K->d_idx[0], usable, n);
+  ZK_CUDA(ctx, cudaMemsetAsync(K->d_masks, 0, (size_t)nsorts * 32, ctx->stream));
+  ZK_LAUNCH(ctx, "lookup_sort", k_key_diff_mask, dim3(32, nsorts), 256, 0, (const uint32_t*)K->d_keys, usable, n, K->d_masks);
+  std::vector<uint32_t> masks((size_t)nsorts * 8);
+  ZK_CUDA(ctx, cudaMemcpyAsync(masks.data(), K->d_masks, masks.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  std::vector<uint32_t> varying;                                   // digit indices, least significant first
-  for (uint32_t d = 0; d < 32; d++) if ((mask[d >> 2] >> (8 * (d & 3))) & 0xFFu) varying.push_back(d);
-  // theta-compressed values look uniform: the top 8 varying digits (64 bits) order them unless two distinct
-  // values agree on all of those digits.  Sort by them first and verify; fall back to every varying digit.
+  // theta-compressed values look uniform: the 8 most significant varying digits (64 bits) order them unless two
+  // distinct values agree on all of those digits.  Sort by them first and verify; fall back to every varying digit.
   const size_t kTop = 8;
-  bool partial = varying.size() > kTop;
-  std::vector<uint32_t> first = partial ? std::vector<uint32_t>(varying.end() - kTop, varying.end()) : varying;
-  ZK_TRY(radix_sort(K, keys, idx, idx_alt, n, first));
-  ZK_LAUNCH(ctx, "lookup_sort", k_gather_keys, blocks_for(n, 256), 256, 0, (const uint4*)keys, idx, (uint4*)sk, n);
+  std::vector<std::vector<uint32_t>> varying(nsorts), first(nsorts);
+  bool partial = false;
+  for (unsigned s_ = 0; s_ < nsorts; s_++) {
+    for (uint32_t d = 0; d < 32; d++) if ((masks[s_ * 8 + (d >> 2)] >> (8 * (d & 3))) & 0xFFu) varying[s_].push_back(d);
+    if (varying[s_].size() > kTop) { partial = true; first[s_].assign(varying[s_].end() - kTop, varying[s_].end()); }
+    else first[s_] = varying[s_];
+  }
+  ZK_TRY(radix_passes(K, usable, nsorts, first));
+  ZK_LAUNCH(ctx, "lookup_sort", k_gather_keys, g256, 256, 0, (const uint4*)K->d_keys, K->d_idx[0], (uint4*)K->d_sk, usable, n);
   if (partial) {
     ZK_CUDA(ctx, cudaMemsetAsync(K->d_flags + 3, 0, 4, ctx->stream));
-    ZK_LAUNCH(ctx, "lookup_sort", k_check_sorted, blocks_for(n, 256), 256, 0, (const uint32_t*)sk, n, K->d_flags + 3);
+    ZK_LAUNCH(ctx, "lookup_sort", k_check_sorted, g256, 256, 0, (const uint32_t*)K->d_sk, usable, n, K->d_flags + 3);
     uint32_t bad = 0;
     ZK_CUDA(ctx, cudaMemcpyAsync(&bad, K->d_flags + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (bad) {
-      std::vector<uint32_t> rest(varying.begin(), varying.end() - kTop);
-      // LSD needs the low digits first: redo from the identity order over every varying digit
-      ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, blocks_for(n, 256), 256, 0, (const uint4*)vals, (uint4*)keys, idx, n);
-      ZK_TRY(radix_sort(K, keys, idx, idx_alt, n, varying));
-      ZK_LAUNCH(ctx, "lookup_sort", k_gather_keys, blocks_for(n, 256), 256, 0, (const uint4*)keys, idx, (uint4*)sk, n);
+    if (bad) {      // LSD needs the low digits first: redo from the identity order over every varying digit
+      K->sort_fallbacks++;
+      ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, g256, 256, 0, (const uint4*)vals, (uint4*)K->d_keys, K->d_idx[0], usable, n);
+      ZK_TRY(radix_passes(K, usable, nsorts, varying));
+      ZK_LAUNCH(ctx, "lookup_sort", k_gather_keys, g256, 256, 0, (const uint4*)K->d_keys, K->d_idx[0], (uint4*)K->d_sk, usable, n);
     }
   }
-  return ZK_OK;
-}
-// (input, table)[0..usable) -> (A', S')[0..usable)
-int permute_expression_pair(zk_pkey* K, const char* input, const char* table, char* pin, char* ptab, size_t usable) {
-  zk_ctx* ctx = K->ctx;
-  uint32_t *ia = K->d_idx[0], *ia2 = K->d_idx[1], *it = K->d_idx[2], *it2 = K->d_idx[3];
-  ZK_TRY(sort_values(K, input, K->d_keys_a, K->d_sk_a, ia, ia2, usable));
-  ZK_TRY(sort_values(K, table, K->d_keys_t, K->d_sk_t, it, it2, usable));
   uint32_t *rep = K->d_u32[0], *left = K->d_u32[1], *rrank = K->d_u32[2], *lrank = K->d_u32[3], *rpos = K->d_u32[4];
-  unsigned g = blocks_for(usable, 256);
-  ZK_LAUNCH(ctx, "lookup_permute", k_permute_flags, g, 256, 0, (const uint32_t*)K->d_sk_a, (const uint32_t*)K->d_sk_t, usable, rep, left, K->d_flags);
-  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", rep, rrank, usable, 0, 1, nullptr));
-  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", left, lrank, usable, 0, 1, nullptr));
-  ZK_LAUNCH(ctx, "lookup_permute", k_permute_totals, 1, 32, 0, rep, rrank, left, lrank, usable, K->d_flags + 1, K->d_flags);
-  ZK_LAUNCH(ctx, "lookup_permute", k_permute_rpos, g, 256, 0, rep, rrank, rpos, usable);
-  ZK_LAUNCH(ctx, "lookup_permute", k_permute_write, g, 256, 0, (const uint4*)input, (const uint4*)table, ia, it, rep, left, lrank, rpos,
-            K->d_flags + 1, (uint4*)pin, (uint4*)ptab, usable);
+  dim3 gl(blocks_for(usable, 256), L);
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_flags, gl, 256, 0, (const uint32_t*)K->d_sk, usable, n, L, rep, left, K->d_flags);
+  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", rep, rrank, usable, 0, 1, nullptr, L, usable, usable));
+  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", left, lrank, usable, 0, 1, nullptr, L, usable, usable));
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_totals, blocks_for(L, 64), 64, 0, rep, rrank, left, lrank, usable, L, K->d_totals, K->d_flags);
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_rpos, gl, 256, 0, rep, rrank, rpos, usable);
+  char* cin = K->d_lookup; char* ctab = cin + (size_t)L * n * 32; char* pin = ctab + (size_t)L * n * 32; char* ptab = pin + (size_t)L * n * 32;
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_write, gl, 256, 0, (const uint4*)cin, (const uint4*)ctab, K->d_idx[0], rep, left, lrank, rpos,
+            K->d_totals, L, (uint4*)pin, (uint4*)ptab, usable, n);
   return ZK_OK;
 }
 
@@ -403,7 +422,10 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
   KG(dev_alloc(K, &K->d_random, nb)); KG(dev_alloc(K, &K->d_hext, K->ext_n * 32));
   KG(dev_alloc(K, &K->d_hpieces, (size_t)(D.degree - 1) * nb));
   KG(dev_alloc(K, &K->d_hpoly, nb)); KG(dev_alloc(K, &K->d_hx, nb)); KG(dev_alloc(K, &K->d_lx, nb));
-  KG(dev_alloc(K, &K->d_w0, nb)); KG(dev_alloc(K, &K->d_w1, nb)); KG(dev_alloc(K, &K->d_w2, nb));
+  {   // w0 / w1 hold one vector per lookup argument or permutation set in the batched product kernels
+    size_t seg = std::max<size_t>(std::max<size_t>(D.n_lookups, K->n_sets), 1);
+    KG(dev_alloc(K, &K->d_w0, seg * nb)); KG(dev_alloc(K, &K->d_w1, seg * nb)); KG(dev_alloc(K, &K->d_w2, nb));
+  }
   // opening points: one per distinct rotation (+ u), each with a table of powers and of inverse powers
   {
     std::set<int32_t> rots = {0, 1, -1, -(int32_t)(K->bf + 1)};
@@ -412,12 +434,20 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
     K->n_table_slots = 2 * ((uint32_t)rots.size() + 1);
   }
   KG(dev_alloc(K, &K->d_tables, (size_t)K->n_table_slots * nb));
-  size_t scan_tiles = std::max<size_t>(blocks_for(std::max(n, (size_t)256 * blocks_for(n, kRadixTile)), kScanTile), 1);
-  KG(dev_alloc(K, &K->d_scan_totals, scan_tiles * 32)); KG(dev_alloc(K, &K->d_seed, 32));
-  KG(dev_alloc(K, &K->d_keys_a, nb)); KG(dev_alloc(K, &K->d_keys_t, nb)); KG(dev_alloc(K, &K->d_sk_a, nb)); KG(dev_alloc(K, &K->d_sk_t, nb));
-  for (int i = 0; i < 4; i++) KG(dev_alloc(K, &K->d_idx[i], n * 4));
-  for (int i = 0; i < 5; i++) KG(dev_alloc(K, &K->d_u32[i], n * 4));
-  KG(dev_alloc(K, &K->d_hist, (size_t)256 * blocks_for(n, kRadixTile) * 4));
+  {
+    const size_t L = D.n_lookups, seg = std::max<size_t>(std::max<size_t>(L, K->n_sets), 1);
+    size_t radix_hist = (size_t)256 * blocks_for(n, kRadixTile) * 2 * L;
+    K->scan_cap = std::max<size_t>(blocks_for(radix_hist, kScanTile), (size_t)blocks_for(n, kScanTile) * seg) + 1;
+    KG(dev_alloc(K, &K->d_scan_totals, K->scan_cap * 32)); KG(dev_alloc(K, &K->d_seed, 32));
+    KG(dev_alloc(K, &K->d_keys, 2 * L * nb)); KG(dev_alloc(K, &K->d_sk, 2 * L * nb));
+    for (int i = 0; i < 2; i++) KG(dev_alloc(K, &K->d_idx[i], 2 * L * n * 4));
+    for (int i = 0; i < 5; i++) KG(dev_alloc(K, &K->d_u32[i], L * n * 4));
+    KG(dev_alloc(K, &K->d_hist, radix_hist * 4));
+    KG(dev_alloc(K, &K->d_masks, 2 * L * 32 + 32)); KG(dev_alloc(K, &K->d_digits, 32 * 2 * (size_t)kMaxLookups * 4));
+    KG(dev_alloc(K, &K->d_totals, L * 4 + 4));
+    KG(dev_alloc(K, &K->d_permcols, (K->n_sets + 1) * sizeof(PermCols))); KG(dev_alloc(K, &K->d_permnum, (K->n_sets + 1) * sizeof(PermNum)));
+    KG(dev_alloc(K, &K->d_seeds, (K->n_sets + 1) * 32));
+  }
   KG(dev_alloc(K, &K->d_flags, 64));
   K->max_list = D.n_advice + D.n_fixed + D.n_instance + K->n_perm + K->n_sets + 3 * D.n_lookups + D.degree + 16;
   K->eval_chunks = (uint32_t)std::min<size_t>(std::max<size_t>(n / 4096, 1), 64);
@@ -559,7 +589,9 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   Fr theta = tr.squeeze_challenge();
 
   // ---- lookups: compress, permute, commit A' and S' ---------------------------------------------------------------------
-  auto lk = [&](uint32_t l, int which) { return K->d_lookup + ((size_t)l * 5 + which) * nb; };   // 0 cin 1 ctab 2 pin 3 ptab 4 z
+  // d_lookup holds five planes of L columns: 0 compressed inputs, 1 compressed tables, 2 A', 3 S', 4 Z -- so that the
+  // commitments, transforms and sorts of all lookup arguments are single batched calls.
+  auto lk = [&](uint32_t l, int which) { return K->d_lookup + ((size_t)which * L + l) * nb; };
   if (L) {
     std::vector<const void*> cols(K->CL.n_slots);
     for (uint32_t i = 0; i < K->n_fixed; i++) cols[K->CL.prog.off_fixed + i] = K->d_fixed_values + i * nb;
@@ -573,20 +605,20 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     for (uint32_t l = 0; l < L; l++) {
       ZK_TRY(eval_rows(K, 2 * l, S, lk(l, 0)));
       ZK_TRY(eval_rows(K, 2 * l + 1, S, lk(l, 1)));
-      ZK_TRY(permute_expression_pair(K, lk(l, 0), lk(l, 1), lk(l, 2), lk(l, 3), usable));
+    }
+    ZK_TRY(permute_expression_pairs(K, usable));
+    for (uint32_t l = 0; l < L; l++) {                 // RNG order: A' rows, S' rows, then the two Blinds, per lookup
       ZK_TRY(draw_to(lk(l, 2) + usable * 32, bf + 1));
       ZK_TRY(draw_to(lk(l, 3) + usable * 32, bf + 1));
-      rpos += 2;                                       // the two Blinds of commit_values
+      rpos += 2;
     }
     uint32_t flags = 0;
     ZK_CUDA(ctx, cudaMemcpyAsync(&flags, K->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (flags & 6u) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: ConstraintSystemFailure (a lookup input is not in its table)");
-    for (uint32_t l = 0; l < L; l++) {
-      std::vector<HostPoint> pts;
-      ZK_TRY(commit(K, lk(l, 2), 2, ZK_BASES_G_LAGRANGE, &pts));      // pin and ptab are adjacent
-      ZK_TRY(write_points(pts));
-    }
+    std::vector<HostPoint> pts;
+    ZK_TRY(commit(K, lk(0, 2), 2 * (size_t)L, ZK_BASES_G_LAGRANGE, &pts));        // planes 2 and 3 are adjacent
+    for (uint32_t l = 0; l < L; l++) ZK_TRY(write_points({pts[l], pts[L + l]}));
   }
   Fr beta = tr.squeeze_challenge();
   Fr gamma = tr.squeeze_challenge();
@@ -597,51 +629,58 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
                                                                                                       : K->d_instance + c.index * nb;
   };
   if (K->n_sets) {
+    // every column set at once: z_s = seed_s * (exclusive prefix products of num/den), seed_{s+1} = z_s[usable]
+    const uint32_t NS = K->n_sets;
     Fr delta = fr_delta(), dpow = Fr::one();
-    zk_fr one_h; f_to_abi(Fr::one(), &one_h);
-    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_seed, &one_h, 32, cudaMemcpyHostToDevice, ctx->stream));     // last_z = 1
-    for (uint32_t s = 0; s < K->n_sets; s++) {
+    std::vector<PermCols> pc(NS);
+    std::vector<PermNum> pn(NS);
+    for (uint32_t s = 0; s < NS; s++) {
       uint32_t c0 = s * K->chunk, c1 = std::min(c0 + K->chunk, K->n_perm);
-      PermCols C; memset(&C, 0, sizeof C);
-      PermNum D;
-      C.ncols = c1 - c0;
+      memset(&pc[s], 0, sizeof(PermCols));
+      pc[s].ncols = c1 - c0;
       for (uint32_t c = c0; c < c1; c++) {
-        C.values[c - c0] = (const uint4*)column_values(K->perm_columns[c]);
-        C.sigma[c - c0] = (const uint4*)(K->d_sigma_values + c * nb);
-        D.dbeta[c - c0] = dpow * beta;
+        pc[s].values[c - c0] = (const uint4*)column_values(K->perm_columns[c]);
+        pc[s].sigma[c - c0] = (const uint4*)(K->d_sigma_values + c * nb);
+        pn[s].dbeta[c - c0] = dpow * beta;
         dpow = dpow * delta;
       }
-      for (uint32_t c = C.ncols; c < 8; c++) D.dbeta[c] = Fr::zero();
-      char* z = K->d_perm_z + s * nb;
-      ZK_LAUNCH(ctx, "permutation_product", k_perm_den, blocks_for(n, 256), 256, 0, C, beta, gamma, (uint4*)K->d_w0, n);
-      ZK_TRY(batch_invert(K, K->d_w0, K->d_w1, n));
-      ZK_LAUNCH(ctx, "permutation_product", k_perm_num, blocks_for(n, 256), 256, 0, C, D, gamma, tw, tw_shift, half_ext, (uint4*)K->d_w0, n);
-      ZK_TRY(run_scan<FrMulMonoid>(K, "permutation_product", K->d_w0, z, n, 0, 1, K->d_seed));
-      ZK_TRY(draw_to(z + (n - bf) * 32, bf));
-      ZK_CUDA(ctx, cudaMemcpyAsync(K->d_seed, z + usable * 32, 32, cudaMemcpyDeviceToDevice, ctx->stream));   // last_z
+      for (uint32_t c = pc[s].ncols; c < 8; c++) pn[s].dbeta[c] = Fr::zero();
+    }
+    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_permcols, pc.data(), NS * sizeof(PermCols), cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_permnum, pn.data(), NS * sizeof(PermNum), cudaMemcpyHostToDevice, ctx->stream));
+    dim3 g(blocks_for(n, 256), NS);
+    ZK_LAUNCH(ctx, "permutation_product", k_perm_den, g, 256, 0, (const PermCols*)K->d_permcols, beta, gamma, (uint4*)K->d_w0, n);
+    ZK_TRY(batch_invert(K, K->d_w0, K->d_w1, (size_t)NS * n));
+    ZK_LAUNCH(ctx, "permutation_product", k_perm_num, g, 256, 0, (const PermCols*)K->d_permcols, (const PermNum*)K->d_permnum, gamma, tw,
+              tw_shift, half_ext, (uint4*)K->d_w0, n);
+    ZK_TRY(run_scan<FrMulMonoid>(K, "permutation_product", K->d_w0, K->d_perm_z, n, 0, 1, nullptr, NS, n, n));
+    ZK_LAUNCH(ctx, "permutation_product", k_perm_seeds, 1, 32, 0, (const uint4*)K->d_perm_z, n, usable, NS, (uint4*)K->d_seeds);
+    ZK_LAUNCH(ctx, "permutation_product", k_scale_seg, g, 256, 0, (uint4*)K->d_perm_z, (const uint4*)K->d_seeds, n);
+    for (uint32_t s = 0; s < NS; s++) {
+      ZK_TRY(draw_to(K->d_perm_z + s * nb + (n - bf) * 32, bf));
       rpos += 1;
     }
     std::vector<HostPoint> pts;
-    ZK_TRY(commit(K, K->d_perm_z, K->n_sets, ZK_BASES_G_LAGRANGE, &pts));
+    ZK_TRY(commit(K, K->d_perm_z, NS, ZK_BASES_G_LAGRANGE, &pts));
     ZK_TRY(write_points(pts));
-    ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)K->d_perm_z, K->n_sets));
+    ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)K->d_perm_z, NS));
   }
 
   // ---- lookups: commit_product -------------------------------------------------------------------------------------------------
-  for (uint32_t l = 0; l < L; l++) {
-    char* z = lk(l, 4);
-    ZK_LAUNCH(ctx, "lookup_product", k_lookup_den, blocks_for(n, 256), 256, 0, (const uint4*)lk(l, 2), (const uint4*)lk(l, 3), beta, gamma, (uint4*)K->d_w0, n);
-    ZK_TRY(batch_invert(K, K->d_w0, K->d_w1, n));
-    ZK_LAUNCH(ctx, "lookup_product", k_lookup_num, blocks_for(n, 256), 256, 0, (const uint4*)lk(l, 0), (const uint4*)lk(l, 1), beta, gamma, (uint4*)K->d_w0, n);
-    ZK_TRY(run_scan<FrMulMonoid>(K, "lookup_product", K->d_w0, z, n, 0, 1, nullptr));
-    ZK_TRY(draw_to(z + (n - bf) * 32, bf));
-    rpos += 1;
-  }
-  for (uint32_t l = 0; l < L; l++) {
+  if (L) {
+    dim3 g(blocks_for(n, 256), L);
+    ZK_LAUNCH(ctx, "lookup_product", k_lookup_den, g, 256, 0, (const uint4*)lk(0, 2), (const uint4*)lk(0, 3), beta, gamma, (uint4*)K->d_w0, n);
+    ZK_TRY(batch_invert(K, K->d_w0, K->d_w1, (size_t)L * n));
+    ZK_LAUNCH(ctx, "lookup_product", k_lookup_num, g, 256, 0, (const uint4*)lk(0, 0), (const uint4*)lk(0, 1), beta, gamma, (uint4*)K->d_w0, n);
+    ZK_TRY(run_scan<FrMulMonoid>(K, "lookup_product", K->d_w0, lk(0, 4), n, 0, 1, nullptr, L, n, n));
+    for (uint32_t l = 0; l < L; l++) {
+      ZK_TRY(draw_to(lk(l, 4) + (n - bf) * 32, bf));
+      rpos += 1;
+    }
     std::vector<HostPoint> pts;
-    ZK_TRY(commit(K, lk(l, 4), 1, ZK_BASES_G_LAGRANGE, &pts));
+    ZK_TRY(commit(K, lk(0, 4), L, ZK_BASES_G_LAGRANGE, &pts));
     ZK_TRY(write_points(pts));
-    ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)lk(l, 2), 3));      // pin, ptab, z -> coefficient form
+    ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)lk(0, 2), 3 * (size_t)L));       // A', S', Z planes -> coefficient form
   }
 
   // ---- vanishing.commit: random polynomial ------------------------------------------------------------------------------------

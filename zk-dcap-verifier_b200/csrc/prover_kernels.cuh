@@ -62,56 +62,62 @@ __device__ typename M::T block_exclusive(typename M::T v, typename M::T* sh, typ
 // Logical element i of a scan lives at physical index (reverse ? n-1-i : i).
 __device__ __forceinline__ size_t scan_phys(size_t i, size_t n, int reverse) { return reverse ? n - 1 - i : i; }
 
+// The scans are SEGMENTED: blockIdx.y selects one of several independent arrays of n elements (segment g starts at
+// element g * stride), so that the lookups' / permutation sets' products run in one launch.
 // phase 1: reduction of every tile
 template <class M>
-__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const void* in, size_t n, int reverse, void* tile_totals) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const void* in, size_t n, size_t stride, int reverse, void* tile_totals) {
   typedef typename M::T T;
   __shared__ T sh[kScanThreads];
+  const size_t seg = (size_t)blockIdx.y * stride;
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   T acc = M::identity();
 #pragma unroll
   for (int k = 0; k < kScanItems; k++)
-    if (base + k < n) acc = M::combine(acc, M::load(in, scan_phys(base + k, n, reverse)));
+    if (base + k < n) acc = M::combine(acc, M::load(in, seg + scan_phys(base + k, n, reverse)));
   T total;
   block_exclusive<M>(acc, sh, &total);
-  if (threadIdx.x == 0) M::store(tile_totals, blockIdx.x, total);
+  if (threadIdx.x == 0) M::store(tile_totals, (size_t)blockIdx.y * gridDim.x + blockIdx.x, total);
 }
-// phase 2: exclusive scan of the tile totals, in place, by ONE block; seed (optional, device) multiplies in front
+// phase 2: exclusive scan of each segment's tile totals, in place, one block per segment; seeds (optional, device,
+// one per segment) multiply in front
 template <class M>
-__global__ void __launch_bounds__(kScanThreads) k_scan_totals(void* tile_totals, size_t ntiles, const void* seed) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_totals(void* tile_totals, size_t ntiles, const void* seeds) {
   typedef typename M::T T;
   __shared__ T sh[kScanThreads];
-  T carry = seed ? M::load(seed, 0) : M::identity();
+  const size_t seg = (size_t)blockIdx.x * ntiles;
+  T carry = seeds ? M::load(seeds, blockIdx.x) : M::identity();
   for (size_t base = 0; base < ntiles; base += kScanThreads) {
     size_t i = base + threadIdx.x;
-    T v = i < ntiles ? M::load(tile_totals, i) : M::identity();
+    T v = i < ntiles ? M::load(tile_totals, seg + i) : M::identity();
     T total;
     T excl = block_exclusive<M>(v, sh, &total);
-    if (i < ntiles) M::store(tile_totals, i, M::combine(carry, excl));
+    if (i < ntiles) M::store(tile_totals, seg + i, M::combine(carry, excl));
     carry = M::combine(carry, total);
   }
 }
 // phase 3: out[i] = prefix(tile) * prefix(thread) * local; exclusive => out[i] excludes element i
 template <class M>
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const void* in, void* out, size_t n, int reverse, int exclusive,
-                                                             const void* tile_prefix) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const void* in, void* out, size_t n, size_t stride_in, size_t stride_out,
+                                                             int reverse, int exclusive, const void* tile_prefix) {
   typedef typename M::T T;
   __shared__ T sh[kScanThreads];
+  const size_t seg_in = (size_t)blockIdx.y * stride_in, seg_out = (size_t)blockIdx.y * stride_out;
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   T v[kScanItems];
   T acc = M::identity();
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
-    v[k] = base + k < n ? M::load(in, scan_phys(base + k, n, reverse)) : M::identity();
+    v[k] = base + k < n ? M::load(in, seg_in + scan_phys(base + k, n, reverse)) : M::identity();
     acc = M::combine(acc, v[k]);
   }
   T total;
   T excl = block_exclusive<M>(acc, sh, &total);
-  T run = M::combine(M::load(tile_prefix, blockIdx.x), excl);
+  T run = M::combine(M::load(tile_prefix, (size_t)blockIdx.y * gridDim.x + blockIdx.x), excl);
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
     T incl = M::combine(run, v[k]);
-    if (base + k < n) M::store(out, scan_phys(base + k, n, reverse), exclusive ? run : incl);
+    if (base + k < n) M::store(out, seg_out + scan_phys(base + k, n, reverse), exclusive ? run : incl);
     run = incl;
   }
 }
@@ -128,37 +134,60 @@ struct PermCols {
   const uint4* values[8];
   const uint4* sigma[8];
   uint32_t ncols;
+  uint32_t pad;
 };
-// mv[i] = prod_c (beta * sigma_c[i] + gamma + v_c[i])
-__global__ void __launch_bounds__(256) k_perm_den(PermCols C, Fr beta, Fr gamma, uint4* mv, size_t n) {
+struct PermNum { Fr dbeta[8]; };
+// one column set per blockIdx.y:  mv[set][i] = prod_c (beta * sigma_c[i] + gamma + v_c[i])
+__global__ void __launch_bounds__(256) k_perm_den(const PermCols* Cs, Fr beta, Fr gamma, uint4* mv, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const PermCols& C = Cs[blockIdx.y];
   Fr m = Fr::one();
   for (uint32_t c = 0; c < C.ncols; c++)
     m = m * (beta * Fr::load(C.sigma[c] + 2 * i) + gamma + Fr::load(C.values[c] + 2 * i));
-  m.store(mv + 2 * i);
+  m.store(mv + 2 * ((size_t)blockIdx.y * n + i));
 }
-// mv[i] *= prod_c (delta^(c0+c) * omega^i * beta + gamma + v_c[i]);  dbeta[c] = delta^(c0+c) * beta
-struct PermNum { Fr dbeta[8]; };
-__global__ void __launch_bounds__(256) k_perm_num(PermCols C, PermNum D, Fr gamma, const uint4* tw, uint32_t tw_shift,
+// mv[set][i] *= prod_c (delta^(c0+c) * omega^i * beta + gamma + v_c[i]);  dbeta[c] = delta^(c0+c) * beta
+__global__ void __launch_bounds__(256) k_perm_num(const PermCols* Cs, const PermNum* Ds, Fr gamma, const uint4* tw, uint32_t tw_shift,
                                                   size_t half_ext, uint4* mv, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const PermCols& C = Cs[blockIdx.y];
+  const PermNum& D = Ds[blockIdx.y];
   Fr w = omega_pow(tw, i, tw_shift, half_ext);
-  Fr m = Fr::load(mv + 2 * i);
+  uint4* p = mv + 2 * ((size_t)blockIdx.y * n + i);
+  Fr m = Fr::load(p);
   for (uint32_t c = 0; c < C.ncols; c++) m = m * (D.dbeta[c] * w + gamma + Fr::load(C.values[c] + 2 * i));
-  m.store(mv + 2 * i);
+  m.store(p);
 }
-// lookup product denominators / numerators
+// seeds[s] = last_z entering set s: seeds[0] = 1, seeds[s+1] = seeds[s] * zloc[s][usable]   (one thread)
+__global__ void k_perm_seeds(const uint4* zloc, size_t n, size_t usable, uint32_t n_sets, uint4* seeds) {
+  if (threadIdx.x || blockIdx.x) return;
+  Fr s = Fr::one();
+  for (uint32_t i = 0; i < n_sets; i++) {
+    s.store(seeds + 2 * i);
+    s = s * Fr::load(zloc + 2 * ((size_t)i * n + usable));
+  }
+}
+// a[seg][i] *= seeds[seg]
+__global__ void __launch_bounds__(256) k_scale_seg(uint4* a, const uint4* seeds, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint4* p = a + 2 * ((size_t)blockIdx.y * n + i);
+  (Fr::load(p) * Fr::load(seeds + 2 * blockIdx.y)).store(p);
+}
+// lookup product denominators / numerators; one lookup per blockIdx.y, planes of L columns each
 __global__ void __launch_bounds__(256) k_lookup_den(const uint4* pin, const uint4* ptab, Fr beta, Fr gamma, uint4* lp, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  ((beta + Fr::load(pin + 2 * i)) * (gamma + Fr::load(ptab + 2 * i))).store(lp + 2 * i);
+  size_t o = 2 * ((size_t)blockIdx.y * n + i);
+  ((beta + Fr::load(pin + o)) * (gamma + Fr::load(ptab + o))).store(lp + o);
 }
 __global__ void __launch_bounds__(256) k_lookup_num(const uint4* cin, const uint4* ctab, Fr beta, Fr gamma, uint4* lp, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  (Fr::load(lp + 2 * i) * (Fr::load(cin + 2 * i) + beta) * (Fr::load(ctab + 2 * i) + gamma)).store(lp + 2 * i);
+  size_t o = 2 * ((size_t)blockIdx.y * n + i);
+  (Fr::load(lp + o) * (Fr::load(cin + o) + beta) * (Fr::load(ctab + o) + gamma)).store(lp + o);
 }
 
 // In-place batch inversion, zeros stay zero (ff batch_invert semantics).  Each thread owns kInvChunk consecutive
@@ -281,16 +310,23 @@ __global__ void __launch_bounds__(128) k_eval_rows(EvalProgram P, EvalScalars S,
 }
 
 // ---- lookup: permute_expression_pair ----------------------------------------------------------------------------
+// All sorts of one proof (2 per lookup argument: compressed inputs and compressed tables) run in the same launches:
+// blockIdx.y = sort index.  Values / keys / sorted keys of sort s start at element s * stride; the index arrays are
+// packed with stride n (the number of sorted elements), so that the concatenation of all sorts is ONE array whose
+// radix offsets come from one global scan of hist[sort][digit][block].
 // keys = canonical (non-Montgomery) values so that limb order = numeric order (Fr: Ord)
-__global__ void __launch_bounds__(256) k_canon_keys(const uint4* v, uint4* keys, uint32_t* idx, size_t n) {
+__global__ void __launch_bounds__(256) k_canon_keys(const uint4* v, uint4* keys, uint32_t* idx, size_t n, size_t stride) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fr::load(v + 2 * i).from_mont().store_raw(keys + 2 * i);
-  idx[i] = (uint32_t)i;
+  size_t o = (size_t)blockIdx.y * stride + i;
+  Fr::load(v + 2 * o).from_mont().store_raw(keys + 2 * o);
+  idx[(size_t)blockIdx.y * n + i] = (uint32_t)i;
 }
-// mask[l] |= keys[i].l[l] ^ keys[0].l[l]: which bits differ anywhere in the array
-__global__ void __launch_bounds__(256) k_key_diff_mask(const uint32_t* keys, size_t n, uint32_t* mask) {
+// mask[sort][l] |= keys[i].l[l] ^ keys[0].l[l]: which bits differ anywhere in the array
+__global__ void __launch_bounds__(256) k_key_diff_mask(const uint32_t* keys_all, size_t n, size_t stride, uint32_t* mask_all) {
   __shared__ uint32_t sh[8];
+  const uint32_t* keys = keys_all + 8 * (size_t)blockIdx.y * stride;
+  uint32_t* mask = mask_all + 8 * blockIdx.y;
   if (threadIdx.x < 8) sh[threadIdx.x] = 0;
   __syncthreads();
   uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -310,13 +346,18 @@ __global__ void __launch_bounds__(256) k_key_diff_mask(const uint32_t* keys, siz
 constexpr int kRadixThreads = 256;
 constexpr int kRadixRows = 8;
 constexpr int kRadixTile = kRadixThreads * kRadixRows;
+constexpr uint32_t kNullDigit = 0xFFu;      // a padding pass: every key has digit 0 (stable identity permutation)
 __device__ __forceinline__ uint32_t key_digit(const uint32_t* keys, uint32_t id, uint32_t d) {
+  if (d == kNullDigit) return 0;
   return (keys[8 * (size_t)id + (d >> 2)] >> (8 * (d & 3))) & 0xFFu;
 }
-// hist[digit * nblocks + block]
-__global__ void __launch_bounds__(kRadixThreads) k_radix_hist(const uint32_t* keys, const uint32_t* idx, size_t n, uint32_t d,
-                                                              uint32_t* hist) {
+// hist[(sort * 256 + digit) * nblocks + block];  digits[sort] = digit index of this pass for that sort
+__global__ void __launch_bounds__(kRadixThreads) k_radix_hist(const uint32_t* keys_all, const uint32_t* idx_all, size_t n, size_t stride,
+                                                              const uint32_t* digits, uint32_t* hist) {
   __shared__ uint32_t sh[256];
+  const uint32_t* keys = keys_all + 8 * (size_t)blockIdx.y * stride;
+  const uint32_t* idx = idx_all + (size_t)blockIdx.y * n;
+  const uint32_t d = digits[blockIdx.y];
   sh[threadIdx.x] = 0;
   __syncthreads();
   size_t base = (size_t)blockIdx.x * kRadixTile;
@@ -325,14 +366,17 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix_hist(const uint32_t* ke
     if (i < n) atomicAdd(&sh[key_digit(keys, idx[i], d)], 1u);
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
+  hist[((size_t)blockIdx.y * 256 + threadIdx.x) * gridDim.x + blockIdx.x] = sh[threadIdx.x];
 }
-// stable scatter; `offs` = exclusive scan of hist
-__global__ void __launch_bounds__(kRadixThreads) k_radix_scatter(const uint32_t* keys, const uint32_t* idx_in, uint32_t* idx_out,
-                                                                 size_t n, uint32_t d, const uint32_t* offs) {
+// stable scatter; `offs` = exclusive scan of the whole hist array (offsets into the concatenated index array)
+__global__ void __launch_bounds__(kRadixThreads) k_radix_scatter(const uint32_t* keys_all, const uint32_t* idx_in_all, uint32_t* idx_out_all,
+                                                                 size_t n, size_t stride, const uint32_t* digits, const uint32_t* offs) {
   __shared__ uint32_t cnt[kRadixThreads / 32][256];
+  const uint32_t* keys = keys_all + 8 * (size_t)blockIdx.y * stride;
+  const uint32_t* idx_in = idx_in_all + (size_t)blockIdx.y * n;
+  const uint32_t d = digits[blockIdx.y];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t running = offs[(size_t)threadIdx.x * gridDim.x + blockIdx.x];     // thread t owns digit t
+  uint32_t running = offs[((size_t)blockIdx.y * 256 + threadIdx.x) * gridDim.x + blockIdx.x];     // thread t owns digit t
   size_t base = (size_t)blockIdx.x * kRadixTile;
   for (int r = 0; r < kRadixRows; r++) {
     for (int q = 0; q < kRadixThreads / 32; q++) cnt[q][threadIdx.x] = 0;
@@ -351,7 +395,7 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix_scatter(const uint32_t*
       running = acc;
     }
     __syncthreads();
-    if (valid) idx_out[cnt[w][dg] + rank] = id;
+    if (valid) idx_out_all[cnt[w][dg] + rank] = id;      // global offset: already includes sort * n
     __syncthreads();
   }
 }
@@ -363,16 +407,20 @@ __device__ __forceinline__ int key_cmp(const uint32_t* a, const uint32_t* b) {
   return 0;
 }
 // sk[j] = keys[idx[j]]
-__global__ void __launch_bounds__(256) k_gather_keys(const uint4* keys, const uint32_t* idx, uint4* sk, size_t n) {
+__global__ void __launch_bounds__(256) k_gather_keys(const uint4* keys_all, const uint32_t* idx_all, uint4* sk_all, size_t n, size_t stride) {
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
-  size_t s = idx[j];
+  const uint4* keys = keys_all + 2 * (size_t)blockIdx.y * stride;
+  uint4* sk = sk_all + 2 * (size_t)blockIdx.y * stride;
+  size_t s = idx_all[(size_t)blockIdx.y * n + j];
   sk[2 * j] = keys[2 * s]; sk[2 * j + 1] = keys[2 * s + 1];
 }
-// flag[0] |= 1 when the order produced by the top-digit passes is not total: some adjacent pair is out of order
-__global__ void __launch_bounds__(256) k_check_sorted(const uint32_t* sk, size_t n, uint32_t* flag) {
+// flag[0] |= 1 when some adjacent pair is out of order under the FULL comparison (the top-digit passes did not
+// produce a total order)
+__global__ void __launch_bounds__(256) k_check_sorted(const uint32_t* sk_all, size_t n, size_t stride, uint32_t* flag) {
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j + 1 >= n) return;
+  const uint32_t* sk = sk_all + 8 * (size_t)blockIdx.y * stride;
   if (key_cmp(sk + 8 * j, sk + 8 * (j + 1)) > 0) atomicOr(flag, 1u);
 }
 // lower_bound of key in sorted array
@@ -384,12 +432,17 @@ __device__ __forceinline__ size_t key_lower_bound(const uint32_t* sorted, size_t
   }
   return lo;
 }
-// sa / st: sorted canonical keys of the input / table.  rep[j] = 1 when row j repeats the previous input value;
-// left[j] = 1 when table entry j is NOT consumed by a first occurrence.  flag |= 2 when an input is not in the table.
-__global__ void __launch_bounds__(256) k_permute_flags(const uint32_t* sa, const uint32_t* st, size_t n, uint32_t* rep,
-                                                       uint32_t* left, uint32_t* flag) {
+// One lookup per blockIdx.y; sorts [0, L) are the inputs, [L, 2L) the tables.  rep[j] = 1 when row j repeats the
+// previous input value; left[j] = 1 when table entry j is NOT consumed by a first occurrence.  flag |= 2 when an
+// input value is not in the table.
+__global__ void __launch_bounds__(256) k_permute_flags(const uint32_t* sk_all, size_t n, size_t stride, uint32_t L, uint32_t* rep_all,
+                                                       uint32_t* left_all, uint32_t* flag) {
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
+  const uint32_t* sa = sk_all + 8 * (size_t)blockIdx.y * stride;
+  const uint32_t* st = sk_all + 8 * (size_t)(L + blockIdx.y) * stride;
+  uint32_t* rep = rep_all + (size_t)blockIdx.y * n;
+  uint32_t* left = left_all + (size_t)blockIdx.y * n;
   bool afirst = j == 0 || key_cmp(sa + 8 * j, sa + 8 * (j - 1)) != 0;
   rep[j] = afirst ? 0u : 1u;
   if (afirst) {
@@ -404,39 +457,49 @@ __global__ void __launch_bounds__(256) k_permute_flags(const uint32_t* sa, const
   }
   left[j] = (tfirst && used) ? 0u : 1u;
 }
+// totals[l] = number of repeated rows of lookup l (from the exclusive ranks + last flags); flag |= 4 on a mismatch
+__global__ void k_permute_totals(const uint32_t* rep, const uint32_t* rrank, const uint32_t* left, const uint32_t* lrank, size_t n,
+                                 uint32_t L, uint32_t* totals, uint32_t* flag) {
+  uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  size_t last = (size_t)l * n + n - 1;
+  uint32_t a = rrank[last] + rep[last], b = lrank[last] + left[last];
+  totals[l] = a;
+  if (a != b) atomicOr(flag, 4u);
+}
 // rpos[rrank[j]] = j for repeated rows
-__global__ void __launch_bounds__(256) k_permute_rpos(const uint32_t* rep, const uint32_t* rrank, uint32_t* rpos, size_t n) {
+__global__ void __launch_bounds__(256) k_permute_rpos(const uint32_t* rep_all, const uint32_t* rrank_all, uint32_t* rpos_all, size_t n) {
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
-  if (rep[j]) rpos[rrank[j]] = (uint32_t)j;
+  size_t o = (size_t)blockIdx.y * n;
+  if (rep_all[o + j]) rpos_all[o + rrank_all[o + j]] = (uint32_t)j;
 }
 // A'[j] = input[ia[j]];  S'[j] = A'[j] on first occurrences; leftover table entry with rank q goes to the
 // (m-1-q)-th repeated row (repeated_input_rows.pop()).  Values are gathered in Montgomery form from the sources.
-__global__ void __launch_bounds__(256) k_permute_write(const uint4* input, const uint4* table, const uint32_t* ia, const uint32_t* it,
-                                                       const uint32_t* rep, const uint32_t* left, const uint32_t* lrank,
-                                                       const uint32_t* rpos, const uint32_t* totals, uint4* pin, uint4* ptab, size_t n) {
+// input / table / pin / ptab are planes of L columns with `stride` elements each.
+__global__ void __launch_bounds__(256) k_permute_write(const uint4* input_all, const uint4* table_all, const uint32_t* idx_all,
+                                                       const uint32_t* rep_all, const uint32_t* left_all, const uint32_t* lrank_all,
+                                                       const uint32_t* rpos_all, const uint32_t* totals, uint32_t L, uint4* pin_all,
+                                                       uint4* ptab_all, size_t n, size_t stride) {
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
-  size_t s = ia[j];
+  const uint32_t l = blockIdx.y;
+  const size_t o = (size_t)l * n, so = 2 * (size_t)l * stride;
+  const uint4* input = input_all + so;
+  const uint4* table = table_all + so;
+  uint4* pin = pin_all + so;
+  uint4* ptab = ptab_all + so;
+  size_t s = idx_all[o + j];
   uint4 a0 = input[2 * s], a1 = input[2 * s + 1];
   pin[2 * j] = a0; pin[2 * j + 1] = a1;
-  if (!rep[j]) { ptab[2 * j] = a0; ptab[2 * j + 1] = a1; }
-  if (left[j]) {
-    uint32_t m = totals[0];                      // number of repeated rows
-    uint32_t q = lrank[j];
+  if (!rep_all[o + j]) { ptab[2 * j] = a0; ptab[2 * j + 1] = a1; }
+  if (left_all[o + j]) {
+    uint32_t m = totals[l];                      // number of repeated rows
+    uint32_t q = lrank_all[o + j];
     if (q < m) {
-      size_t row = rpos[m - 1 - q], t = it[j];
+      size_t row = rpos_all[o + m - 1 - q], t = idx_all[(size_t)(L + l) * n + j];
       ptab[2 * row] = table[2 * t]; ptab[2 * row + 1] = table[2 * t + 1];
     }
-  }
-}
-// totals[0] = number of ones in rep, totals[1] = number of ones in left (from the exclusive ranks + last flags)
-__global__ void k_permute_totals(const uint32_t* rep, const uint32_t* rrank, const uint32_t* left, const uint32_t* lrank, size_t n,
-                                 uint32_t* totals, uint32_t* flag) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    totals[0] = rrank[n - 1] + rep[n - 1];
-    totals[1] = lrank[n - 1] + left[n - 1];
-    if (totals[0] != totals[1]) atomicOr(flag, 4u);
   }
 }
 
