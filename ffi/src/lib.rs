@@ -28,6 +28,16 @@ pub struct zk_evaluator_desc {
     pub custom_gates: zk_graph, pub lookups: *const zk_graph, pub n_lookups: u32,
     pub perm_columns: *const zk_column, pub n_perm_columns: u32,
 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct zk_query { pub column: u32, pub rotation: i32 }
+#[repr(C)]
+pub struct zk_circuit_desc {
+    pub ev: zk_evaluator_desc,
+    pub lookup_inputs: *const zk_graph, pub lookup_tables: *const zk_graph,
+    pub advice_queries: *const zk_query, pub n_advice_queries: u32,
+    pub fixed_queries: *const zk_query, pub n_fixed_queries: u32,
+    pub transcript_repr: zk_fr,
+}
+#[repr(C)] pub struct zk_pkey { _p: [u8; 0] }
 pub const ZK_BASES_HOST: c_int = 0;
 pub const ZK_BASES_G: c_int = 1;
 pub const ZK_BASES_G_LAGRANGE: c_int = 2;
@@ -52,4 +62,15 @@ extern "C" {
     pub fn zk_evaluate_h(pk: *mut zk_pk, advice: *const *const zk_fr, instance: *const *const zk_fr, challenges: *const zk_fr,
                          y: *const zk_fr, beta: *const zk_fr, gamma: *const zk_fr, theta: *const zk_fr,
                          lookups: *const *const zk_fr, perm_products: *const *const zk_fr, out_ext: *mut zk_fr) -> c_int;
+    // keygen_vk + keygen_pk / create_proof with every n-sized loop on the device
+    pub fn zk_keygen(ctx: *mut zk_ctx, circuit: *const zk_circuit_desc, fixed_values: *const *const zk_fr, perm_mapping: *const u32,
+                     out: *mut *mut zk_pkey) -> c_int;
+    pub fn zk_pkey_destroy(pk: *mut zk_pkey);
+    pub fn zk_pkey_vk_commitments(pk: *const zk_pkey, fixed_commitments: *mut zk_g1_affine, perm_commitments: *mut zk_g1_affine) -> c_int;
+    pub fn zk_pkey_pk(pk: *mut zk_pkey) -> *mut zk_pk;
+    pub fn zk_proof_randoms(pk: *const zk_pkey) -> usize;
+    pub fn zk_proof_max_bytes(pk: *const zk_pkey) -> usize;
+    pub fn zk_create_proof(pk: *mut zk_pkey, advice_values: *const *const zk_fr, instance_values: *const *const zk_fr,
+                           instance_lens: *const u32, randoms: *const zk_fr, n_randoms: usize, proof: *mut u8, proof_cap: usize,
+                           proof_len: *mut usize) -> c_int;
 }
