@@ -421,6 +421,8 @@ class ProofWorkload:
         self.key = zk.ProverKey(self.params, self.circ, fixed, mapping)
         torch.cuda.synchronize()
         self.keygen_s = time.perf_counter() - t0
+        if self.key.aux_ctx is not None:
+            self.ctxs.append(self.key.aux_ctx)
         del fixed, mapping
         self.pk_stats = self._program_stats()
         rng = np.random.default_rng(seed)
@@ -612,7 +614,7 @@ def main():
                              "CPU verifier)" if full else "one create_proof hot path"),
               "shape": None, "l2": "inputs (>= 1 GiB of witness columns per step) exceed the 126 MB L2",
               "parallelism": "independent proofs per GPU (replicas)" if args.gpus > 1 else "1 GPU",
-              "streams": 1 if full else args.streams}
+              "streams": (1 if os.environ.get("ZK_PROVER_STREAMS") == "1" else 2) if full else args.streams}
 
     if args.impl == "reference":
         if rank != 0:

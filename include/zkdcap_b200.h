@@ -304,6 +304,9 @@ void zk_pkey_destroy(zk_pkey* pk);
 int zk_pkey_vk_commitments(const zk_pkey* pk, zk_g1_affine* fixed_commitments, zk_g1_affine* perm_commitments);
 /* The evaluate_h side of the key (for zk_evaluate_h* / zk_pk_program_stats). */
 zk_pk* zk_pkey_pk(zk_pkey* pk);
+/* The key's second context (= its second stream: the witness polynomials' transforms overlap the commitments
+ * there), for zk_ctx_timing* / zk_ctx_launch_count; NULL when ZK_PROVER_STREAMS=1.  Owned by the key. */
+zk_ctx* zk_pkey_aux_ctx(zk_pkey* pk);
 /* Number of Fr::random draws one create_proof makes for this circuit. */
 size_t zk_proof_randoms(const zk_pkey* pk);
 /* Upper bound of the proof size in bytes. */

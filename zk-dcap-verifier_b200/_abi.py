@@ -82,7 +82,7 @@ SYMBOLS = [
     "zk_divide_by_vanishing_poly_dev",
     "zk_pk_upload", "zk_pk_destroy", "zk_pk_domain", "zk_pk_program_stats",
     "zk_evaluate_h", "zk_evaluate_h_dev",
-    "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_proof_randoms", "zk_proof_max_bytes",
+    "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_pkey_aux_ctx", "zk_proof_randoms", "zk_proof_max_bytes",
     "zk_create_proof",
     "zk_field_op", "zk_bench_modmul", "zk_bench_imad",
 ]
@@ -150,6 +150,7 @@ def load():
         "zk_pkey_destroy": (None, [vp]),
         "zk_pkey_vk_commitments": (i32, [vp, vp, vp]),
         "zk_pkey_pk": (vp, [vp]),
+        "zk_pkey_aux_ctx": (vp, [vp]),
         "zk_proof_randoms": (sz, [vp]),
         "zk_proof_max_bytes": (sz, [vp]),
         "zk_create_proof": (i32, [vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz)]),

@@ -212,6 +212,14 @@ int launch_evalh(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr
 
 }  // namespace
 
+// ---- internal entry points for prover.cu: the witness cosets are produced by the caller (on another stream) -------
+// slot order: advice | instance | permutation z sets | lookup (Z, A', S') triples; 2^extended_k elements each
+char* zk_pk_witness_slot(zk_pk* pk, size_t slot) { return (char*)pk->d_witness + slot * zk_domain_ext_n(pk->dom) * 32; }
+int zk_evaluate_h_launch(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr* beta, const zk_fr* gamma,
+                         const zk_fr* theta, zk_fr* d_out_ext) {
+  return launch_evalh(pk, challenges, y, beta, gamma, theta, d_out_ext);
+}
+
 extern "C" int zk_evaluate_h_dev(zk_pk* pk, const zk_fr* const* d_advice, const zk_fr* const* d_instance,
                                  const zk_fr* challenges, const zk_fr* y, const zk_fr* beta, const zk_fr* gamma,
                                  const zk_fr* theta, const zk_fr* const* d_lookup, const zk_fr* const* d_perm_product,

@@ -403,6 +403,16 @@ extern "C" int zk_lagrange_to_coeff_dev(zk_domain* d, zk_fr* d_a, size_t count) 
   ZK_CUDA(ctx, cudaMemcpyAsync(d_a, d->work_a.p, count * d->n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
   return ZK_OK;
 }
+// out-of-place lagrange_to_coeff (internal: the prover keeps the Lagrange values for the commitment running on
+// another stream)
+int zk_lagrange_to_coeff_oop(zk_domain* d, const zk_fr* d_src, zk_fr* d_dst, size_t count) {
+  if (!d || !d_src || !d_dst) return ZK_ERR_ARG;
+  zk_ctx* ctx = d->ctx;
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!count) return ZK_OK;
+  PassConsts K; memset(&K, 0, sizeof K); K.post[0] = d->ifft_divisor;
+  return domain_ntt(d, d_src, d_dst, count, d->n, d->n, d->k, 1, 0, 1, K);
+}
 extern "C" int zk_coeff_to_lagrange_dev(zk_domain* d, zk_fr* d_a, size_t count) {
   if (!d || !d_a) return ZK_ERR_ARG;
   zk_ctx* ctx = d->ctx;

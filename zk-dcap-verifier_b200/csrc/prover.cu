@@ -25,6 +25,11 @@ extern "C" int zk_lagrange_to_coeff_dev(zk_domain* d, zk_fr* d_a, size_t count);
 extern "C" int zk_extended_to_coeff_dev(zk_domain* d, zk_fr* d_a_ext, zk_fr* d_out);
 extern "C" int zk_divide_by_vanishing_poly_dev(zk_domain* d, zk_fr* d_a_ext);
 extern "C" int zk_msm_batch_dev(zk_ctx* ctx, const zk_fr* d_scalars, int which, size_t n, size_t count, zk_g1* d_out);
+extern "C" int zk_coeff_to_extended_dev(zk_domain* d, const zk_fr* d_a, zk_fr* d_out_ext, size_t count);
+int zk_lagrange_to_coeff_oop(zk_domain* d, const zk_fr* d_src, zk_fr* d_dst, size_t count);
+char* zk_pk_witness_slot(zk_pk* pk, size_t slot);
+int zk_evaluate_h_launch(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr* beta, const zk_fr* gamma,
+                         const zk_fr* theta, zk_fr* d_out_ext);
 const void* zk_domain_twiddles(const zk_domain* d);
 size_t zk_domain_ext_n(const zk_domain* d);
 
@@ -32,6 +37,12 @@ struct zk_pkey {
   zk_ctx* ctx = nullptr;
   zk_pk* pk = nullptr;             // evaluate_h side (cosets, compiled program); owns its own domain
   zk_domain* dom = nullptr;
+  // second stream: every lagrange_to_coeff / coeff_to_extended of the witness polynomials runs here, overlapping the
+  // commitments and the lookup / permutation kernels of the main stream (they only meet again at evaluate_h)
+  zk_ctx* ctxB = nullptr;
+  zk_domain* domB = nullptr;
+  cudaEvent_t ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, ev_done = nullptr;
+  char *d_advice_polys = nullptr, *d_lookup_polys = nullptr, *d_perm_z_polys = nullptr;
   uint32_t k = 0, degree = 0, bf = 0, n_fixed = 0, n_advice = 0, n_instance = 0, n_challenges = 0, n_lookups = 0;
   uint32_t n_perm = 0, n_sets = 0, chunk = 0;
   size_t n = 0, ext_n = 0;
@@ -325,11 +336,17 @@ extern "C" void zk_pkey_destroy(zk_pkey* K) {
   cudaStreamSynchronize(K->ctx->stream);
   for (void* p : K->allocs) cudaFree(p);
   for (char* p : K->d_setacc) cudaFree(p);
+  if (K->ctxB) cudaStreamSynchronize(K->ctxB->stream);
+  for (auto& e : K->ev_in) if (e) cudaEventDestroy(e);
+  if (K->ev_done) cudaEventDestroy(K->ev_done);
   if (K->pk) zk_pk_destroy(K->pk);
   if (K->dom) zk_domain_destroy(K->dom);
+  if (K->domB) zk_domain_destroy(K->domB);
+  if (K->ctxB) zk_ctx_destroy(K->ctxB);
   delete K;
 }
 extern "C" zk_pk* zk_pkey_pk(zk_pkey* K) { return K ? K->pk : nullptr; }
+extern "C" zk_ctx* zk_pkey_aux_ctx(zk_pkey* K) { return K ? K->ctxB : nullptr; }
 extern "C" size_t zk_proof_randoms(const zk_pkey* K) {
   if (!K) return 0;
   size_t a = K->n_advice, l = K->n_lookups, bf = K->bf;
@@ -380,6 +397,14 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
   K->transcript_repr = f_from_abi<Fr>(&cd->transcript_repr);
   KG(zk_domain_create(ctx, D.degree, D.k, &K->dom));
   K->ext_n = zk_domain_ext_n(K->dom);
+  if (!(getenv("ZK_PROVER_STREAMS") && atoi(getenv("ZK_PROVER_STREAMS")) == 1)) {
+    int r = zk_ctx_create(ctx->device, nullptr, &K->ctxB);
+    if (r != ZK_OK) { ctx->err = "zk_keygen: cannot create the second stream"; zk_pkey_destroy(K); return r; }
+    r = zk_domain_create(K->ctxB, D.degree, D.k, &K->domB);
+    if (r != ZK_OK) { ctx->err = "zk_keygen: " + K->ctxB->err; zk_pkey_destroy(K); return r; }
+    for (auto& e : K->ev_in) KG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    KG_CUDA(cudaEventCreateWithFlags(&K->ev_done, cudaEventDisableTiming));
+  }
   zk_fr dc[8];
   zk_domain_constants(K->dom, dc);
   K->omega = f_from_abi<Fr>(&dc[0]); K->omega_inv = f_from_abi<Fr>(&dc[1]);
@@ -416,6 +441,9 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
   KG(dev_alloc(K, &K->d_fixed_values, D.n_fixed * nb)); KG(dev_alloc(K, &K->d_fixed_polys, D.n_fixed * nb));
   KG(dev_alloc(K, &K->d_sigma_values, K->n_perm * nb)); KG(dev_alloc(K, &K->d_sigma_polys, K->n_perm * nb));
   KG(dev_alloc(K, &K->d_advice, D.n_advice * nb));
+  KG(dev_alloc(K, &K->d_advice_polys, D.n_advice * nb));
+  KG(dev_alloc(K, &K->d_lookup_polys, (size_t)D.n_lookups * 3 * nb));
+  KG(dev_alloc(K, &K->d_perm_z_polys, K->n_sets * nb));
   KG(dev_alloc(K, &K->d_instance, D.n_instance * nb)); KG(dev_alloc(K, &K->d_instance_polys, D.n_instance * nb));
   KG(dev_alloc(K, &K->d_lookup, (size_t)D.n_lookups * 5 * nb));
   KG(dev_alloc(K, &K->d_perm_z, K->n_sets * nb));
@@ -550,6 +578,27 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   const uint4* tw = (const uint4*)zk_domain_twiddles(dom);
   const uint32_t tw_shift = zk_domain_extended_k(dom) - K->k;
   const size_t half_ext = K->ext_n >> 1;
+  // Work for the second stream: `body(domain)` is enqueued there after everything queued so far on the main stream.
+  // With per-kernel timing on (the breakdown pass of bench.py) the two streams take turns so that kernel times do
+  // not overlap; with ZK_PROVER_STREAMS=1 there is no second stream and the work runs in line.
+  zk_ctx* cB = K->ctxB;
+  const bool serialize = ctx->timing;
+  if (cB) cB->timing = ctx->timing;
+  auto side = [&](int ev, auto&& fn) -> int {
+    if (!cB) return fn(dom);
+    if (serialize) ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, cudaEventRecord(K->ev_in[ev], ctx->stream));
+    ZK_CUDA(ctx, cudaStreamWaitEvent(cB->stream, K->ev_in[ev], 0));
+    int r = fn(K->domB);
+    if (r != ZK_OK) { ctx->err = cB->err; return r; }
+    if (serialize) ZK_CUDA(ctx, cudaStreamSynchronize(cB->stream));
+    return ZK_OK;
+  };
+  const uint32_t I_ = K->n_instance;
+  auto slot_adv = [&](uint32_t i) { return (zk_fr*)zk_pk_witness_slot(K->pk, i); };
+  auto slot_ins = [&](uint32_t i) { return (zk_fr*)zk_pk_witness_slot(K->pk, (size_t)K->n_advice + i); };
+  auto slot_z = [&](uint32_t s_) { return (zk_fr*)zk_pk_witness_slot(K->pk, (size_t)K->n_advice + I_ + s_); };
+  auto slot_lk = [&](uint32_t l, uint32_t t) { return (zk_fr*)zk_pk_witness_slot(K->pk, (size_t)K->n_advice + I_ + K->n_sets + 3 * (size_t)l + t); };
 
   // vk.hash_into; instances (KZG: the values are absorbed as scalars)
   tr.common_scalar(K->transcript_repr);
@@ -565,6 +614,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   if (K->n_instance) {
     ZK_CUDA(ctx, cudaMemcpyAsync(K->d_instance_polys, K->d_instance, K->n_instance * nb, cudaMemcpyDeviceToDevice, ctx->stream));
     ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)K->d_instance_polys, K->n_instance));
+    ZK_TRY(zk_coeff_to_extended_dev(dom, (const zk_fr*)K->d_instance_polys, slot_ins(0), K->n_instance));
   }
 
   // ---- advice: upload, blind, commit ---------------------------------------------------------------------------------
@@ -574,6 +624,10 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   }
   for (uint32_t i = 0; i < A; i++) ZK_TRY(draw_to(K->d_advice + i * nb + usable * 32, bf + 1));
   rpos += A;                                           // one Blind per column: drawn, unused by KZG
+  if (A) ZK_TRY(side(0, [&](zk_domain* d) -> int {       // advice_polys and their cosets, concurrently with the commitments
+    ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)K->d_advice, (zk_fr*)K->d_advice_polys, A));
+    return zk_coeff_to_extended_dev(d, (const zk_fr*)K->d_advice_polys, slot_adv(0), A);
+  }));
   {
     std::vector<HostPoint> pts;
     if (A) ZK_TRY(commit(K, K->d_advice, A, ZK_BASES_G_LAGRANGE, &pts));
@@ -592,6 +646,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   // d_lookup holds five planes of L columns: 0 compressed inputs, 1 compressed tables, 2 A', 3 S', 4 Z -- so that the
   // commitments, transforms and sorts of all lookup arguments are single batched calls.
   auto lk = [&](uint32_t l, int which) { return K->d_lookup + ((size_t)which * L + l) * nb; };
+  auto lkp = [&](uint32_t l, int which) { return K->d_lookup_polys + ((size_t)which * L + l) * nb; };   // 0 A', 1 S', 2 Z (coefficients)
   if (L) {
     std::vector<const void*> cols(K->CL.n_slots);
     for (uint32_t i = 0; i < K->n_fixed; i++) cols[K->CL.prog.off_fixed + i] = K->d_fixed_values + i * nb;
@@ -612,6 +667,14 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       ZK_TRY(draw_to(lk(l, 3) + usable * 32, bf + 1));
       rpos += 2;
     }
+    ZK_TRY(side(1, [&](zk_domain* d) -> int {          // A', S' -> coefficient forms and cosets
+      ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)lk(0, 2), (zk_fr*)lkp(0, 0), 2 * (size_t)L));
+      for (uint32_t l = 0; l < L; l++) {
+        ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)lkp(l, 0), slot_lk(l, 1), 1));
+        ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)lkp(l, 1), slot_lk(l, 2), 1));
+      }
+      return ZK_OK;
+    }));
     uint32_t flags = 0;
     ZK_CUDA(ctx, cudaMemcpyAsync(&flags, K->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -660,10 +723,13 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       ZK_TRY(draw_to(K->d_perm_z + s * nb + (n - bf) * 32, bf));
       rpos += 1;
     }
+    ZK_TRY(side(2, [&](zk_domain* d) -> int {
+      ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)K->d_perm_z, (zk_fr*)K->d_perm_z_polys, NS));
+      return zk_coeff_to_extended_dev(d, (const zk_fr*)K->d_perm_z_polys, slot_z(0), NS);
+    }));
     std::vector<HostPoint> pts;
     ZK_TRY(commit(K, K->d_perm_z, NS, ZK_BASES_G_LAGRANGE, &pts));
     ZK_TRY(write_points(pts));
-    ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)K->d_perm_z, NS));
   }
 
   // ---- lookups: commit_product -------------------------------------------------------------------------------------------------
@@ -677,10 +743,14 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       ZK_TRY(draw_to(lk(l, 4) + (n - bf) * 32, bf));
       rpos += 1;
     }
+    ZK_TRY(side(3, [&](zk_domain* d) -> int {
+      ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)lk(0, 4), (zk_fr*)lkp(0, 2), L));
+      for (uint32_t l = 0; l < L; l++) ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)lkp(l, 2), slot_lk(l, 0), 1));
+      return ZK_OK;
+    }));
     std::vector<HostPoint> pts;
     ZK_TRY(commit(K, lk(0, 4), L, ZK_BASES_G_LAGRANGE, &pts));
     ZK_TRY(write_points(pts));
-    ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)lk(0, 2), 3 * (size_t)L));       // A', S', Z planes -> coefficient form
   }
 
   // ---- vanishing.commit: random polynomial ------------------------------------------------------------------------------------
@@ -693,19 +763,17 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   }
   Fr y = tr.squeeze_challenge();
 
-  // ---- h(X) ----------------------------------------------------------------------------------------------------------------------
-  if (A) ZK_TRY(zk_lagrange_to_coeff_dev(dom, (zk_fr*)K->d_advice, A));
+  // ---- h(X): every coset is in place once the second stream has drained ----------------------------------------------
   {
-    std::vector<const zk_fr*> ap(A + 1), ip(K->n_instance + 1), lp(3 * L + 1), zp(K->n_sets + 1);
-    for (uint32_t i = 0; i < A; i++) ap[i] = (const zk_fr*)(K->d_advice + i * nb);
-    for (uint32_t i = 0; i < K->n_instance; i++) ip[i] = (const zk_fr*)(K->d_instance_polys + i * nb);
-    for (uint32_t l = 0; l < L; l++) { lp[3 * l] = (const zk_fr*)lk(l, 4); lp[3 * l + 1] = (const zk_fr*)lk(l, 2); lp[3 * l + 2] = (const zk_fr*)lk(l, 3); }
-    for (uint32_t s = 0; s < K->n_sets; s++) zp[s] = (const zk_fr*)(K->d_perm_z + s * nb);
+    if (cB) {
+      ZK_CUDA(ctx, cudaEventRecord(K->ev_done, cB->stream));
+      ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, K->ev_done, 0));
+    }
     std::vector<zk_fr> ch(K->n_challenges + 1);
     for (uint32_t i = 0; i < K->n_challenges; i++) f_to_abi(challenges[i], &ch[i]);
     zk_fr yh, bh, gh, th;
     f_to_abi(y, &yh); f_to_abi(beta, &bh); f_to_abi(gamma, &gh); f_to_abi(theta, &th);
-    ZK_TRY(zk_evaluate_h_dev(K->pk, ap.data(), ip.data(), ch.data(), &yh, &bh, &gh, &th, lp.data(), zp.data(), (zk_fr*)K->d_hext));
+    ZK_TRY(zk_evaluate_h_launch(K->pk, ch.data(), &yh, &bh, &gh, &th, (zk_fr*)K->d_hext));
   }
   // vanishing.construct
   ZK_TRY(zk_divide_by_vanishing_poly_dev(dom, (zk_fr*)K->d_hext));
@@ -733,7 +801,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   struct EvalReq { const void* poly; uint32_t point; };
   std::vector<EvalReq> reqs;
   auto req = [&](const void* poly, int32_t r) { reqs.push_back({poly, point_of(r)}); };
-  for (auto& q : K->advice_queries) req(K->d_advice + q.column * nb, q.rotation);
+  for (auto& q : K->advice_queries) req(K->d_advice_polys + q.column * nb, q.rotation);
   for (auto& q : K->fixed_queries) req(K->d_fixed_polys + q.column * nb, q.rotation);
   // vanishing.evaluate: h(X) = sum_i xn^i h_i(X) (opened, not written); random_eval
   {
@@ -746,11 +814,11 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   for (uint32_t i = 0; i < K->n_perm; i++) req(K->d_sigma_polys + i * nb, 0);
   const int32_t last_rot = -(int32_t)(bf + 1);
   for (uint32_t s = 0; s < K->n_sets; s++) {
-    req(K->d_perm_z + s * nb, 0); req(K->d_perm_z + s * nb, 1);
-    if (s + 1 < K->n_sets) req(K->d_perm_z + s * nb, last_rot);
+    req(K->d_perm_z_polys + s * nb, 0); req(K->d_perm_z_polys + s * nb, 1);
+    if (s + 1 < K->n_sets) req(K->d_perm_z_polys + s * nb, last_rot);
   }
   for (uint32_t l = 0; l < L; l++) {
-    req(lk(l, 4), 0); req(lk(l, 4), 1); req(lk(l, 2), 0); req(lk(l, 2), -1); req(lk(l, 3), 0);
+    req(lkp(l, 2), 0); req(lkp(l, 2), 1); req(lkp(l, 0), 0); req(lkp(l, 0), -1); req(lkp(l, 1), 0);
   }
   const size_t n_written = reqs.size();
   req(K->d_hpoly, 0);                                  // the prover's own evaluation of h (ProverQuery::get_eval)
@@ -786,15 +854,15 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     Fr h_eval = evals[e++];
     const uint32_t p0 = point_of(0);
     for (size_t i = 0; i < K->advice_queries.size(); i++)
-      queries.push_back({K->d_advice + K->advice_queries[i].column * nb, point_of(K->advice_queries[i].rotation), adv_e[i]});
+      queries.push_back({K->d_advice_polys + K->advice_queries[i].column * nb, point_of(K->advice_queries[i].rotation), adv_e[i]});
     for (uint32_t s = 0; s < K->n_sets; s++) {
-      queries.push_back({K->d_perm_z + s * nb, p0, pe[s].x});
-      queries.push_back({K->d_perm_z + s * nb, point_of(1), pe[s].next});
+      queries.push_back({K->d_perm_z_polys + s * nb, p0, pe[s].x});
+      queries.push_back({K->d_perm_z_polys + s * nb, point_of(1), pe[s].next});
     }
-    for (uint32_t s = K->n_sets; s-- > 0;) if (s + 1 < K->n_sets) queries.push_back({K->d_perm_z + s * nb, point_of(last_rot), pe[s].last});
+    for (uint32_t s = K->n_sets; s-- > 0;) if (s + 1 < K->n_sets) queries.push_back({K->d_perm_z_polys + s * nb, point_of(last_rot), pe[s].last});
     for (uint32_t l = 0; l < L; l++) {
-      queries.push_back({lk(l, 4), p0, le[l][0]}); queries.push_back({lk(l, 2), p0, le[l][2]}); queries.push_back({lk(l, 3), p0, le[l][4]});
-      queries.push_back({lk(l, 2), point_of(-1), le[l][3]}); queries.push_back({lk(l, 4), point_of(1), le[l][1]});
+      queries.push_back({lkp(l, 2), p0, le[l][0]}); queries.push_back({lkp(l, 0), p0, le[l][2]}); queries.push_back({lkp(l, 1), p0, le[l][4]});
+      queries.push_back({lkp(l, 0), point_of(-1), le[l][3]}); queries.push_back({lkp(l, 2), point_of(1), le[l][1]});
     }
     for (size_t i = 0; i < K->fixed_queries.size(); i++)
       queries.push_back({K->d_fixed_polys + K->fixed_queries[i].column * nb, point_of(K->fixed_queries[i].rotation), fix_e[i]});

@@ -63,6 +63,13 @@ class Context:
         self.h = h
         self.device = device
 
+    @classmethod
+    def borrowed(cls, handle, device=0):
+        """Wrap a zk_ctx owned by another object (e.g. a key's second stream) for timing / launch statistics."""
+        self = cls.__new__(cls)
+        self.lib, self.h, self.device, self._borrowed = _abi.load(), C.c_void_p(handle), device, True
+        return self
+
     def check(self, rc):
         if rc < 0:
             raise ZkError("%s (status %d)" % (self.lib.zk_last_error(self.h).decode(), rc))
@@ -70,7 +77,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.zk_ctx_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                self.lib.zk_ctx_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -619,6 +627,8 @@ class ProverKey:
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.zk_keygen(self.ctx.h, C.byref(self._cd), tf, _ptr(mp), C.byref(h)))
         self.h = h
+        aux = self.ctx.lib.zk_pkey_aux_ctx(h)
+        self.aux_ctx = Context.borrowed(aux, self.ctx.device) if aux else None
         self.randoms_needed = int(self.ctx.lib.zk_proof_randoms(h))
         self.max_proof_bytes = int(self.ctx.lib.zk_proof_max_bytes(h))
 
