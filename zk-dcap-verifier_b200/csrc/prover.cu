@@ -42,6 +42,7 @@ struct zk_pkey {
   zk_ctx* ctxB = nullptr;
   zk_domain* domB = nullptr;
   cudaEvent_t ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, ev_done = nullptr;
+  cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};   // groups of advice columns uploaded on the copy stream
   char *d_advice_polys = nullptr, *d_lookup_polys = nullptr, *d_perm_z_polys = nullptr;
   uint32_t k = 0, degree = 0, bf = 0, n_fixed = 0, n_advice = 0, n_instance = 0, n_challenges = 0, n_lookups = 0;
   uint32_t n_perm = 0, n_sets = 0, chunk = 0;
@@ -187,9 +188,11 @@ int kate_divide(zk_pkey* K, char* a, uint32_t slot_z, uint32_t slot_zinv) {
 
 // commitments: `count` contiguous polynomials -> affine points on the host (normalised Jacobian from the MSM)
 struct HostPoint { Fq x, y; bool identity; };
-int commit(zk_pkey* K, const char* d_polys, size_t count, int which, std::vector<HostPoint>* out) {
+int commit_enqueue(zk_pkey* K, const char* d_polys, size_t count, int which, size_t slot) {
+  return zk_msm_batch_dev(K->ctx, (const zk_fr*)d_polys, which, K->n, count, (zk_g1*)K->d_points + slot);
+}
+int commit_fetch(zk_pkey* K, size_t count, std::vector<HostPoint>* out) {
   zk_ctx* ctx = K->ctx;
-  ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, count, (zk_g1*)K->d_points));
   std::vector<zk_g1> h(count);
   ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), K->d_points, count * sizeof(zk_g1), cudaMemcpyDeviceToHost, ctx->stream));
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -200,6 +203,15 @@ int commit(zk_pkey* K, const char* d_polys, size_t count, int which, std::vector
     out->push_back(q);
   }
   return ZK_OK;
+}
+int commit(zk_pkey* K, const char* d_polys, size_t count, int which, std::vector<HostPoint>* out) {
+  ZK_TRY(commit_enqueue(K, d_polys, count, which, 0));
+  return commit_fetch(K, count, out);
+}
+bool is_device_pointer(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
 // ---- lookup: permute_expression_pair on the device, all lookup arguments at once --------------------------------------
@@ -338,6 +350,7 @@ extern "C" void zk_pkey_destroy(zk_pkey* K) {
   for (char* p : K->d_setacc) cudaFree(p);
   if (K->ctxB) cudaStreamSynchronize(K->ctxB->stream);
   for (auto& e : K->ev_in) if (e) cudaEventDestroy(e);
+  for (auto& e : K->ev_copy) if (e) cudaEventDestroy(e);
   if (K->ev_done) cudaEventDestroy(K->ev_done);
   if (K->pk) zk_pk_destroy(K->pk);
   if (K->dom) zk_domain_destroy(K->dom);
@@ -397,6 +410,7 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
   K->transcript_repr = f_from_abi<Fr>(&cd->transcript_repr);
   KG(zk_domain_create(ctx, D.degree, D.k, &K->dom));
   K->ext_n = zk_domain_ext_n(K->dom);
+  for (auto& e : K->ev_copy) KG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (!(getenv("ZK_PROVER_STREAMS") && atoi(getenv("ZK_PROVER_STREAMS")) == 1)) {
     int r = zk_ctx_create(ctx->device, nullptr, &K->ctxB);
     if (r != ZK_OK) { ctx->err = "zk_keygen: cannot create the second stream"; zk_pkey_destroy(K); return r; }
@@ -618,19 +632,41 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   }
 
   // ---- advice: upload, blind, commit ---------------------------------------------------------------------------------
-  for (uint32_t i = 0; i < A; i++) {
+  // Host-resident columns are uploaded in groups on the copy stream; the commitments (main stream) and the
+  // coefficient forms / cosets (second stream) of a group start as soon as that group has arrived.
+  for (uint32_t i = 0; i < A; i++)
     if (!advice_values[i]) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: null advice column");
-    ZK_CUDA(ctx, cudaMemcpyAsync(K->d_advice + i * nb, advice_values[i], usable * 32, cudaMemcpyDefault, ctx->stream));
-  }
-  for (uint32_t i = 0; i < A; i++) ZK_TRY(draw_to(K->d_advice + i * nb + usable * 32, bf + 1));
-  rpos += A;                                           // one Blind per column: drawn, unused by KZG
-  if (A) ZK_TRY(side(0, [&](zk_domain* d) -> int {       // advice_polys and their cosets, concurrently with the commitments
-    ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)K->d_advice, (zk_fr*)K->d_advice_polys, A));
-    return zk_coeff_to_extended_dev(d, (const zk_fr*)K->d_advice_polys, slot_adv(0), A);
-  }));
   {
+    const bool split = A >= 8 && n >= ((size_t)1 << 14) && !is_device_pointer(advice_values[0]) && !getenv("ZK_PROVER_NO_SPLIT_UPLOAD");
+    const uint32_t G = split ? 4 : 1;
+    cudaStream_t up = ctx->stream;
+    if (split) { ZK_TRY(zk_copy_stream(ctx)); up = ctx->copy_stream; }
+    const size_t r_adv = rpos;
+    rpos += (size_t)A * (bf + 1) + A;                    // blinding rows of every column, then one (unused) Blind per column
+    auto gb = [&](uint32_t g) { return (uint32_t)((uint64_t)A * g / G); };
+    for (uint32_t g = 0; g < G; g++) {
+      for (uint32_t i = gb(g); i < gb(g + 1); i++) {
+        ZK_CUDA(ctx, cudaMemcpyAsync(K->d_advice + i * nb, advice_values[i], usable * 32, cudaMemcpyDefault, up));
+        ZK_CUDA(ctx, cudaMemcpyAsync(K->d_advice + i * nb + usable * 32, randoms + r_adv + (size_t)i * (bf + 1), (size_t)(bf + 1) * 32,
+                                     cudaMemcpyDefault, up));
+      }
+      if (split) ZK_CUDA(ctx, cudaEventRecord(K->ev_copy[g], up));
+    }
+    for (uint32_t g = 0; g < G; g++) {
+      const uint32_t i0 = gb(g), cnt = gb(g + 1) - gb(g);
+      if (!cnt) continue;
+      if (split) {
+        ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, K->ev_copy[g], 0));
+        if (serialize) ZK_CUDA(ctx, cudaStreamSynchronize(up));
+      }
+      ZK_TRY(side(0, [&](zk_domain* d) -> int {          // advice_polys and their cosets, concurrently with the commitments
+        ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)(K->d_advice + i0 * nb), (zk_fr*)(K->d_advice_polys + i0 * nb), cnt));
+        return zk_coeff_to_extended_dev(d, (const zk_fr*)(K->d_advice_polys + i0 * nb), slot_adv(i0), cnt);
+      }));
+      ZK_TRY(commit_enqueue(K, K->d_advice + i0 * nb, cnt, ZK_BASES_G_LAGRANGE, i0));
+    }
     std::vector<HostPoint> pts;
-    if (A) ZK_TRY(commit(K, K->d_advice, A, ZK_BASES_G_LAGRANGE, &pts));
+    if (A) ZK_TRY(commit_fetch(K, A, &pts));
     ZK_TRY(write_points(pts));
   }
   std::vector<Fr> challenges(K->n_challenges);
