@@ -433,21 +433,59 @@ __global__ void __launch_bounds__(128) k_xyzz_segsum(const uint4* in, size_t row
   for (uint32_t i = a; i < b; i++) acc = acc.add(XYZZ::load(in + 8 * (row * len + i)));
   acc.store(out + 8 * tid);
 }
+// ---- 4': reduction by chunked running sums ------------------------------------------------------------
+// sum_v (v + w0) * X_v over a row of `len` points: the row is cut into chunks of m; thread (row, j) walks its chunk from
+// the top, running += X, T += running, which leaves  T_j = sum_i (i + w0) X_(jm+i)  (i = position in the chunk) and
+// S_j = sum_i X_(jm+i)  after 2 additions per point.  Then  sum = sum_j T_j + m * sum_j j * S_j : the first term is a
+// plain sum, the second the same problem on the m-times shorter row S with w0 = 0.  ~2.1 additions per bucket in total
+// instead of c/2 for the bit-sliced reduction above.
+__global__ void __launch_bounds__(128) k_msm_chunk_sums(const uint4* in, size_t rows, uint32_t len, uint32_t m, uint32_t w0,
+                                                        uint32_t nch, uint4* outT, uint4* outS) {
+  size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (tid >= rows * nch) return;
+  size_t row = tid / nch;
+  uint32_t j = (uint32_t)(tid % nch);
+  uint32_t lo = j * m, hi = lo + m < len ? lo + m : len;
+  const uint4* base = in + 8 * (row * len);
+  XYZZ run = XYZZ::identity(), T = XYZZ::identity();
+  // positions hi-1 .. lo+1 carry weights >= 1 for either w0; position lo carries weight w0
+  for (uint32_t v = hi; v-- > lo + 1;) {
+    run = run.add(XYZZ::load(base + 8 * (size_t)v));
+    T = T.add(run);
+  }
+  run = run.add(XYZZ::load(base + 8 * (size_t)lo));
+  if (w0) T = T.add(run);
+  T.store(outT + 8 * tid);
+  run.store(outS + 8 * tid);
+}
+// R[row] = A_0 + m_0 * (A_1 + m_1 * (A_2 + ...)),  A_l = plain sum of level l's T row; lg[l] = log2 m_l
+struct LevelPlan { const uint4* A[8]; uint32_t lg[8]; uint32_t levels; };
+__global__ void __launch_bounds__(128) k_msm_combine_levels(LevelPlan L, size_t rows, uint4* out) {
+  size_t row = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  XYZZ acc = XYZZ::load(L.A[L.levels - 1] + 8 * row);
+  for (int l = (int)L.levels - 2; l >= 0; l--) {
+    for (uint32_t d = 0; d < L.lg[l]; d++) acc = acc.dbl();
+    acc = acc.add(XYZZ::load(L.A[l] + 8 * row));
+  }
+  acc.store(out + 8 * row);
+}
+
 // final: per MSM the G*c partial sums S_e (weight 2^e, e = g*c + k) are folded by a binary tree,
 // V[2j] += 2^(stride) * V[2j+1], so the serial chain is (items - 1) doublings + log2(items) additions instead
 // of items doublings + items additions; one CTA per MSM, the items live in shared memory.
 constexpr uint32_t kFinalMaxItems = 512;
-__global__ void __launch_bounds__(256) k_msm_final(const uint4* sums, MsmPlan P, uint4* out) {
+// `items` values V_e per MSM with weight 2^(shift * e)
+__global__ void __launch_bounds__(256) k_msm_final(const uint4* sums, uint32_t items, uint32_t shift, uint4* out) {
   extern __shared__ uint4 fsm[];
   size_t msm = blockIdx.x;
-  const uint32_t items = P.G * P.c;
   const uint4* s = sums + 8 * (msm * items);
   for (uint32_t q = threadIdx.x; q < items * 8; q += blockDim.x) fsm[q] = s[q];
   __syncthreads();
   for (uint32_t stride = 1; stride < items; stride <<= 1) {
     for (uint32_t j = threadIdx.x; (2 * j + 1) * stride < items; j += blockDim.x) {
       XYZZ hi = XYZZ::load(fsm + 8 * ((2 * j + 1) * stride));
-      for (uint32_t d = 0; d < stride; d++) hi = hi.dbl();
+      for (uint32_t d = 0; d < stride * shift; d++) hi = hi.dbl();
       XYZZ lo = XYZZ::load(fsm + 8 * (2 * j * stride));
       lo.add(hi).store(fsm + 8 * (2 * j * stride));
     }
@@ -516,11 +554,23 @@ MsmPlan make_plan(size_t n, size_t count, bool table, uint32_t table_c, size_t s
   return P;
 }
 
+// ZK_MSM_REDUCE=chunk selects the chunked running-sum reduction (fewer additions, longer dependent chains);
+// the default is the bit-sliced one, which measured faster at the default window width.
+bool use_chunk_reduce() {
+  const char* v = getenv("ZK_MSM_REDUCE");
+  return v && strcmp(v, "chunk") == 0;
+}
+
 uint32_t table_window_bits(uint32_t k) {
   if (const char* v = getenv("ZK_MSM_C")) { int c = atoi(v); if (c >= 2 && c <= 22) return (uint32_t)c; }
   int c = (int)k - 3;
   if (c < 4) c = 4;
   if (c > 16) c = 16;
+  // W = floor(254/c) + 1 moves in steps: one more bit can remove two windows (c = 14 -> 15: 19 -> 17).  Take it when the
+  // modelled work (10 multiplications per bucket addition, c/2 * 14 per bucket in the reduction) drops by > 3 %
+  // (measured: k = 17 complete proof 53.0 -> 50.6 ms; k = 16, 18, 19 within 1 % either way).
+  auto work = [&](int cc) { return (double)(254 / cc + 1) * (double)((size_t)1 << k) * 10.0 + (double)((size_t)1 << (cc - 1)) * cc * 7.0; };
+  if (c < 16 && work(c + 1) < 0.97 * work(c)) c++;
   return (uint32_t)c;
 }
 
@@ -653,6 +703,45 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
     ZK_LAUNCH(ctx, "msm_acc_partials", k_msm_acc_partials_tail, (unsigned)P.count, kTailThreads, 0, ida, pta, idb, ptb, n_in,
               P.nb, buckets, stride_in, stride_out);
   }
+  if (use_chunk_reduce()) {
+    // chunked running sums: level 0 over the buckets of every (msm, group) row, then over the rows of chunk totals
+    const size_t rws = P.count * P.G;
+    const uint32_t m0 = getenv("ZK_MSM_M0") ? (uint32_t)atoi(getenv("ZK_MSM_M0")) : 8, m1 = 8, sseg = 8;
+    LevelPlan L; memset(&L, 0, sizeof L);
+    // scratch inside r1 / r2: each level needs T and S rows of nch points and the plain-sum ladder of T
+    uint4* cur = buckets; uint32_t len = (uint32_t)(P.B * P.S);
+    char* arena = (char*)r1; size_t arena_off = 0;
+    auto take = [&](size_t points) { uint4* p = (uint4*)(arena + arena_off); arena_off += ((points * 128 + 255) & ~(size_t)255); return p; };
+    uint32_t level = 0, w0 = 1;
+    while (true) {
+      uint32_t m = level == 0 ? m0 : m1;
+      uint32_t nch = (len + m - 1) / m;
+      uint4* T = take(rws * nch); uint4* S = take(rws * nch);
+      ZK_LAUNCH(ctx, "msm_reduce_bits", k_msm_chunk_sums, zk_div_up(rws * nch, 128), 128, 0, (const uint4*)cur, rws, len, m, w0, nch, T, S);
+      // plain sum of the T row
+      uint32_t tl = nch; uint4* tsrc = T;
+      while (tl > 1) {
+        uint32_t ns = (tl + sseg - 1) / sseg;
+        uint4* tdst = take(rws * ns);
+        ZK_LAUNCH(ctx, "msm_segsum", k_xyzz_segsum, zk_div_up(rws * ns, 128), 128, 0, (const uint4*)tsrc, rws, tl, sseg, ns, tdst);
+        tsrc = tdst; tl = ns;
+      }
+      L.A[level] = tsrc;
+      uint32_t lg = 0; while ((1u << lg) < m) lg++;
+      L.lg[level] = lg;
+      level++;
+      if (nch == 1 || level == 8) { if (nch != 1) ZK_FAIL(ctx, ZK_ERR_ARG, "msm: reduction needs more than 8 levels"); break; }
+      cur = S; len = nch; w0 = 0;
+    }
+    L.levels = level;
+    if (arena_off + rws * 128 + 256 > off_sa_id - off_r1) ZK_FAIL(ctx, ZK_ERR_STATE, "msm: reduction arena overflow");
+    uint4* R = take(rws);
+    ZK_LAUNCH(ctx, "msm_final", k_msm_combine_levels, zk_div_up(rws, 128), 128, 0, L, rws, R);
+    size_t fsmem = (size_t)P.G * 128;
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFinalMaxItems * 128)));
+    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)R, P.G, P.c, (uint4*)d_out);
+    return ZK_OK;
+  }
   size_t rows = P.count * P.G * P.c;
   dim3 gr(zk_div_up((size_t)P.G * P.c * nseg1, 128), (unsigned)P.count);
   ZK_LAUNCH(ctx, "msm_reduce_bits", k_msm_reduce_bits, gr, 128, 0, (const uint4*)buckets, P, seg1, nseg1, r1);
@@ -667,7 +756,7 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   {
     size_t fsmem = (size_t)P.G * P.c * 128;
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFinalMaxItems * 128)));
-    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)src, P, (uint4*)d_out);
+    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)src, P.G * P.c, 1u, (uint4*)d_out);
   }
   return ZK_OK;
 }
