@@ -72,7 +72,20 @@ __device__ __forceinline__ void sts_fr(uint4* p0, uint4* p1, uint32_t e, const F
 #ifndef ZK_NTT_MIN_CTAS
 #define ZK_NTT_MIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(kThreads, ZK_NTT_MIN_CTAS) k_ntt_pass(PassArgs A, PassConsts K) {
+// one butterfly output of the DIF network: (x - y) * omega^ex, resp. (y - x) * omega^(N/2 - ex) = (x - y) * omega^-ex
+__device__ __forceinline__ Fr bf_diff(const Fr& x, const Fr& y, size_t ex, const PassArgs& A, uint32_t halfN_sh) {
+  if (ex == 0) return x - y;
+  if (!A.inverse) return (x - y) * Fr::load(A.tw + 2 * (ex << A.tw_shift));
+  return (y - x) * Fr::load(A.tw + 2 * ((((size_t)1 << halfN_sh) - ex) << A.tw_shift));
+}
+
+// R4: two stages per trip through shared memory (radix-4 butterflies in registers): half the LDS/STS traffic and
+// half the barriers of the radix-2 loop; needs ~2x the registers, so 2 CTAs per SM instead of 4.
+template <int R4>
+#ifndef ZK_NTT_R4_CTAS
+#define ZK_NTT_R4_CTAS 3
+#endif
+__global__ void __launch_bounds__(kThreads, R4 ? ZK_NTT_R4_CTAS : ZK_NTT_MIN_CTAS) k_ntt_pass_t(PassArgs A, PassConsts K) {
   extern __shared__ uint4 smem[];
   const uint32_t t = A.t, logC = A.logC, C = 1u << logC, L = A.L, P = A.s0;
   const uint32_t rows = 1u << t, tile = rows << logC;
@@ -111,7 +124,30 @@ __global__ void __launch_bounds__(kThreads, ZK_NTT_MIN_CTAS) k_ntt_pass(PassArgs
 
   // ---- t butterfly stages in shared memory ---------------------------------------------------
   const uint32_t halfN_sh = L - 1;    // log2(N/2)
-  for (uint32_t u = 1; u <= t; u++) {
+  uint32_t u = 1;
+  if (R4) {
+    for (; u + 1 <= t; u += 2) {
+      const uint32_t s = P + u, hb = t - u, hb2 = hb - 1;   // partner distances 2^hb (stage u) and 2^hb2 (stage u+1) rows
+      for (uint32_t b = threadIdx.x; b < (tile >> 2); b += kThreads) {
+        uint32_t c = b & (C - 1), mm = b >> logC;
+        uint32_t m_lo = mm & ((1u << hb2) - 1), m_hi = mm >> hb2;
+        uint32_t m = (m_hi << (hb + 1)) | m_lo;               // row with bits hb and hb2 cleared
+        uint32_t e00 = (m << logC) + c, e01 = e00 + (1u << (hb2 + logC)), e10 = e00 + (1u << (hb + logC)), e11 = e10 + (1u << (hb2 + logC));
+        Fr x0 = lds_fr(p0, p1, e00), x1 = lds_fr(p0, p1, e01), y0 = lds_fr(p0, p1, e10), y1 = lds_fr(p0, p1, e11);
+        size_t lo = (rest0 + c) >> P;
+        size_t ja = ((size_t)m_lo << (L - P - t)) + lo, jb = ((size_t)(m_lo | (1u << hb2)) << (L - P - t)) + lo;
+        Fr s0 = x0 + y0, d0 = bf_diff(x0, y0, ja << (s - 1), A, halfN_sh);
+        Fr s1 = x1 + y1, d1 = bf_diff(x1, y1, jb << (s - 1), A, halfN_sh);
+        size_t exc = ja << s;                                  // stage u+1: the row bits below hb2 are m_lo for all four
+        sts_fr(p0, p1, e00, s0 + s1);
+        sts_fr(p0, p1, e01, bf_diff(s0, s1, exc, A, halfN_sh));
+        sts_fr(p0, p1, e10, d0 + d1);
+        sts_fr(p0, p1, e11, bf_diff(d0, d1, exc, A, halfN_sh));
+      }
+      __syncthreads();
+    }
+  }
+  for (; u <= t; u++) {
     const uint32_t s = P + u, hb = t - u;             // partner distance 2^hb rows
     for (uint32_t b = threadIdx.x; b < (tile >> 1); b += kThreads) {
       uint32_t c = b & (C - 1), mm = b >> logC;
@@ -122,15 +158,7 @@ __global__ void __launch_bounds__(kThreads, ZK_NTT_MIN_CTAS) k_ntt_pass(PassArgs
       // logical index bits below this pass's digit = the still-unprocessed bits of the column
       size_t lo = (rest0 + c) >> P;
       size_t j = ((size_t)m_lo << (L - P - t)) + lo;
-      size_t ex = j << (s - 1);                        // exponent of omega_N, < N/2
-      Fr sum = x + y, d;
-      if (ex == 0) {
-        d = x - y;
-      } else if (!A.inverse) {
-        d = (x - y) * Fr::load(A.tw + 2 * (ex << A.tw_shift));
-      } else {
-        d = (y - x) * Fr::load(A.tw + 2 * ((((size_t)1 << halfN_sh) - ex) << A.tw_shift));
-      }
+      Fr sum = x + y, d = bf_diff(x, y, j << (s - 1), A, halfN_sh);
       sts_fr(p0, p1, e0, sum);
       sts_fr(p0, p1, e1, d);
     }
@@ -214,7 +242,11 @@ int run_ntt(zk_ctx* ctx, const NttJob& J) {
   const uint32_t L = J.L;
   const size_t N = (size_t)1 << L;
   size_t smem_max = (((size_t)1 << kTileLog) * 32) + 64;
-  ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  // radix-4 stages (ZK_NTT_RADIX4=1): measured on B200 at k = 19 -- 35.7 ms of NTT per proof with 3 CTAs / SM (39.2 ms with 2)
+  // against 35.4 ms for the radix-2 loop: shared-memory traffic and barriers are not what bounds the pass, so it stays off.
+  static const bool radix4 = getenv("ZK_NTT_RADIX4") && atoi(getenv("ZK_NTT_RADIX4")) == 1;
+  ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass_t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   uint32_t npass = L == 0 ? 1 : (L + kMaxT - 1) / kMaxT;
   uint32_t base_t = L / npass, extra = L % npass;   // first `extra` passes take one more stage
   uint32_t min_t = base_t;
@@ -240,7 +272,8 @@ int run_ntt(zk_ctx* ctx, const NttJob& J) {
     size_t tile = (size_t)1 << (t + logC);
     dim3 grid((unsigned)(N >> (t + logC)), (unsigned)J.count);
     size_t smem = tile * 32 + 64;
-    ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass, grid, kThreads, smem, A, J.K);
+    if (radix4) { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_t<1>, grid, kThreads, smem, A, J.K); }
+    else { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_t<0>, grid, kThreads, smem, A, J.K); }
     src = dst; src_stride = N;
     s0 += t;
   }
