@@ -95,3 +95,80 @@ def test_sort_fallback_with_colliding_high_digits(ctx):
     got = key.create_proof(advice, [], rnd)
     assert got == want, "first differing item %d" % first_diff(got, want)
     assert ov.verify_proof(pc.verifier_params(), opk["vk"], cs2, k, [], got)
+
+
+def _random_witness_case(cs, k, seed, lookup_table_cols=()):
+    """Random fixed / advice columns (no satisfying assignment: the provers do not check satisfiability, byte equality
+    of the two provers is what is tested); lookup inputs are forced into their tables by the caller."""
+    rng = np.random.default_rng(seed)
+    n = 1 << k
+    rnd = lambda: pc.shapes._rand_fr(rng, n)
+    fixed = [rnd() for _ in range(cs.num_fixed_columns)]
+    advice = [rnd() for _ in range(cs.num_advice_columns)]
+    mapping = np.empty((len(cs.permutation_columns), n, 2), dtype=np.uint32)
+    mapping[:, :, 0] = np.arange(len(cs.permutation_columns), dtype=np.uint32)[:, None]
+    mapping[:, :, 1] = np.arange(n, dtype=np.uint32)[None, :]
+    return fixed, advice, mapping
+
+
+def _both_provers(ctx, cs, k, fixed, advice, mapping, instances_int, seed):
+    circ = zk.Circuit(cs, k, transcript_repr=1000 + seed)
+    p = pc.params_for(k)
+    params = zk.ParamsKZG(k, p["g"], p["g_lagrange"], ctx, precompute=True)
+    key = zk.ProverKey(params, circ, fixed, mapping)
+    opk = op.keygen(orc, p, circ, fixed, mapping, circ.transcript_repr)
+    rnd = orc.gen_scalars(seed, key.randoms_needed)
+    want = op.create_proof(orc, p, opk, circ, advice, instances_int, rnd)
+    got = key.create_proof(advice, [pm.to_mont_limbs(i, pm.R_MOD) for i in instances_int], rnd)
+    assert got == want, "first differing item %d of %d" % (first_diff(got, want), len(want) // 32)
+    return got, opk
+
+
+def test_circuit_without_lookups_or_permutation(ctx):
+    """only custom gates: no lookup argument, no permutation argument (empty product / z lists everywhere)"""
+    E = zk.Expression
+    cs = zk.ConstraintSystem(num_fixed=2, num_advice=3)
+    cs.create_gate([E.Fixed(0) * (E.Advice(0) * E.Advice(1) - E.Advice(2)), E.Fixed(1) * (E.Advice(0, 1) - E.Advice(2, -1)) * 5])
+    k = 6
+    n = 1 << k
+    fixed, advice, mapping = _random_witness_case(cs, k, 11)
+    # make it satisfying so that the verifier can be asked too: q0 on even rows with c = a*b, q1 off
+    one = pm.to_mont_limbs([1], pm.R_MOD)[0]
+    fixed[0][:] = 0; fixed[1][:] = 0
+    fixed[0][0:n - 8:2] = one
+    advice[2] = orc.field_op("fr", "mul", advice[0], advice[1])
+    got, opk = _both_provers(ctx, cs, k, fixed, advice, mapping, [], 21)
+    assert ov.verify_proof(pc.verifier_params(), opk["vk"], cs, k, [], got)
+
+
+def test_circuit_with_permutation_only(ctx):
+    E = zk.Expression
+    cs = zk.ConstraintSystem(num_fixed=1, num_advice=2)
+    cs.create_gate([E.Fixed(0) * (E.Advice(0) - E.Advice(1))])
+    cs.enable_equality(0, 0)
+    cs.enable_equality(0, 1)
+    k = 5
+    n = 1 << k
+    fixed, advice, mapping = _random_witness_case(cs, k, 12)
+    fixed[0][:] = 0
+    advice[1][:10] = advice[0][:10]
+    for r in range(10):      # cell (0, r) <-> cell (1, r)
+        mapping[0, r] = (1, r); mapping[1, r] = (0, r)
+    got, opk = _both_provers(ctx, cs, k, fixed, advice, mapping, [], 22)
+    assert ov.verify_proof(pc.verifier_params(), opk["vk"], cs, k, [], got)
+
+
+def test_first_phase_challenge_and_instance(ctx):
+    """shapes.toy_shape(): a gate that reads a challenge and an instance column, instance column in the permutation"""
+    cs = pc.shapes.toy_shape()
+    k = 6
+    n = 1 << k
+    usable = n - (cs.blinding_factors() + 1)
+    fixed, advice, mapping = _random_witness_case(cs, k, 13)
+    # the lookup is (F1*A1, F1*A2 + (1-F1)*5) in (F2, F3): switch it off (F1 = 0) and put (0, 5) into the table
+    fixed[1][:] = 0
+    fixed[2][0] = 0
+    fixed[3][0] = pm.to_mont_limbs([5], pm.R_MOD)[0]
+    inst = [[3, 1, 4, 1, 5, 9, 2, 6]]
+    got, opk = _both_provers(ctx, cs, k, fixed, advice, mapping, inst, 23)
+    assert len(got) > 0
