@@ -48,8 +48,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--k", type=int, default=19, help="log2 rows (19 = full-chain shape, 17 = QE3 shape)")
-    ap.add_argument("--mode", default="proof", choices=["proof", "hotpath", "msm-sharded", "sweep"],
-                    help="proof = complete create_proof on the device (default); hotpath = only the MSM / NTT / h(X) calls")
+    ap.add_argument("--mode", default="proof", choices=["proof", "proof-sharded", "hotpath", "msm-sharded", "sweep"],
+                    help="proof = complete create_proof on the device, independent proofs per GPU (default); proof-sharded = ONE "
+                         "proof computed jointly by all GPUs (strong scaling); hotpath = only the MSM / NTT / h(X) calls")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=3, help="1 = one stream, 3 = commitments on two streams + NTT/h(X) on a third")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -634,18 +635,37 @@ def oracle_h_fast(orc, zk, cs, k, case, threads):
 
 
 # ---- main ------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else written to fd 1 meanwhile (NCCL's version banner,
+    library chatter) has been diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    full = args.mode == "proof"
+    full = args.mode in ("proof", "proof-sharded")
+    sharded = args.mode == "proof-sharded"
     metric = METRIC if full else METRIC_HOTPATH
     config = {"workload": "full-chain DCAP shape: QE3 column set at k=%d (ext_k=%d), %s per step"
                           % (args.k, args.k + 2, "one complete create_proof (satisfying synthetic witness, proof verified by the "
                              "CPU verifier)" if full else "one create_proof hot path"),
               "shape": None, "l2": "inputs (>= 1 GiB of witness columns per step) exceed the 126 MB L2",
-              "parallelism": "independent proofs per GPU (replicas)" if args.gpus > 1 else "1 GPU",
+              "parallelism": ("one proof sharded over the GPUs: commitments by column / base range, h(X) by rows; NCCL all-gather"
+                              if sharded else "independent proofs per GPU (replicas)") if args.gpus > 1 else "1 GPU",
               "streams": (1 if os.environ.get("ZK_PROVER_STREAMS") == "1" else 2) if full else args.streams}
 
     if args.impl == "reference":
@@ -663,7 +683,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": best["cores"], "kind": "port",
                                  "sample": best["sample"], "parts": best["parts"]},
                 "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import importlib
@@ -687,8 +707,13 @@ def main():
         return msm_sharded(args, zk, torch, dist, dev, rank, local_rank, world)
 
     if full:
-        wl = ProofWorkload(zk, shapes, torch, local_rank, args.k, seed=0xDCA90002 + rank)
+        wl = ProofWorkload(zk, shapes, torch, local_rank, args.k, seed=0xDCA90002 + (0 if sharded else rank))
         config["keygen_s"] = wl.keygen_s
+        if sharded and world > 1:
+            uid = [zk.Group.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            wl.group = zk.Group(wl.ctx, rank, world, uid[0])
+            wl.key.set_group(wl.group)
     else:
         wl = Workload(zk, shapes, torch, local_rank, args.k, seed=0xDCA90002 + rank, with_host=(rank == 0 and not args.no_e2e), streams=args.streams)
     config["shape"] = wl.counts
@@ -741,10 +766,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     ms_per_step = ms_max / args.steps
-    value = world * args.steps / (ms_max * 1e-3)
+    value = (1 if sharded else world) * args.steps / (ms_max * 1e-3)
 
     e2e = None
-    if rank == 0 and not args.no_e2e:
+    if sharded and not args.no_e2e:           # every rank takes part: the proof is a joint computation
+        wl.step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(1, min(args.steps, 3))
+        for _ in range(reps):
+            h2d, d2h = wl.step_e2e()
+        barrier()
+        dt = (time.perf_counter() - t0) / reps
+        e2e = {"value": 1.0 / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3, "note": "zk_create_proof on every rank with the advice columns and the RNG stream in "
+                                                "pinned HOST memory; one proof computed jointly"}
+    elif rank == 0 and not args.no_e2e:
         for _ in range(1):
             wl.step_e2e()
         torch.cuda.synchronize()
@@ -762,7 +799,7 @@ def main():
                         "zk_evaluate_h, zk_divide_by_vanishing_poly, zk_extended_to_coeff); pinned host buffers; "
                         "measured on rank 0 and scaled by the GPU count (ranks are independent)")}
     batch = None
-    if full and args.inflight > 1:
+    if full and args.inflight > 1 and not sharded:
         # throughput with several proofs in flight per GPU: the latency- and atomic-bound stages of one proof overlap
         # the integer-pipe-bound stages of another (every rank does this; rank 0 reports max over ranks)
         wl.enable_inflight(args.inflight, wl._keygen_inputs)
@@ -844,6 +881,9 @@ def main():
         int_pipe["evalh_frac_of_modmul_peak"] = int_pipe["evalh_modmul_G_per_s"] / modmul_peak
 
     cpu = None
+    if sharded and world > 1 and not args.no_cpu_baseline:      # checker only: the jointly computed proof must verify
+        cpu = {"value": None, "unit": "proofs/s", "cores": 0, "kind": "port", "sample": "verification only",
+               "gpu_proof_verified": verify_gpu_proof(wl), "proof_bytes": len(wl.last_proof)}
     if not args.no_cpu_baseline and world == 1:
         try:
             b = cpu_baseline_proof(args.k, full=full)
@@ -856,11 +896,11 @@ def main():
             cpu = {"value": None, "unit": "proofs/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
     line = {"metric": metric, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_step_one_stream": ms_serial,
-            "higher_is_better": True, "scaling": "weak",
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "u32 limbs (254-bit modular)", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "int_pipe": int_pipe,
             "kernels": fam, "cpu_baseline": cpu, "batch": batch}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -907,7 +947,7 @@ def sweep(args, zk, torch, dev, local_rank):
         ms = e0.elapsed_time(e1) / 5
         res["ntt_ms"] = ms; res["ntt_GB_s"] = 64 * n / (ms * 1e-3) / 1e9
         res["ntt_Gmul_s"] = (n // 2) * k / (ms * 1e-3) / 1e9
-        print(json.dumps(res), flush=True)
+        emit(res)
         del sc, pts, a
     return 0
 
@@ -955,12 +995,12 @@ def msm_sharded(args, zk, torch, dist, dev, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
     if rank == 0:
-        print(json.dumps({"metric": "BN254 G1 MSM sharded by base range, Gpts/s", "value": n / (ms * 1e-3) / 1e9,
+        emit({"metric": "BN254 G1 MSM sharded by base range, Gpts/s", "value": n / (ms * 1e-3) / 1e9,
                           "unit": "Gpts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": "u32 limbs (254-bit modular)", "data": "synthetic",
                           "config": {"workload": "one MSM of 2^%d points, bases sharded by contiguous range" % k},
-                          "result_point": [int(x) & 0xFFFFFFFFFFFFFFFF for x in out.cpu().view(-1).tolist()]}))
+                          "result_point": [int(x) & 0xFFFFFFFFFFFFFFFF for x in out.cpu().view(-1).tolist()]})
     if dist is not None:
         dist.destroy_process_group()
     return 0

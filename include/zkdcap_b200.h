@@ -323,6 +323,25 @@ int zk_create_proof(zk_pkey* pk, const zk_fr* const* advice_values,
                     const zk_fr* randoms, size_t n_randoms,
                     uint8_t* proof, size_t proof_cap, size_t* proof_len);
 
+/* ---- one proof over several GPUs ------------------------- */
+/* One process per GPU, as torch.distributed launches them.  Every rank creates its own context, SRS and key from the
+ * SAME inputs and calls zk_create_proof with the SAME witness and randoms; inside, the independent column commitments
+ * are split over the ranks (a single commitment: by base range), h(X) by row range, and the results are all-gathered
+ * over NVLink (NCCL, bound at run time), so that every rank ends with the same proof bytes.  The reference has no
+ * counterpart: halo2 scales only with rayon threads on one host. */
+typedef struct zk_group zk_group;
+/* rank 0 obtains the rendezvous id (ncclGetUniqueId) and distributes it to the other ranks out of band */
+int zk_group_unique_id(uint8_t id[128]);
+int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t id[128], zk_group** out);
+void zk_group_destroy(zk_group* g);
+uint32_t zk_group_rank(const zk_group* g);
+uint32_t zk_group_world(const zk_group* g);
+/* Attach (or detach with NULL) a group: the key's proofs are then computed jointly.  The group must outlive its use. */
+int zk_pkey_set_group(zk_pkey* pk, zk_group* g);
+/* How `count` commitments over n bases are split: *mode 0 = rank commits columns [*lo, *hi) (every rank's share padded
+ * to *per columns), *mode 1 = every rank commits all of them over the bases [*lo, *hi).  Pure host function. */
+void zk_group_shard_plan(uint32_t rank, uint32_t world, size_t count, size_t n, int* mode, size_t* per, size_t* lo, size_t* hi);
+
 /* ---- element-wise field arithmetic (parity self-test of the device field) --- */
 /* op: 0 add, 1 sub, 2 mul, 3 neg, 4 invert, 5 square, 6 to Montgomery form,
  * 7 from Montgomery form (to_repr), 8 double.  field: 0 = Fr, 1 = Fq.

@@ -59,3 +59,28 @@ def test_msm_base_range_sharding_world2():
         assert p.exitcode == 0
     assert got == want
     assert tmax == 2.0
+
+
+def test_group_shard_plan_covers_everything_once():
+    """zk_group_shard_plan (host logic of the one-proof-over-several-GPUs mode): column shares are disjoint, padded to
+    equal size and cover every column; base-range shares tile [0, n)."""
+    import zkdcap_b200 as zk
+    n = 1 << 19
+    for world in (1, 2, 4, 8):
+        for count in (1, 2, 3, 4, 6, 7, 11, 22, 28):
+            plans = [zk.Group.shard_plan(r, world, count, n) for r in range(world)]
+            modes = {p[0] for p in plans}
+            assert len(modes) == 1
+            mode, per = plans[0][0], plans[0][1]
+            total = count if mode == 0 else n
+            assert mode == (0 if (count >= world or world == 1) else 1)
+            covered = []
+            for r, (_, p, lo, hi) in enumerate(plans):
+                assert p == per and hi - lo <= per and lo <= hi
+                if hi > lo:
+                    assert lo == r * per          # rank r's share sits at slot r * per of the exchange buffer
+                covered += list(range(lo, hi)) if total < 1000 else [(lo, hi)]
+            if total < 1000:
+                assert covered == list(range(total))
+            else:
+                assert covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))

@@ -32,10 +32,10 @@ namespace {
 template <int NI>
 __global__ void __launch_bounds__(128, ZK_EVALH_MIN_CTAS) k_evalh(EvalProgram P, EvalScalars S, const uint32_t* code,
                                                const uint4* const* cols, const uint4* consts,
-                                               const uint4* challenges, const uint4* tw, uint4* out) {
-  size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+                                               const uint4* challenges, const uint4* tw, uint4* out, size_t row0, size_t row1) {
+  size_t idx = row0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t ext = (size_t)1 << P.ext_k;
-  if (idx >= ext) return;
+  if (idx >= row1) return;
   EvalState<NI> st;
   Fr bt = S.one;
   if (P.ext_k > 0) {
@@ -163,7 +163,7 @@ namespace {
 // Fills the column pointer table and launches the fused kernel.  `wit` holds the witness
 // cosets in slot order (advice, instance, z sets, lookup triples), E elements each.
 int launch_evalh(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr* beta, const zk_fr* gamma,
-                 const zk_fr* theta, zk_fr* d_out_ext) {
+                 const zk_fr* theta, zk_fr* d_out_ext, size_t row0 = 0, size_t row1 = ~(size_t)0) {
   zk_ctx* ctx = pk->ctx;
   const EvalProgram& P = pk->C.prog;
   const zk_evaluator_desc& D = pk->shape;
@@ -193,14 +193,16 @@ int launch_evalh(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr
   S.delta = fr_canon(delta_c);
   S.one = Fr::one();
   const uint4* tw = (const uint4*)zk_domain_twiddles(pk->dom);
-  unsigned grid = zk_div_up(E, 128);
+  if (row1 > E) row1 = E;
+  if (row0 >= row1) return ZK_OK;
+  unsigned grid = zk_div_up(row1 - row0, 128);
   uint32_t ni = pk->C.max_intermediates;
   // measured on B200: the select-based register file (NI = 4) is slower than 16 L1-resident slots (21.5 vs 19.2 ms)
   uint32_t ni_min = 16;
   if (const char* v = getenv("ZK_EVALH_NI_MIN")) ni_min = (uint32_t)atoi(v);
   if (ni < ni_min) ni = ni_min;
 #define EVALH_ARGS P, S, (const uint32_t*)pk->d_code, (const uint4* const*)pk->d_cols, (const uint4*)pk->d_consts, \
-                   (const uint4*)pk->d_challenges, tw, (uint4*)d_out_ext
+                   (const uint4*)pk->d_challenges, tw, (uint4*)d_out_ext, row0, row1
   if (ni <= 4) { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<4>, grid, 128, 0, EVALH_ARGS); }
   else if (ni <= 16) { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<16>, grid, 128, 0, EVALH_ARGS); }
   else if (ni <= 32) { ZK_LAUNCH(ctx, "evaluate_h", k_evalh<32>, grid, 128, 0, EVALH_ARGS); }
@@ -215,9 +217,10 @@ int launch_evalh(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr
 // ---- internal entry points for prover.cu: the witness cosets are produced by the caller (on another stream) -------
 // slot order: advice | instance | permutation z sets | lookup (Z, A', S') triples; 2^extended_k elements each
 char* zk_pk_witness_slot(zk_pk* pk, size_t slot) { return (char*)pk->d_witness + slot * zk_domain_ext_n(pk->dom) * 32; }
+// rows [row0, row1) of the extended domain only (a group of GPUs splits the rows)
 int zk_evaluate_h_launch(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr* beta, const zk_fr* gamma,
-                         const zk_fr* theta, zk_fr* d_out_ext) {
-  return launch_evalh(pk, challenges, y, beta, gamma, theta, d_out_ext);
+                         const zk_fr* theta, zk_fr* d_out_ext, size_t row0, size_t row1) {
+  return launch_evalh(pk, challenges, y, beta, gamma, theta, d_out_ext, row0, row1);
 }
 
 extern "C" int zk_evaluate_h_dev(zk_pk* pk, const zk_fr* const* d_advice, const zk_fr* const* d_instance,

@@ -39,6 +39,8 @@ struct MsmPlan {
   size_t stride;           // window table: table[w * stride + i]
   size_t nb;               // G * B buckets per MSM
   size_t ent_per_msm;      // n * W
+  size_t sc_stride;        // scalars of MSM m start at m * sc_stride + base_off (a base RANGE of a longer column)
+  size_t base_off;         // first base of the range: table index = w * stride + base_off + i
 };
 
 // ---- 1+2: digits, histogram, scatter --------------------------------------------------------------
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint4* scalars, MsmPla
   size_t i = i_begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t msm = blockIdx.y;
   if (i >= i_end) return;
-  Fr s = Fr::load(scalars + 2 * (msm * P.n + i)).from_mont();
+  Fr s = Fr::load(scalars + 2 * (msm * P.sc_stride + P.base_off + i)).from_mont();
   uint32_t* cnt = counts + msm * P.nb;
   int carry = 0;
   for (uint32_t w = 0; w < P.W; w++) {
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint4* scalars, MsmPla
       atomicAdd(&cnt[bucket], 1u);
     } else {
       uint32_t pos = atomicAdd(&cnt[bucket], 1u);   // cnt is the zeroed cursor array here
-      uint32_t idx = (P.G == 1) ? (uint32_t)(w * P.stride + i) : (uint32_t)i;
+      uint32_t idx = (P.G == 1) ? (uint32_t)(w * P.stride + P.base_off + i) : (uint32_t)i;
       entries[msm * P.ent_per_msm + starts[msm * (P.nb + 1) + bucket] + pos] = idx | (neg << 31);
     }
   }
@@ -530,11 +532,20 @@ __global__ void k_g1_sum(const uint4* pts, size_t count, uint4* out) {
   store_g1_normalised(out, acc.to_affine());
 }
 
+// out[p] = sum over r < parts of pts[r * count + p]  (partial MSMs of the ranks of a group, one thread per output)
+__global__ void k_g1_sum_strided(const uint4* pts, size_t parts, size_t count, uint4* out) {
+  size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (p >= count) return;
+  XYZZ acc = XYZZ::identity();
+  for (size_t r = 0; r < parts; r++) acc = acc.add(load_g1_as_xyzz(pts + 6 * (r * count + p)));
+  store_g1_normalised(out + 6 * p, acc.to_affine());
+}
+
 uint32_t ilog2(size_t x) { uint32_t l = 0; while (((size_t)1 << (l + 1)) <= x) l++; return l; }
 
 MsmPlan make_plan(size_t n, size_t count, bool table, uint32_t table_c, size_t stride, int sm_count) {
   MsmPlan P; memset(&P, 0, sizeof P);
-  P.n = n; P.count = count; P.stride = stride;
+  P.n = n; P.count = count; P.stride = stride; P.sc_stride = n; P.base_off = 0;
   uint32_t lg = ilog2(n ? n : 1);
   if (table) {
     P.c = table_c;
@@ -866,6 +877,26 @@ extern "C" int zk_msm(zk_ctx* ctx, const zk_fr* scalars, const zk_g1_affine* bas
   }
   ZK_CUDA(ctx, cudaMemcpyAsync(out, ctx->msm_out.p, sizeof(zk_g1), cudaMemcpyDeviceToHost, ctx->stream));
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZK_OK;
+}
+
+// `count` commitments restricted to the bases [base_off, base_off + n_sub) of the resident SRS: the scalars of
+// commitment m are d_scalars[m * sc_stride + base_off ..].  Internal (group-sharded single commitments).
+int zk_msm_range_batch_dev(zk_ctx* ctx, const zk_fr* d_scalars, int which, size_t sc_stride, size_t base_off, size_t n_sub,
+                           size_t count, zk_g1* d_out) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!d_out || !d_scalars || (which != ZK_BASES_G && which != ZK_BASES_G_LAGRANGE)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_msm_range: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!count) return ZK_OK;
+  zk_srs_set& s = which == ZK_BASES_G ? ctx->srs_g : ctx->srs_lagrange;
+  if (!s.table) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_msm_range: needs the window table (zk_srs_upload with precompute_windows)");
+  if (base_off + n_sub > ctx->srs_n) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_msm_range: range exceeds the SRS");
+  MsmPlan P = make_plan(n_sub, count, true, (uint32_t)s.table_c, ctx->srs_n, ctx->sm_count);
+  P.sc_stride = sc_stride; P.base_off = base_off;
+  return run_msm(ctx, d_scalars, s.table, P, d_out);
+}
+int zk_g1_sum_strided_dev(zk_ctx* ctx, const zk_g1* d_points, size_t parts, size_t count, zk_g1* d_out) {
+  ZK_LAUNCH(ctx, "g1_sum", k_g1_sum_strided, zk_div_up(count, 32), 32, 0, (const uint4*)d_points, parts, count, (uint4*)d_out);
   return ZK_OK;
 }
 

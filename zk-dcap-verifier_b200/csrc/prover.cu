@@ -29,7 +29,15 @@ extern "C" int zk_coeff_to_extended_dev(zk_domain* d, const zk_fr* d_a, zk_fr* d
 int zk_lagrange_to_coeff_oop(zk_domain* d, const zk_fr* d_src, zk_fr* d_dst, size_t count);
 char* zk_pk_witness_slot(zk_pk* pk, size_t slot);
 int zk_evaluate_h_launch(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr* beta, const zk_fr* gamma,
-                         const zk_fr* theta, zk_fr* d_out_ext);
+                         const zk_fr* theta, zk_fr* d_out_ext, size_t row0, size_t row1);
+struct zk_group;
+int zk_group_allgather(zk_group* g, void* d_buf, size_t bytes_per_rank);
+extern "C" uint32_t zk_group_rank(const zk_group* g);
+extern "C" uint32_t zk_group_world(const zk_group* g);
+extern "C" void zk_group_shard_plan(uint32_t rank, uint32_t world, size_t count, size_t n, int* mode, size_t* per, size_t* lo, size_t* hi);
+int zk_msm_range_batch_dev(zk_ctx* ctx, const zk_fr* d_scalars, int which, size_t sc_stride, size_t base_off, size_t n_sub,
+                           size_t count, zk_g1* d_out);
+int zk_g1_sum_strided_dev(zk_ctx* ctx, const zk_g1* d_points, size_t parts, size_t count, zk_g1* d_out);
 const void* zk_domain_twiddles(const zk_domain* d);
 size_t zk_domain_ext_n(const zk_domain* d);
 
@@ -37,6 +45,7 @@ struct zk_pkey {
   zk_ctx* ctx = nullptr;
   zk_pk* pk = nullptr;             // evaluate_h side (cosets, compiled program); owns its own domain
   zk_domain* dom = nullptr;
+  zk_group* group = nullptr;      // not owned: the GPUs that share this proof's commitments and h(X) rows
   // second stream: every lagrange_to_coeff / coeff_to_extended of the witness polynomials runs here, overlapping the
   // commitments and the lookup / permutation kernels of the main stream (they only meet again at evaluate_h)
   zk_ctx* ctxB = nullptr;
@@ -75,6 +84,7 @@ struct zk_pkey {
   size_t scan_cap = 0;
   uint64_t sort_fallbacks = 0;
   uint32_t* d_flags = nullptr;                                  // [0] failure bits, [1..2] totals, [8..15] diff mask
+  char* d_xchg = nullptr;                                       // group exchange area for commitment points
   char *d_points = nullptr, *d_ptrs = nullptr, *d_scalars = nullptr, *d_partial = nullptr, *d_evals = nullptr;
   uint32_t max_list = 0, eval_chunks = 1;
   std::vector<void*> allocs;
@@ -188,8 +198,29 @@ int kate_divide(zk_pkey* K, char* a, uint32_t slot_z, uint32_t slot_zinv) {
 
 // commitments: `count` contiguous polynomials -> affine points on the host (normalised Jacobian from the MSM)
 struct HostPoint { Fq x, y; bool identity; };
+// Commitments of `count` contiguous polynomials into d_points[slot ..].  In a group the work is split (by column when
+// there are at least as many polynomials as GPUs, by base range otherwise) and the points are all-gathered, so every
+// rank continues with the same transcript.
 int commit_enqueue(zk_pkey* K, const char* d_polys, size_t count, int which, size_t slot) {
-  return zk_msm_batch_dev(K->ctx, (const zk_fr*)d_polys, which, K->n, count, (zk_g1*)K->d_points + slot);
+  zk_ctx* ctx = K->ctx;
+  zk_g1* out = (zk_g1*)K->d_points + slot;
+  const uint32_t world = K->group ? zk_group_world(K->group) : 1;
+  if (world <= 1 || !count) return zk_msm_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, count, out);
+  const uint32_t rank = zk_group_rank(K->group);
+  int mode; size_t per, lo, hi;
+  zk_group_shard_plan(rank, world, count, K->n, &mode, &per, &lo, &hi);
+  zk_g1* xchg = (zk_g1*)K->d_xchg;
+  if (mode == 0) {
+    if (hi > lo) ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)(d_polys + lo * K->n * 32), which, K->n, hi - lo, xchg + (size_t)rank * per));
+    ZK_TRY(zk_group_allgather(K->group, xchg, per * sizeof(zk_g1)));
+    ZK_CUDA(ctx, cudaMemcpyAsync(out, xchg, count * sizeof(zk_g1), cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    if (hi > lo) ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, lo, hi - lo, count, xchg + (size_t)rank * count));
+    else ZK_CUDA(ctx, cudaMemsetAsync(xchg + (size_t)rank * count, 0, count * sizeof(zk_g1), ctx->stream));   // z = 0: identity
+    ZK_TRY(zk_group_allgather(K->group, xchg, count * sizeof(zk_g1)));
+    ZK_TRY(zk_g1_sum_strided_dev(ctx, xchg, world, count, out));
+  }
+  return ZK_OK;
 }
 int commit_fetch(zk_pkey* K, size_t count, std::vector<HostPoint>* out) {
   zk_ctx* ctx = K->ctx;
@@ -360,6 +391,12 @@ extern "C" void zk_pkey_destroy(zk_pkey* K) {
 }
 extern "C" zk_pk* zk_pkey_pk(zk_pkey* K) { return K ? K->pk : nullptr; }
 extern "C" zk_ctx* zk_pkey_aux_ctx(zk_pkey* K) { return K ? K->ctxB : nullptr; }
+extern "C" int zk_pkey_set_group(zk_pkey* K, zk_group* g) {
+  if (!K) return ZK_ERR_ARG;
+  if (g && zk_group_world(g) > 16) ZK_FAIL(K->ctx, ZK_ERR_ARG, "zk_pkey_set_group: at most 16 GPUs");
+  K->group = g;
+  return ZK_OK;
+}
 extern "C" size_t zk_proof_randoms(const zk_pkey* K) {
   if (!K) return 0;
   size_t a = K->n_advice, l = K->n_lookups, bf = K->bf;
@@ -494,6 +531,7 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
   K->max_list = D.n_advice + D.n_fixed + D.n_instance + K->n_perm + K->n_sets + 3 * D.n_lookups + D.degree + 16;
   K->eval_chunks = (uint32_t)std::min<size_t>(std::max<size_t>(n / 4096, 1), 64);
   KG(dev_alloc(K, &K->d_points, (size_t)K->max_list * sizeof(zk_g1)));
+  KG(dev_alloc(K, &K->d_xchg, (size_t)(K->max_list + 64) * 16 * sizeof(zk_g1)));
   KG(dev_alloc(K, &K->d_ptrs, (size_t)K->max_list * sizeof(void*)));
   KG(dev_alloc(K, &K->d_scalars, (size_t)K->max_list * 32));
   KG(dev_alloc(K, &K->d_partial, (size_t)K->max_list * K->eval_chunks * 32));
@@ -809,7 +847,14 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     for (uint32_t i = 0; i < K->n_challenges; i++) f_to_abi(challenges[i], &ch[i]);
     zk_fr yh, bh, gh, th;
     f_to_abi(y, &yh); f_to_abi(beta, &bh); f_to_abi(gamma, &gh); f_to_abi(theta, &th);
-    ZK_TRY(zk_evaluate_h_launch(K->pk, ch.data(), &yh, &bh, &gh, &th, (zk_fr*)K->d_hext));
+    const uint32_t world = K->group ? zk_group_world(K->group) : 1;
+    if (world > 1 && (K->ext_n % world) == 0) {          // every GPU evaluates its slice of the extended rows
+      const size_t rows = K->ext_n / world, r0 = rows * zk_group_rank(K->group);
+      ZK_TRY(zk_evaluate_h_launch(K->pk, ch.data(), &yh, &bh, &gh, &th, (zk_fr*)K->d_hext, r0, r0 + rows));
+      ZK_TRY(zk_group_allgather(K->group, K->d_hext, rows * 32));
+    } else {
+      ZK_TRY(zk_evaluate_h_launch(K->pk, ch.data(), &yh, &bh, &gh, &th, (zk_fr*)K->d_hext, 0, K->ext_n));
+    }
   }
   // vanishing.construct
   ZK_TRY(zk_divide_by_vanishing_poly_dev(dom, (zk_fr*)K->d_hext));

@@ -610,6 +610,39 @@ class ProvingKey:
         return out
 
 
+class Group:
+    """The GPUs (one process each) that compute one proof together (zk_group): `uid` comes from Group.unique_id() on
+    rank 0 and reaches the other ranks out of band (e.g. torch.distributed.broadcast_object_list)."""
+
+    @staticmethod
+    def unique_id():
+        lib = _abi.load()
+        buf = (C.c_uint8 * 128)()
+        if lib.zk_group_unique_id(buf) != 0:
+            raise ZkError("zk_group_unique_id failed (NCCL not available)")
+        return bytes(buf)
+
+    def __init__(self, ctx, rank, world, uid):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128)(*uid)
+        ctx.check(ctx.lib.zk_group_create(ctx.h, rank, world, buf, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.zk_group_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def shard_plan(rank, world, count, n):
+        """(mode, per, lo, hi): mode 0 = columns [lo, hi) per rank, mode 1 = base range [lo, hi) per rank"""
+        lib = _abi.load()
+        mode, per, lo, hi = C.c_int(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        lib.zk_group_shard_plan(rank, world, count, n, C.byref(mode), C.byref(per), C.byref(lo), C.byref(hi))
+        return mode.value, per.value, lo.value, hi.value
+
+
 # ---- plonk/keygen.rs + plonk/prover.rs ------------------------------------------------------------------
 class ProverKey:
     """keygen_vk + keygen_pk (circuits/src/sgx_dcap_verifier.rs:803, :807): the whole ProvingKey resident in HBM,
@@ -638,6 +671,11 @@ class ProverKey:
                 self.ctx.lib.zk_pkey_destroy(self.h)
         except Exception:
             pass
+
+    def set_group(self, group):
+        """Proofs of this key are computed jointly by the group's GPUs (every rank must make the same calls)."""
+        self.ctx.check(self.ctx.lib.zk_pkey_set_group(self.h, group.h if group is not None else None))
+        self._group = group
 
     def vk_commitments(self):
         """(vk.fixed_commitments, vk.permutation.commitments) as (count, 8) G1Affine arrays"""
