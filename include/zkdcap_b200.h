@@ -326,13 +326,14 @@ int zk_create_proof(zk_pkey* pk, const zk_fr* const* advice_values,
 /* ---- one proof over several GPUs ------------------------- */
 /* One process per GPU, as torch.distributed launches them.  Every rank creates its own context, SRS and key from the
  * SAME inputs and calls zk_create_proof with the SAME witness and randoms; inside, the independent column commitments
- * are split over the ranks (a single commitment: by base range), h(X) by row range, and the results are all-gathered
+ * and the witness polynomials' transforms are split over the ranks (a single commitment: by base range), h(X) by row
+ * range, and the results are all-gathered
  * over NVLink (NCCL, bound at run time), so that every rank ends with the same proof bytes.  The reference has no
  * counterpart: halo2 scales only with rayon threads on one host. */
 typedef struct zk_group zk_group;
 /* rank 0 obtains the rendezvous id (ncclGetUniqueId) and distributes it to the other ranks out of band */
-int zk_group_unique_id(uint8_t id[128]);
-int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t id[128], zk_group** out);
+int zk_group_unique_id(uint8_t id[256]);
+int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t id[256], zk_group** out);
 void zk_group_destroy(zk_group* g);
 uint32_t zk_group_rank(const zk_group* g);
 uint32_t zk_group_world(const zk_group* g);

@@ -18,7 +18,8 @@
 struct zk_group {
   zk_ctx* ctx = nullptr;
   uint32_t rank = 0, world = 1;
-  void* comm = nullptr;
+  void* comm = nullptr;      // collectives of the context's own stream
+  void* comm2 = nullptr;     // collectives issued on another stream of the same device (the prover's transform stream)
 };
 
 namespace {
@@ -58,17 +59,19 @@ Nccl* nccl() {
 
 }  // namespace
 
-extern "C" int zk_group_unique_id(uint8_t id[128]) {
+extern "C" int zk_group_unique_id(uint8_t id[256]) {     // two NCCL ids: one communicator per stream
   Nccl* N = nccl();
   if (!N || !id) return ZK_ERR_STATE;
-  nccl_uid u;
-  memset(&u, 0, sizeof u);
-  if (N->get_uid(&u) != 0) return ZK_ERR_CUDA;
-  memcpy(id, &u, 128);
+  for (int i = 0; i < 2; i++) {
+    nccl_uid u;
+    memset(&u, 0, sizeof u);
+    if (N->get_uid(&u) != 0) return ZK_ERR_CUDA;
+    memcpy(id + 128 * i, &u, 128);
+  }
   return ZK_OK;
 }
 
-extern "C" int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t id[128], zk_group** out) {
+extern "C" int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t id[256], zk_group** out) {
   if (!ctx) return ZK_ERR_ARG;
   if (!out || !id || world == 0 || rank >= world) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_group_create: bad argument");
   if (world & (world - 1)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_group_create: the group size must be a power of two (got %u)", world);
@@ -77,13 +80,16 @@ extern "C" int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
   zk_group* g = new zk_group();
   g->ctx = ctx; g->rank = rank; g->world = world;
-  nccl_uid u;
-  memcpy(&u, id, 128);
-  int r = N->comm_init(&g->comm, (int)world, u, (int)rank);
-  if (r != 0) {
-    std::string e = N->err ? N->err(r) : "nccl error";
-    delete g;
-    ZK_FAIL(ctx, ZK_ERR_CUDA, "zk_group_create: ncclCommInitRank: %s", e.c_str());
+  for (int i = 0; i < 2; i++) {
+    nccl_uid u;
+    memcpy(&u, id + 128 * i, 128);
+    int r = N->comm_init(i == 0 ? &g->comm : &g->comm2, (int)world, u, (int)rank);
+    if (r != 0) {
+      std::string e = N->err ? N->err(r) : "nccl error";
+      if (g->comm) N->comm_destroy(g->comm);
+      delete g;
+      ZK_FAIL(ctx, ZK_ERR_CUDA, "zk_group_create: ncclCommInitRank: %s", e.c_str());
+    }
   }
   *out = g;
   return ZK_OK;
@@ -92,19 +98,25 @@ extern "C" int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const
 extern "C" void zk_group_destroy(zk_group* g) {
   if (!g) return;
   Nccl* N = nccl();
-  if (N && g->comm) { cudaSetDevice(g->ctx->device); cudaStreamSynchronize(g->ctx->stream); N->comm_destroy(g->comm); }
+  if (N && g->comm) {
+    cudaSetDevice(g->ctx->device); cudaDeviceSynchronize();
+    N->comm_destroy(g->comm);
+    if (g->comm2) N->comm_destroy(g->comm2);
+  }
   delete g;
 }
 extern "C" uint32_t zk_group_rank(const zk_group* g) { return g ? g->rank : 0; }
 extern "C" uint32_t zk_group_world(const zk_group* g) { return g ? g->world : 1; }
 
-// In-place all-gather on the context stream: rank r's contribution sits at d_buf + r * bytes_per_rank.
-int zk_group_allgather(zk_group* g, void* d_buf, size_t bytes_per_rank) {
-  zk_ctx* ctx = g->ctx;
+// In-place all-gather on the stream of `on`: rank r's contribution sits at d_buf + r * bytes_per_rank.  `on` is the
+// group's own context or another context of the same device (then the second communicator is used).
+int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank) {
+  zk_ctx* ctx = on ? on : g->ctx;
   Nccl* N = nccl();
   if (!N) ZK_FAIL(ctx, ZK_ERR_STATE, "group: NCCL not loaded");
+  void* comm = ctx == g->ctx ? g->comm : g->comm2;
   zk_timing_begin(ctx, "group_allgather");
-  int r = N->allgather((const char*)d_buf + (size_t)g->rank * bytes_per_rank, d_buf, bytes_per_rank, /*ncclChar*/ 0, g->comm, ctx->stream);
+  int r = N->allgather((const char*)d_buf + (size_t)g->rank * bytes_per_rank, d_buf, bytes_per_rank, /*ncclChar*/ 0, comm, ctx->stream);
   zk_timing_end(ctx);
   if (r != 0) ZK_FAIL(ctx, ZK_ERR_CUDA, "group: ncclAllGather: %s", N->err ? N->err(r) : "error");
   return ZK_OK;

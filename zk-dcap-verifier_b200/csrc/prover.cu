@@ -31,7 +31,7 @@ char* zk_pk_witness_slot(zk_pk* pk, size_t slot);
 int zk_evaluate_h_launch(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr* beta, const zk_fr* gamma,
                          const zk_fr* theta, zk_fr* d_out_ext, size_t row0, size_t row1);
 struct zk_group;
-int zk_group_allgather(zk_group* g, void* d_buf, size_t bytes_per_rank);
+int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank);
 extern "C" uint32_t zk_group_rank(const zk_group* g);
 extern "C" uint32_t zk_group_world(const zk_group* g);
 extern "C" void zk_group_shard_plan(uint32_t rank, uint32_t world, size_t count, size_t n, int* mode, size_t* per, size_t* lo, size_t* hi);
@@ -85,6 +85,8 @@ struct zk_pkey {
   uint64_t sort_fallbacks = 0;
   uint32_t* d_flags = nullptr;                                  // [0] failure bits, [1..2] totals, [8..15] diff mask
   char* d_xchg = nullptr;                                       // group exchange area for commitment points
+  char *d_stage_p = nullptr, *d_stage_c = nullptr;              // group staging of coefficient forms / cosets (allocated by set_group)
+  size_t stage_cols = 0;
   char *d_points = nullptr, *d_ptrs = nullptr, *d_scalars = nullptr, *d_partial = nullptr, *d_evals = nullptr;
   uint32_t max_list = 0, eval_chunks = 1;
   std::vector<void*> allocs;
@@ -212,12 +214,12 @@ int commit_enqueue(zk_pkey* K, const char* d_polys, size_t count, int which, siz
   zk_g1* xchg = (zk_g1*)K->d_xchg;
   if (mode == 0) {
     if (hi > lo) ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)(d_polys + lo * K->n * 32), which, K->n, hi - lo, xchg + (size_t)rank * per));
-    ZK_TRY(zk_group_allgather(K->group, xchg, per * sizeof(zk_g1)));
+    ZK_TRY(zk_group_allgather(K->group, ctx, xchg, per * sizeof(zk_g1)));
     ZK_CUDA(ctx, cudaMemcpyAsync(out, xchg, count * sizeof(zk_g1), cudaMemcpyDeviceToDevice, ctx->stream));
   } else {
     if (hi > lo) ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, lo, hi - lo, count, xchg + (size_t)rank * count));
     else ZK_CUDA(ctx, cudaMemsetAsync(xchg + (size_t)rank * count, 0, count * sizeof(zk_g1), ctx->stream));   // z = 0: identity
-    ZK_TRY(zk_group_allgather(K->group, xchg, count * sizeof(zk_g1)));
+    ZK_TRY(zk_group_allgather(K->group, ctx, xchg, count * sizeof(zk_g1)));
     ZK_TRY(zk_g1_sum_strided_dev(ctx, xchg, world, count, out));
   }
   return ZK_OK;
@@ -243,6 +245,39 @@ bool is_device_pointer(const void* p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// lagrange_to_coeff + coeff_to_extended of `count` witness columns on domain `d` (= on d's stream): values (contiguous
+// Lagrange columns) -> polys (contiguous coefficient forms) and the cosets at slot(i).  In a group every rank transforms
+// a share of the columns into the staging buffers, which are all-gathered and copied into place.
+template <class SlotFn>
+int transform_columns(zk_pkey* K, zk_domain* d, zk_ctx* on, const char* values, char* polys, size_t count, SlotFn slot, bool contiguous) {
+  const size_t nb = K->n * 32, eb = K->ext_n * 32;
+  const uint32_t world = K->group ? zk_group_world(K->group) : 1;
+  if (world <= 1 || count < 2 || !K->d_stage_c) {
+    ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)values, (zk_fr*)polys, count));
+    if (contiguous) return zk_coeff_to_extended_dev(d, (const zk_fr*)polys, slot(0), count);
+    for (size_t i = 0; i < count; i++) ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(polys + i * nb), slot(i), 1));
+    return ZK_OK;
+  }
+  const uint32_t rank = zk_group_rank(K->group);
+  const size_t per = (count + world - 1) / world;
+  const size_t lo = std::min(count, (size_t)rank * per), hi = std::min(count, (size_t)(rank + 1) * per);
+  if (per * world > K->stage_cols) ZK_FAIL(on, ZK_ERR_STATE, "prover: group staging holds %zu columns, %zu needed", K->stage_cols, per * world);
+  char* sp = K->d_stage_p; char* sc = K->d_stage_c;
+  if (hi > lo) {
+    ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)(values + lo * nb), (zk_fr*)(sp + (size_t)rank * per * nb), hi - lo));
+    ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(sp + (size_t)rank * per * nb), (zk_fr*)(sc + (size_t)rank * per * eb), hi - lo));
+  }
+  ZK_TRY(zk_group_allgather(K->group, on, sp, per * nb));
+  ZK_TRY(zk_group_allgather(K->group, on, sc, per * eb));
+  ZK_CUDA(on, cudaMemcpyAsync(polys, sp, count * nb, cudaMemcpyDeviceToDevice, on->stream));
+  if (contiguous) {
+    ZK_CUDA(on, cudaMemcpyAsync(slot(0), sc, count * eb, cudaMemcpyDeviceToDevice, on->stream));
+  } else {
+    for (size_t i = 0; i < count; i++) ZK_CUDA(on, cudaMemcpyAsync(slot(i), sc + i * eb, eb, cudaMemcpyDeviceToDevice, on->stream));
+  }
+  return ZK_OK;
 }
 
 // ---- lookup: permute_expression_pair on the device, all lookup arguments at once --------------------------------------
@@ -395,6 +430,16 @@ extern "C" int zk_pkey_set_group(zk_pkey* K, zk_group* g) {
   if (!K) return ZK_ERR_ARG;
   if (g && zk_group_world(g) > 16) ZK_FAIL(K->ctx, ZK_ERR_ARG, "zk_pkey_set_group: at most 16 GPUs");
   K->group = g;
+  if (g && zk_group_world(g) > 1 && !K->d_stage_c && !getenv("ZK_GROUP_NO_NTT_SHARD")) {
+    zk_ctx* ctx = K->ctx;
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t cols = std::max<size_t>(std::max<size_t>(K->n_advice, 2 * (size_t)K->n_lookups), K->n_sets) + zk_group_world(g);
+    void *p = nullptr, *q = nullptr;
+    ZK_CUDA(ctx, cudaMalloc(&p, cols * K->n * 32));
+    ZK_CUDA(ctx, cudaMalloc(&q, cols * K->ext_n * 32));
+    K->allocs.push_back(p); K->allocs.push_back(q);
+    K->d_stage_p = (char*)p; K->d_stage_c = (char*)q; K->stage_cols = cols;
+  }
   return ZK_OK;
 }
 extern "C" size_t zk_proof_randoms(const zk_pkey* K) {
@@ -637,11 +682,11 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   const bool serialize = ctx->timing;
   if (cB) cB->timing = ctx->timing;
   auto side = [&](int ev, auto&& fn) -> int {
-    if (!cB) return fn(dom);
+    if (!cB) return fn(dom, ctx);
     if (serialize) ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ZK_CUDA(ctx, cudaEventRecord(K->ev_in[ev], ctx->stream));
     ZK_CUDA(ctx, cudaStreamWaitEvent(cB->stream, K->ev_in[ev], 0));
-    int r = fn(K->domB);
+    int r = fn(K->domB, cB);
     if (r != ZK_OK) { ctx->err = cB->err; return r; }
     if (serialize) ZK_CUDA(ctx, cudaStreamSynchronize(cB->stream));
     return ZK_OK;
@@ -697,9 +742,8 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
         ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, K->ev_copy[g], 0));
         if (serialize) ZK_CUDA(ctx, cudaStreamSynchronize(up));
       }
-      ZK_TRY(side(0, [&](zk_domain* d) -> int {          // advice_polys and their cosets, concurrently with the commitments
-        ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)(K->d_advice + i0 * nb), (zk_fr*)(K->d_advice_polys + i0 * nb), cnt));
-        return zk_coeff_to_extended_dev(d, (const zk_fr*)(K->d_advice_polys + i0 * nb), slot_adv(i0), cnt);
+      ZK_TRY(side(0, [&](zk_domain* d, zk_ctx* on) -> int {   // advice_polys and their cosets, concurrently with the commitments
+        return transform_columns(K, d, on, K->d_advice + i0 * nb, K->d_advice_polys + i0 * nb, cnt, [&](size_t i) { return slot_adv(i0 + (uint32_t)i); }, true);
       }));
       ZK_TRY(commit_enqueue(K, K->d_advice + i0 * nb, cnt, ZK_BASES_G_LAGRANGE, i0));
     }
@@ -741,13 +785,9 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       ZK_TRY(draw_to(lk(l, 3) + usable * 32, bf + 1));
       rpos += 2;
     }
-    ZK_TRY(side(1, [&](zk_domain* d) -> int {          // A', S' -> coefficient forms and cosets
-      ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)lk(0, 2), (zk_fr*)lkp(0, 0), 2 * (size_t)L));
-      for (uint32_t l = 0; l < L; l++) {
-        ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)lkp(l, 0), slot_lk(l, 1), 1));
-        ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)lkp(l, 1), slot_lk(l, 2), 1));
-      }
-      return ZK_OK;
+    ZK_TRY(side(1, [&](zk_domain* d, zk_ctx* on) -> int {   // A', S' -> coefficient forms and cosets
+      return transform_columns(K, d, on, lk(0, 2), lkp(0, 0), 2 * (size_t)L,
+                               [&](size_t i) { return i < L ? slot_lk((uint32_t)i, 1) : slot_lk((uint32_t)(i - L), 2); }, false);
     }));
     uint32_t flags = 0;
     ZK_CUDA(ctx, cudaMemcpyAsync(&flags, K->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -797,9 +837,8 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       ZK_TRY(draw_to(K->d_perm_z + s * nb + (n - bf) * 32, bf));
       rpos += 1;
     }
-    ZK_TRY(side(2, [&](zk_domain* d) -> int {
-      ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)K->d_perm_z, (zk_fr*)K->d_perm_z_polys, NS));
-      return zk_coeff_to_extended_dev(d, (const zk_fr*)K->d_perm_z_polys, slot_z(0), NS);
+    ZK_TRY(side(2, [&](zk_domain* d, zk_ctx* on) -> int {
+      return transform_columns(K, d, on, K->d_perm_z, K->d_perm_z_polys, NS, [&](size_t i) { return slot_z((uint32_t)i); }, true);
     }));
     std::vector<HostPoint> pts;
     ZK_TRY(commit(K, K->d_perm_z, NS, ZK_BASES_G_LAGRANGE, &pts));
@@ -817,10 +856,8 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       ZK_TRY(draw_to(lk(l, 4) + (n - bf) * 32, bf));
       rpos += 1;
     }
-    ZK_TRY(side(3, [&](zk_domain* d) -> int {
-      ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)lk(0, 4), (zk_fr*)lkp(0, 2), L));
-      for (uint32_t l = 0; l < L; l++) ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)lkp(l, 2), slot_lk(l, 0), 1));
-      return ZK_OK;
+    ZK_TRY(side(3, [&](zk_domain* d, zk_ctx* on) -> int {
+      return transform_columns(K, d, on, lk(0, 4), lkp(0, 2), L, [&](size_t i) { return slot_lk((uint32_t)i, 0); }, false);
     }));
     std::vector<HostPoint> pts;
     ZK_TRY(commit(K, lk(0, 4), L, ZK_BASES_G_LAGRANGE, &pts));
@@ -851,7 +888,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     if (world > 1 && (K->ext_n % world) == 0) {          // every GPU evaluates its slice of the extended rows
       const size_t rows = K->ext_n / world, r0 = rows * zk_group_rank(K->group);
       ZK_TRY(zk_evaluate_h_launch(K->pk, ch.data(), &yh, &bh, &gh, &th, (zk_fr*)K->d_hext, r0, r0 + rows));
-      ZK_TRY(zk_group_allgather(K->group, K->d_hext, rows * 32));
+      ZK_TRY(zk_group_allgather(K->group, ctx, K->d_hext, rows * 32));
     } else {
       ZK_TRY(zk_evaluate_h_launch(K->pk, ch.data(), &yh, &bh, &gh, &th, (zk_fr*)K->d_hext, 0, K->ext_n));
     }

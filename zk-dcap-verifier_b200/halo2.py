@@ -617,7 +617,7 @@ class Group:
     @staticmethod
     def unique_id():
         lib = _abi.load()
-        buf = (C.c_uint8 * 128)()
+        buf = (C.c_uint8 * 256)()
         if lib.zk_group_unique_id(buf) != 0:
             raise ZkError("zk_group_unique_id failed (NCCL not available)")
         return bytes(buf)
@@ -625,7 +625,7 @@ class Group:
     def __init__(self, ctx, rank, world, uid):
         self.ctx, self.rank, self.world = ctx, rank, world
         h = C.c_void_p()
-        buf = (C.c_uint8 * 128)(*uid)
+        buf = (C.c_uint8 * 256)(*uid)
         ctx.check(ctx.lib.zk_group_create(ctx.h, rank, world, buf, C.byref(h)))
         self.h = h
 
