@@ -30,6 +30,8 @@ typedef int (*fn_comm_init)(void**, int, nccl_uid, int);
 typedef int (*fn_comm_destroy)(void*);
 typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef const char* (*fn_err)(int);
+typedef int (*fn_sendrecv)(void*, size_t, int, int, void*, cudaStream_t);     // ncclSend (const void*) / ncclRecv share this shape
+typedef int (*fn_group)(void);
 
 struct Nccl {
   void* lib = nullptr;
@@ -38,6 +40,8 @@ struct Nccl {
   fn_comm_destroy comm_destroy = nullptr;
   fn_allgather allgather = nullptr;
   fn_err err = nullptr;
+  fn_sendrecv send = nullptr, recv = nullptr;
+  fn_group group_start = nullptr, group_end = nullptr;
 };
 Nccl* nccl() {
   static Nccl N;
@@ -51,6 +55,8 @@ Nccl* nccl() {
       N.comm_destroy = (fn_comm_destroy)dlsym(N.lib, "ncclCommDestroy");
       N.allgather = (fn_allgather)dlsym(N.lib, "ncclAllGather");
       N.err = (fn_err)dlsym(N.lib, "ncclGetErrorString");
+      N.send = (fn_sendrecv)dlsym(N.lib, "ncclSend"); N.recv = (fn_sendrecv)dlsym(N.lib, "ncclRecv");
+      N.group_start = (fn_group)dlsym(N.lib, "ncclGroupStart"); N.group_end = (fn_group)dlsym(N.lib, "ncclGroupEnd");
       if (!N.get_uid || !N.comm_init || !N.comm_destroy || !N.allgather) N.lib = nullptr;
     }
   }
@@ -119,6 +125,44 @@ int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_ra
   int r = N->allgather((const char*)d_buf + (size_t)g->rank * bytes_per_rank, d_buf, bytes_per_rank, /*ncclChar*/ 0, comm, ctx->stream);
   zk_timing_end(ctx);
   if (r != 0) ZK_FAIL(ctx, ZK_ERR_CUDA, "group: ncclAllGather: %s", N->err ? N->err(r) : "error");
+  return ZK_OK;
+}
+
+// Row-slice exchange of full-height columns.  Column c (c < count; `col(c)` = its device address on THIS rank, the same
+// layout on every rank) is owned by rank c / per and complete there; afterwards every rank q also holds rows
+// [q * rows - halo, (q + 1) * rows + halo) (mod height) of every column -- what its slice of h(X) reads.  One grouped
+// ncclSend / ncclRecv batch; nothing is staged.
+int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, size_t count, size_t per, size_t height, size_t halo) {
+  zk_ctx* ctx = on ? on : g->ctx;
+  Nccl* N = nccl();
+  if (!N || !N->send || !N->recv || !N->group_start || !N->group_end) ZK_FAIL(ctx, ZK_ERR_STATE, "group: NCCL point-to-point not available");
+  void* comm = ctx == g->ctx ? g->comm : g->comm2;
+  const size_t rows = height / g->world;
+  zk_timing_begin(ctx, "group_exchange_rows");
+  int r = N->group_start();
+  for (size_t c = 0; c < count && r == 0; c++) {
+    const uint32_t owner = (uint32_t)(c / per);
+    for (uint32_t q = 0; q < g->world && r == 0; q++) {
+      // the peer's rows as up to two contiguous pieces of the (cyclic) column
+      if (owner != g->rank && q != g->rank) continue;
+      if (owner == q) continue;                                  // the owner already has everything
+      const uint32_t peer = owner == g->rank ? q : owner;        // I send to q, or I (= q) receive from the owner
+      size_t lo = (size_t)q * rows + height - halo, len = rows + 2 * halo;      // start taken mod height below
+      if (len >= height) { lo = 0; len = height; }
+      lo %= height;
+      size_t first = std::min(len, height - lo);
+      for (int piece = 0; piece < 2 && r == 0; piece++) {
+        size_t off = piece == 0 ? lo : 0, n = piece == 0 ? first : len - first;
+        if (!n) continue;
+        char* p = cols[c] + off * 32;
+        r = owner == g->rank ? N->send(p, n * 32, /*ncclChar*/ 0, (int)peer, comm, ctx->stream)
+                             : N->recv(p, n * 32, 0, (int)peer, comm, ctx->stream);
+      }
+    }
+  }
+  int r2 = N->group_end();
+  zk_timing_end(ctx);
+  if (r != 0 || r2 != 0) ZK_FAIL(ctx, ZK_ERR_CUDA, "group: row exchange: %s", N->err ? N->err(r ? r : r2) : "error");
   return ZK_OK;
 }
 

@@ -32,6 +32,7 @@ int zk_evaluate_h_launch(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, con
                          const zk_fr* theta, zk_fr* d_out_ext, size_t row0, size_t row1);
 struct zk_group;
 int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank);
+int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, size_t count, size_t per, size_t height, size_t halo);
 extern "C" uint32_t zk_group_rank(const zk_group* g);
 extern "C" uint32_t zk_group_world(const zk_group* g);
 extern "C" void zk_group_shard_plan(uint32_t rank, uint32_t world, size_t count, size_t n, int* mode, size_t* per, size_t* lo, size_t* hi);
@@ -60,6 +61,7 @@ struct zk_pkey {
   std::vector<zk_query> advice_queries, fixed_queries;
   Fr transcript_repr;
   Fr omega, omega_inv;
+  uint32_t max_rotation = 0;       // largest |rotation| any expression, the permutation or the lookup arguments use
   // resident key material (Lagrange values and coefficient forms; the cosets live in `pk`)
   char *d_fixed_values = nullptr, *d_fixed_polys = nullptr, *d_sigma_values = nullptr, *d_sigma_polys = nullptr;
   std::vector<zk_g1_affine> fixed_commitments, perm_commitments;
@@ -87,6 +89,7 @@ struct zk_pkey {
   char* d_xchg = nullptr;                                       // group exchange area for commitment points
   char *d_stage_p = nullptr, *d_stage_c = nullptr;              // group staging of coefficient forms / cosets (allocated by set_group)
   size_t stage_cols = 0;
+  size_t halo_rows = 0;                                          // extended rows a slice of h(X) reads beyond its own range (0: exchange whole columns)
   char *d_points = nullptr, *d_ptrs = nullptr, *d_scalars = nullptr, *d_partial = nullptr, *d_evals = nullptr;
   uint32_t max_list = 0, eval_chunks = 1;
   std::vector<void*> allocs;
@@ -264,14 +267,28 @@ int transform_columns(zk_pkey* K, zk_domain* d, zk_ctx* on, const char* values, 
   const size_t per = (count + world - 1) / world;
   const size_t lo = std::min(count, (size_t)rank * per), hi = std::min(count, (size_t)(rank + 1) * per);
   if (per * world > K->stage_cols) ZK_FAIL(on, ZK_ERR_STATE, "prover: group staging holds %zu columns, %zu needed", K->stage_cols, per * world);
-  char* sp = K->d_stage_p; char* sc = K->d_stage_c;
+  char* sp = K->d_stage_p;
+  // coefficient forms go through the staging buffer (every rank needs all of them for the openings); the cosets are
+  // written straight into their slots and only the row slices each rank's part of h(X) reads are exchanged
+  const bool rows_only = K->halo_rows > 0 && (K->ext_n % world) == 0;
+  char* sc = rows_only ? nullptr : K->d_stage_c;
   if (hi > lo) {
     ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)(values + lo * nb), (zk_fr*)(sp + (size_t)rank * per * nb), hi - lo));
-    ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(sp + (size_t)rank * per * nb), (zk_fr*)(sc + (size_t)rank * per * eb), hi - lo));
+    if (rows_only) {
+      if (contiguous) ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(sp + (size_t)rank * per * nb), slot(lo), hi - lo));
+      else for (size_t i = lo; i < hi; i++) ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(sp + ((size_t)rank * per + (i - lo)) * nb), slot(i), 1));
+    } else {
+      ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(sp + (size_t)rank * per * nb), (zk_fr*)(sc + (size_t)rank * per * eb), hi - lo));
+    }
   }
   ZK_TRY(zk_group_allgather(K->group, on, sp, per * nb));
-  ZK_TRY(zk_group_allgather(K->group, on, sc, per * eb));
   ZK_CUDA(on, cudaMemcpyAsync(polys, sp, count * nb, cudaMemcpyDeviceToDevice, on->stream));
+  if (rows_only) {
+    std::vector<char*> cols(count);
+    for (size_t i = 0; i < count; i++) cols[i] = (char*)slot(i);
+    return zk_group_exchange_rows(K->group, on, cols.data(), count, per, K->ext_n, K->halo_rows);
+  }
+  ZK_TRY(zk_group_allgather(K->group, on, sc, per * eb));
   if (contiguous) {
     ZK_CUDA(on, cudaMemcpyAsync(slot(0), sc, count * eb, cudaMemcpyDeviceToDevice, on->stream));
   } else {
@@ -439,6 +456,8 @@ extern "C" int zk_pkey_set_group(zk_pkey* K, zk_group* g) {
     ZK_CUDA(ctx, cudaMalloc(&q, cols * K->ext_n * 32));
     K->allocs.push_back(p); K->allocs.push_back(q);
     K->d_stage_p = (char*)p; K->d_stage_c = (char*)q; K->stage_cols = cols;
+    // rows of the extended domain that evaluate_h reads relative to its own row: rotation * 2^(ext_k - k)
+    if (!getenv("ZK_GROUP_ALLGATHER_COSETS")) K->halo_rows = (size_t)K->max_rotation * (K->ext_n / K->n);
   }
   return ZK_OK;
 }
@@ -490,6 +509,15 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
   for (auto& q : K->advice_queries) if (q.column >= D.n_advice) { zk_pkey_destroy(K); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: advice query column out of range"); }
   for (auto& q : K->fixed_queries) if (q.column >= D.n_fixed) { zk_pkey_destroy(K); ZK_FAIL(ctx, ZK_ERR_ARG, "zk_keygen: fixed query column out of range"); }
   K->transcript_repr = f_from_abi<Fr>(&cd->transcript_repr);
+  {
+    auto scan = [&](const zk_graph& g) {
+      for (uint32_t i = 0; i < g.n_rotations; i++) K->max_rotation = std::max<uint32_t>(K->max_rotation, (uint32_t)abs(g.rotations[i]));
+    };
+    scan(D.custom_gates);
+    for (uint32_t l = 0; l < D.n_lookups; l++) scan(D.lookups[l]);
+    if (D.n_lookups) K->max_rotation = std::max<uint32_t>(K->max_rotation, 1);
+    if (D.n_perm_columns) K->max_rotation = std::max<uint32_t>(K->max_rotation, D.blinding_factors + 1);
+  }
   KG(zk_domain_create(ctx, D.degree, D.k, &K->dom));
   K->ext_n = zk_domain_ext_n(K->dom);
   for (auto& e : K->ev_copy) KG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
