@@ -96,3 +96,32 @@ extern "C" int evh_run(const zk_evaluator_desc* desc, const void* const* cols, c
   stats[0] = C.muls_per_row; stats[1] = C.columns_read; stats[2] = C.n_slots; stats[3] = C.max_intermediates;
   return 0;
 }
+
+// ---- transcript.hpp (Blake2b-512, Blake2bWrite, Fr::from_bytes_wide, point compression) on the host ----------------
+#include "../../zk-dcap-verifier_b200/csrc/transcript.hpp"
+// ops: a sequence of records  [kind (1 byte)] [payload]; kind 0 = squeeze (no payload; 32-byte challenge appended to
+// `out`), 1 = write_point (64 bytes: x, y canonical little-endian), 2 = write_scalar (32 bytes canonical), 3 = common_scalar.
+// Returns the number of bytes written to `out`; the proof bytes are copied to `proof` (proof_len receives their count).
+extern "C" size_t transcript_replay(const unsigned char* ops, size_t n_ops_bytes, unsigned char* out, unsigned char* proof,
+                                    size_t* proof_len) {
+  TranscriptWrite t;
+  size_t pos = 0, w = 0;
+  auto canon_to_mont_fr = [](const unsigned char* p) { Fr v; memcpy(v.l, p, 32); return v.to_mont(); };
+  auto canon_to_mont_fq = [](const unsigned char* p) { Fq v; memcpy(v.l, p, 32); return v.to_mont(); };
+  while (pos < n_ops_bytes) {
+    unsigned char kind = ops[pos++];
+    if (kind == 0) {
+      Fr c = t.squeeze_challenge();
+      f_to_repr(c, out + w); w += 32;
+    } else if (kind == 1) {
+      t.write_point(canon_to_mont_fq(ops + pos), canon_to_mont_fq(ops + pos + 32), false); pos += 64;
+    } else if (kind == 2) {
+      t.write_scalar(canon_to_mont_fr(ops + pos)); pos += 32;
+    } else {
+      t.common_scalar(canon_to_mont_fr(ops + pos)); pos += 32;
+    }
+  }
+  memcpy(proof, t.proof.data(), t.proof.size());
+  *proof_len = t.proof.size();
+  return w;
+}

@@ -118,3 +118,39 @@ def test_signed_digit_recoding(ffh, c):
         assert d[W] == 0, "carry out of the top window"
         assert all(-(1 << (c - 1)) < int(x) <= (1 << (c - 1)) for x in d[:W])
         assert sum(int(x) << (c * w) for w, x in enumerate(d[:W])) == v
+
+
+def test_blake2b_transcript_host_build_matches_python(ffh):
+    """csrc/transcript.hpp (Blake2b-512 with personalisation, Challenge255 = from_bytes_wide, point compression) replayed
+    on the host against oracle/prover.py's hashlib-based transcript, across block boundaries."""
+    import ctypes as C
+    import random
+    from oracle import prover as op
+    from oracle import pymodel as pm
+    rnd = random.Random(7)
+    t = op.Blake2bWrite()
+    ops = bytearray()
+    want_ch = []
+    pts = [pm.ec_mul(rnd.randrange(1, pm.R_MOD), (1, 2)) for _ in range(6)]
+    for step in range(60):
+        kind = rnd.choice([0, 1, 2, 2, 3])
+        if kind == 0:
+            ops.append(0); want_ch.append(t.squeeze_challenge())
+        elif kind == 1:
+            p = rnd.choice(pts)
+            ops.append(1); ops += p[0].to_bytes(32, "little") + p[1].to_bytes(32, "little"); t.write_point(p)
+        elif kind == 2:
+            s = rnd.randrange(pm.R_MOD)
+            ops.append(2); ops += s.to_bytes(32, "little"); t.write_scalar(s)
+        else:
+            s = rnd.randrange(pm.R_MOD)
+            ops.append(3); ops += s.to_bytes(32, "little"); t.common_scalar(s)
+    out = (C.c_ubyte * (32 * (len(want_ch) + 1)))()
+    proof = (C.c_ubyte * (len(t.proof) + 64))()
+    plen = C.c_size_t()
+    ffh.transcript_replay.restype = C.c_size_t
+    w = ffh.transcript_replay(bytes(ops), C.c_size_t(len(ops)), out, proof, C.byref(plen))
+    assert w == 32 * len(want_ch)
+    got = [int.from_bytes(bytes(out[32 * i:32 * i + 32]), "little") for i in range(len(want_ch))]
+    assert got == want_ch
+    assert bytes(proof[:plen.value]) == t.finalize()
