@@ -38,6 +38,7 @@ pub struct zk_circuit_desc {
     pub transcript_repr: zk_fr,
 }
 #[repr(C)] pub struct zk_pkey { _p: [u8; 0] }
+#[repr(C)] pub struct zk_group { _p: [u8; 0] }
 pub const ZK_BASES_HOST: c_int = 0;
 pub const ZK_BASES_G: c_int = 1;
 pub const ZK_BASES_G_LAGRANGE: c_int = 2;
@@ -73,4 +74,15 @@ extern "C" {
     pub fn zk_create_proof(pk: *mut zk_pkey, advice_values: *const *const zk_fr, instance_values: *const *const zk_fr,
                            instance_lens: *const u32, randoms: *const zk_fr, n_randoms: usize, proof: *mut u8, proof_cap: usize,
                            proof_len: *mut usize) -> c_int;
+    // ParamsKZG::{read, write}, G1Affine::{to_bytes, from_bytes} on the device
+    pub fn zk_params_read(ctx: *mut zk_ctx, file: *const u8, len: usize, precompute_windows: c_int, k_out: *mut u32,
+                          g2: *mut u8, s_g2: *mut u8) -> c_int;
+    pub fn zk_params_write(ctx: *mut zk_ctx, g2: *const u8, s_g2: *const u8, file: *mut u8, cap: usize, len: *mut usize) -> c_int;
+    pub fn zk_g1_compress(ctx: *mut zk_ctx, points: *const zk_g1_affine, n: usize, out: *mut u8) -> c_int;
+    pub fn zk_g1_decompress(ctx: *mut zk_ctx, input: *const u8, n: usize, out: *mut zk_g1_affine) -> c_int;
+    // one proof over several GPUs (one process per GPU)
+    pub fn zk_group_unique_id(id: *mut u8) -> c_int;                 // 256 bytes
+    pub fn zk_group_create(ctx: *mut zk_ctx, rank: u32, world: u32, id: *const u8, out: *mut *mut zk_group) -> c_int;
+    pub fn zk_group_destroy(g: *mut zk_group);
+    pub fn zk_pkey_set_group(pk: *mut zk_pkey, g: *mut zk_group) -> c_int;
 }

@@ -112,6 +112,19 @@ int zk_g1_fixed_base_mul_dev(zk_ctx* ctx, const zk_g1_affine* base, const zk_fr*
  * against the SRS that `src` keeps resident; `src` must outlive `dst`'s use. */
 int zk_ctx_share_srs(zk_ctx* dst, const zk_ctx* src);
 
+/* ParamsKZG::read / write (poly/kzg/commitment.rs; halo2-base gen_srs keeps params/kzg_bn254_{k}.srs):
+ *   k (u32 LE) | n compressed g | n compressed g_lagrange | g2 (64 B) | s_g2 (64 B)
+ * zk_params_read decompresses the 2n points on the device (one square root in Fq each) and keeps them resident
+ * exactly like zk_srs_upload; g2 / s_g2 are returned as the opaque 64-byte encodings (the prover never uses them).
+ * zk_params_write serialises the resident SRS.  Point encoding = halo2curves 0.3.1 G1Affine::to_bytes. */
+int zk_params_read(zk_ctx* ctx, const uint8_t* file, size_t len, int precompute_windows, uint32_t* k_out,
+                   uint8_t g2[64], uint8_t s_g2[64]);
+int zk_params_write(zk_ctx* ctx, const uint8_t g2[64], const uint8_t s_g2[64], uint8_t* file, size_t cap, size_t* len);
+/* G1Affine::to_bytes / from_bytes for n points (host or device pointers in, host out); decompression fails with
+ * ZK_ERR_ARG on a non-canonical x or a point that is not on the curve. */
+int zk_g1_compress(zk_ctx* ctx, const zk_g1_affine* points, size_t n, uint8_t* out);
+int zk_g1_decompress(zk_ctx* ctx, const uint8_t* in, size_t n, zk_g1_affine* out);
+
 /* ---- best_multiexp ------------------------------------------------------ */
 
 typedef enum { ZK_BASES_HOST = 0, ZK_BASES_G = 1, ZK_BASES_G_LAGRANGE = 2 } zk_bases;

@@ -255,3 +255,54 @@ def test_batched_affine_round_forced():
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
                         "(multiexp or commit or linearity) and not forced"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+# ---- ParamsKZG file format, point compression (csrc/params.cu) ------------------------------------------------------
+def test_point_compression_round_trip_and_bytes(ctx, orc):
+    from oracle import prover as op
+    from oracle import pymodel as pm
+    pts = orc.gen_points(77, 300)
+    pts[5] = 0                                                     # the identity
+    comp = zk.g1_compress(pts, ctx)
+    want = [op.compress_point(p) for p in pm.limbs_to_affine(pts)]
+    assert [bytes(c) for c in comp] == want
+    back = zk.g1_decompress(comp, ctx)
+    assert np.array_equal(back, pts)
+    # negated y flips the sign bit only
+    neg = pts.copy()
+    neg[:, 4:] = orc.field_op("fq", "neg", pts[:, 4:])
+    neg[5] = 0
+    comp2 = zk.g1_compress(neg, ctx)
+    assert np.array_equal(comp2[:, :31], comp[:, :31]) and np.array_equal(np.delete(comp2[:, 31] ^ comp[:, 31], 5), np.full(299, 0x80, np.uint8))
+    assert np.array_equal(zk.g1_decompress(comp2, ctx), neg)
+    # invalid encodings: x >= p, and an x whose x^3 + 3 is not a square
+    bad = comp.copy()
+    bad[0] = np.frombuffer((pm.P_MOD + 1).to_bytes(32, "little"), dtype=np.uint8)
+    with pytest.raises(zk.ZkError):
+        zk.g1_decompress(bad, ctx)
+    x = 4
+    while pow((x ** 3 + 3) % pm.P_MOD, (pm.P_MOD - 1) // 2, pm.P_MOD) == 1:
+        x += 1
+    bad = comp.copy()
+    bad[0] = np.frombuffer(x.to_bytes(32, "little"), dtype=np.uint8)
+    with pytest.raises(zk.ZkError):
+        zk.g1_decompress(bad, ctx)
+
+
+def test_params_file_round_trip(ctx, orc):
+    from oracle import prover as op
+    from oracle import pymodel as pm
+    k = 6
+    n = 1 << k
+    g, gl = orc.gen_points(91, n), orc.gen_points(92, n)
+    g2 = bytes(range(64)); s_g2 = bytes(range(64, 128))
+    data = (k).to_bytes(4, "little") + b"".join(op.compress_point(p) for p in pm.limbs_to_affine(g)) + \
+        b"".join(op.compress_point(p) for p in pm.limbs_to_affine(gl)) + g2 + s_g2
+    params = zk.ParamsKZG.read(data, ctx)
+    assert params.k == k and bytes(params.g2) == g2 and bytes(params.s_g2) == s_g2
+    poly = orc.gen_scalars(93, n)
+    assert np.array_equal(orc.g1_to_affine(params.commit(poly)), orc.g1_to_affine(orc.best_multiexp(poly, g)))
+    assert np.array_equal(orc.g1_to_affine(params.commit_lagrange(poly)), orc.g1_to_affine(orc.best_multiexp(poly, gl)))
+    assert params.write() == data
+    with pytest.raises(zk.ZkError):
+        zk.ParamsKZG.read(data[:-1], ctx)

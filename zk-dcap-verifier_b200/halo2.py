@@ -159,6 +159,24 @@ def best_fft(a, omega, log_n, ctx=None):
     return a
 
 
+def g1_compress(points, ctx=None):
+    """G1Affine::to_bytes for (n, 8) points -> (n, 32) uint8"""
+    ctx = ctx or default_context()
+    points = _u64(points, (-1, 8))
+    out = np.empty((points.shape[0], 32), dtype=np.uint8)
+    ctx.check(ctx.lib.zk_g1_compress(ctx.h, _ptr(points), points.shape[0], _ptr(out)))
+    return out
+
+
+def g1_decompress(data, ctx=None):
+    """G1Affine::from_bytes for (n, 32) uint8 -> (n, 8) points; raises on an invalid encoding"""
+    ctx = ctx or default_context()
+    data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 32)
+    out = np.empty((data.shape[0], 8), dtype=np.uint64)
+    ctx.check(ctx.lib.zk_g1_decompress(ctx.h, _ptr(data), data.shape[0], _ptr(out)))
+    return out
+
+
 def g1_sum(points, ctx=None):
     ctx = ctx or default_context()
     points = _u64(points, (-1, 12))
@@ -177,6 +195,28 @@ class ParamsKZG:
         g = _u64(g, (self.n, 8))
         gl = _u64(g_lagrange, (self.n, 8))
         self.ctx.check(self.ctx.lib.zk_srs_upload(self.ctx.h, k, _ptr(g), _ptr(gl), 1 if precompute else 0))
+
+    @classmethod
+    def read(cls, data, ctx=None, precompute=True):
+        """ParamsKZG::read: `data` = bytes of a kzg_bn254_{k}.srs file; the points are decompressed on the device."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        k = C.c_uint32()
+        self.g2, self.s_g2 = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+        self.ctx.check(self.ctx.lib.zk_params_read(self.ctx.h, _ptr(buf), buf.size, 1 if precompute else 0, C.byref(k),
+                                                   _ptr(self.g2), _ptr(self.s_g2)))
+        self.k, self.n = k.value, 1 << k.value
+        return self
+
+    def write(self, g2=None, s_g2=None):
+        """ParamsKZG::write of the resident SRS -> bytes"""
+        out = np.empty(4 + 2 * self.n * 32 + 128, dtype=np.uint8)
+        ln = C.c_size_t()
+        g2 = np.ascontiguousarray(g2 if g2 is not None else getattr(self, "g2", np.zeros(64, np.uint8)), dtype=np.uint8)
+        s_g2 = np.ascontiguousarray(s_g2 if s_g2 is not None else getattr(self, "s_g2", np.zeros(64, np.uint8)), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.zk_params_write(self.ctx.h, _ptr(g2), _ptr(s_g2), _ptr(out), out.size, C.byref(ln)))
+        return out[:ln.value].tobytes()
 
     def _commit(self, poly, which):
         poly = _u64(poly, (-1, 4))
