@@ -519,6 +519,59 @@ def verify_gpu_proof(wl):
     return bool(ov.verify_proof(vp, vk, wl.cs, wl.k, [], wl.last_proof))
 
 
+def verify_native(wl):
+    """The library's own verifier (zk_verify_proof: host code with its own pairing) on the device's proof."""
+    from zkdcap_b200 import verify_proof
+    fc, pc = wl.key.vk_commitments()
+    # [s]G2 of the synthetic setup, computed with the product's scalar field only: G2 arithmetic lives in the verifier,
+    # so the uncompressed encodings are produced once by the small affine ladder below
+    g2, s_g2 = g2_encodings(TRAPDOOR)
+    g1 = np.concatenate([wl.zk.fq_to_limbs(1), wl.zk.fq_to_limbs(2)])
+    return bool(verify_proof(wl.circ, fc, pc, g1, g2, s_g2, [], wl.last_proof))
+
+
+P_MOD = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+G2_GEN = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+           11559732032986387107991004021392285783925812861821192530917403151452391805634),
+          (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+           4082367875863433681332203403145435568316851327593401208105741076214120093531))
+
+
+def g2_encodings(s):
+    """(G2, [s]G2) as 128 uncompressed bytes each (x.c0, x.c1, y.c0, y.c1 little-endian): plain affine double-and-add
+    over Fq2 on Python integers -- setup of the synthetic SRS, not part of any measured path."""
+    p = P_MOD
+    mul = lambda a, b: ((a[0] * b[0] - a[1] * b[1]) % p, (a[0] * b[1] + a[1] * b[0]) % p)
+    sub = lambda a, b: ((a[0] - b[0]) % p, (a[1] - b[1]) % p)
+
+    def inv(a):
+        d = pow((a[0] * a[0] + a[1] * a[1]) % p, -1, p)
+        return (a[0] * d % p, (-a[1]) * d % p)
+
+    def add(P, Q):
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        if P[0] == Q[0]:
+            if P[1] != Q[1] or P[1] == (0, 0):
+                return None
+            xx = mul(P[0], P[0])
+            m = mul(((3 * xx[0]) % p, (3 * xx[1]) % p), inv(((2 * P[1][0]) % p, (2 * P[1][1]) % p)))
+        else:
+            m = mul(sub(Q[1], P[1]), inv(sub(Q[0], P[0])))
+        x3 = sub(sub(mul(m, m), P[0]), Q[0])
+        return (x3, sub(mul(m, sub(P[0], x3)), P[1]))
+    acc, base, e = None, G2_GEN, s
+    while e:
+        if e & 1:
+            acc = add(acc, base)
+        base = add(base, base)
+        e >>= 1
+    enc = lambda q: b"".join(v.to_bytes(32, "little") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
+    return enc(G2_GEN), enc(acc)
+
+
 def cpu_tail_sample(orc, zk, shapes, cs, k, threads):
     """Times the prover's loops BETWEEN the hot-path calls on the CPU oracle (one lookup argument, one permutation
     set, a few evaluations, one kate division, one linear combination) and scales by their counts."""
@@ -894,12 +947,18 @@ def main():
                 cpu["proof_bytes"] = len(wl.last_proof)
         except Exception as ex:          # the oracle is a checker; its absence must not hide the GPU number
             cpu = {"value": None, "unit": "proofs/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+    verified = None
+    if full:
+        try:
+            verified = verify_native(wl)
+        except Exception as ex:
+            verified = "failed: %r" % (ex,)
     line = {"metric": metric, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_step_one_stream": ms_serial,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "u32 limbs (254-bit modular)", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "int_pipe": int_pipe,
-            "kernels": fam, "cpu_baseline": cpu, "batch": batch}
+            "kernels": fam, "cpu_baseline": cpu, "batch": batch, "proof_verified": verified}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

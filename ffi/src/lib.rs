@@ -36,6 +36,12 @@ pub struct zk_circuit_desc {
     pub advice_queries: *const zk_query, pub n_advice_queries: u32,
     pub fixed_queries: *const zk_query, pub n_fixed_queries: u32,
     pub transcript_repr: zk_fr,
+    pub instance_queries: *const zk_query, pub n_instance_queries: u32,
+}
+#[repr(C)]
+pub struct zk_verifier_params {
+    pub fixed_commitments: *const zk_g1_affine, pub permutation_commitments: *const zk_g1_affine,
+    pub g1: zk_g1_affine, pub g2: *const u8, pub s_g2: *const u8,
 }
 #[repr(C)] pub struct zk_pkey { _p: [u8; 0] }
 #[repr(C)] pub struct zk_group { _p: [u8; 0] }
@@ -85,4 +91,7 @@ extern "C" {
     pub fn zk_group_create(ctx: *mut zk_ctx, rank: u32, world: u32, id: *const u8, out: *mut *mut zk_group) -> c_int;
     pub fn zk_group_destroy(g: *mut zk_group);
     pub fn zk_pkey_set_group(pk: *mut zk_pkey, g: *mut zk_group) -> c_int;
+    // verify_proof (host code with its own BN254 pairing)
+    pub fn zk_verify_proof(circuit: *const zk_circuit_desc, vp: *const zk_verifier_params, instance_values: *const *const zk_fr,
+                           instance_lens: *const u32, proof: *const u8, proof_len: usize, accepted: *mut c_int) -> c_int;
 }

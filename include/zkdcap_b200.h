@@ -301,6 +301,7 @@ typedef struct {
   const zk_query* fixed_queries;  uint32_t n_fixed_queries;    /* cs.fixed_queries, in order */
   zk_fr transcript_repr;             /* vk.transcript_repr: upstream hashes the Debug string of the pinned
                                         vk, which only Rust can produce -- supplied by the caller */
+  const zk_query* instance_queries; uint32_t n_instance_queries;   /* cs.instance_queries (read by zk_verify_proof only) */
 } zk_circuit_desc;
 
 typedef struct zk_pkey zk_pkey;
@@ -335,6 +336,23 @@ int zk_create_proof(zk_pkey* pk, const zk_fr* const* advice_values,
                     const zk_fr* const* instance_values, const uint32_t* instance_lens,
                     const zk_fr* randoms, size_t n_randoms,
                     uint8_t* proof, size_t proof_cap, size_t* proof_len);
+
+/* ---- verify_proof (plonk/verifier.rs, VerifierSHPLONK, SingleStrategy) -------- */
+/* the check the reference makes at circuits/src/sgx_dcap_verifier.rs:827-843 and
+ * bin/src/main.rs:244-251, on the HOST (a few hundred field operations per column, ~150 scalar multiplications and
+ * two BN254 optimal-ate pairings; no device needed).  g2 / s_g2: ParamsKZG.g2 and .s_g2 as 128 uncompressed bytes
+ * (x.c0, x.c1, y.c0, y.c1 canonical little-endian); g1 = params.g[0]. */
+typedef struct {
+  const zk_g1_affine* fixed_commitments;        /* vk.fixed_commitments, ev.n_fixed */
+  const zk_g1_affine* permutation_commitments;  /* vk.permutation.commitments, ev.n_perm_columns */
+  zk_g1_affine g1;
+  const uint8_t* g2;
+  const uint8_t* s_g2;
+} zk_verifier_params;
+/* *accepted = 1 when the proof verifies, 0 otherwise (malformed proofs are rejected, not errors). */
+int zk_verify_proof(const zk_circuit_desc* circuit, const zk_verifier_params* vp,
+                    const zk_fr* const* instance_values, const uint32_t* instance_lens,
+                    const uint8_t* proof, size_t proof_len, int* accepted);
 
 /* ---- one proof over several GPUs ------------------------- */
 /* One process per GPU, as torch.distributed launches them.  Every rank creates its own context, SRS and key from the

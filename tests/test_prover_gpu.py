@@ -41,6 +41,11 @@ def test_proof_bytes_match_the_cpu_prover(ctx, shape, k, seed):
     got = key.create_proof(case["advice"], case["instances_limbs"], case["randoms"])
     assert len(got) == len(want) and got == want, "first differing 32-byte item: %d of %d" % (first_diff(got, want), len(want) // 32)
     assert ov.verify_proof(pc.verifier_params(), opk["vk"], case["cs"], k, case["instances_int"], got)
+    # the library's own verifier, fed with the device's vk commitments
+    from tests.test_verifier_host import g2_bytes
+    vp = pc.verifier_params()
+    assert zk.verify_proof(case["circ"], fc, pcm, pm.affine_to_limbs([(1, 2)])[0], g2_bytes(vp["g2"]), g2_bytes(vp["s_g2"]),
+                           case["instances_limbs"], got)
     # a second proof on the same key (work area reuse) with another RNG stream
     rnd2 = orc.gen_scalars(4242, key.randoms_needed)
     got2 = key.create_proof(case["advice"], case["instances_limbs"], rnd2)

@@ -1,0 +1,59 @@
+"""CPU: zk_verify_proof (csrc/verifier.cu: transcript replay, expected h(x), SHPLONK, its own BN254 pairing) against the
+oracle's provers and verifier.  The C++ verifier and oracle/verifier.py share no code (C++ tower arithmetic on the
+Montgomery limbs vs Python integers), so agreement on acceptance AND on every rejection below pins both."""
+import random
+
+import numpy as np
+import pytest
+
+import zkdcap_b200 as zk
+from oracle import oracle as orc
+from oracle import prover as op
+from oracle import pymodel as pm
+from oracle import verifier as ov
+from tests import prover_common as pc
+
+
+def g2_bytes(q):
+    return b"".join(v.to_bytes(32, "little") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
+
+
+def native_verify(case, pk, instances_limbs, proof, s_g2=None):
+    vp = pc.verifier_params()
+    fc = pm.affine_to_limbs(pk["vk"]["fixed_commitments"])
+    pcm = pm.affine_to_limbs(pk["vk"]["permutation_commitments"])
+    g1 = pm.affine_to_limbs([(1, 2)])[0]
+    return zk.verify_proof(case["circ"], fc, pcm, g1, g2_bytes(vp["g2"]), g2_bytes(s_g2 or vp["s_g2"]), instances_limbs, proof)
+
+
+@pytest.mark.parametrize("shape,k", [("toy", 5), ("qe3", 9)])
+def test_native_verifier_agrees_with_the_oracle(shape, k):
+    case = pc.make_case(shape, k, 3)
+    pk = pc.oracle_key(case)
+    proof = op.create_proof(orc, pc.params_for(k), pk, case["circ"], case["advice"], case["instances_int"], case["randoms"])
+    assert ov.verify_proof(pc.verifier_params(), pk["vk"], case["cs"], k, case["instances_int"], proof)
+    assert native_verify(case, pk, case["instances_limbs"], proof)
+    rnd = random.Random(k)
+    for _ in range(12 if shape == "toy" else 4):          # any flipped bit: both reject
+        bad = bytearray(proof)
+        bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+        assert not native_verify(case, pk, case["instances_limbs"], bytes(bad))
+    assert not native_verify(case, pk, case["instances_limbs"], proof[:-32])          # truncated
+    assert not native_verify(case, pk, case["instances_limbs"], proof + bytes(32))    # trailing bytes
+    assert not native_verify(case, pk, case["instances_limbs"], b"")
+    # a different SRS secret on the G2 side must break the pairing equation
+    from oracle import pairing
+    assert not native_verify(case, pk, case["instances_limbs"], proof, s_g2=pairing.g2_mul(pc.TRAPDOOR + 1, pairing.G2_GEN))
+    if case["instances_limbs"]:
+        wrong = [case["instances_limbs"][0].copy()]
+        wrong[0][0] = pm.to_mont_limbs([12345], pm.R_MOD)[0]
+        assert not native_verify(case, pk, wrong, proof)
+
+
+def test_native_verifier_rejects_an_unsatisfied_witness():
+    case = pc.make_case("toy", 5, 4)
+    pk = pc.oracle_key(case)
+    adv = [a.copy() for a in case["advice"]]
+    adv[0][3] = adv[0][7]
+    proof = op.create_proof(orc, pc.params_for(5), pk, case["circ"], adv, case["instances_int"], case["randoms"])
+    assert not native_verify(case, pk, case["instances_limbs"], proof)

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkdcap_b200.so")
+LIB_PATH = os.environ.get("ZKDCAP_B200_LIB") or os.path.join(_HERE, "libzkdcap_b200.so")   # override: A/B builds of the kernels
 
 
 class ZkError(RuntimeError):
@@ -53,7 +53,13 @@ class zk_circuit_desc(C.Structure):
                 ("lookup_inputs", C.POINTER(zk_graph)), ("lookup_tables", C.POINTER(zk_graph)),
                 ("advice_queries", C.POINTER(zk_query)), ("n_advice_queries", C.c_uint32),
                 ("fixed_queries", C.POINTER(zk_query)), ("n_fixed_queries", C.c_uint32),
-                ("transcript_repr", zk_fr)]
+                ("transcript_repr", zk_fr),
+                ("instance_queries", C.POINTER(zk_query)), ("n_instance_queries", C.c_uint32)]
+
+
+class zk_verifier_params(C.Structure):
+    _fields_ = [("fixed_commitments", C.c_void_p), ("permutation_commitments", C.c_void_p),
+                ("g1", C.c_uint64 * 8), ("g2", C.c_void_p), ("s_g2", C.c_void_p)]
 
 
 class zk_kernel_stat(C.Structure):
@@ -84,7 +90,7 @@ SYMBOLS = [
     "zk_pk_upload", "zk_pk_destroy", "zk_pk_domain", "zk_pk_program_stats",
     "zk_evaluate_h", "zk_evaluate_h_dev",
     "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_pkey_aux_ctx", "zk_proof_randoms", "zk_proof_max_bytes",
-    "zk_create_proof",
+    "zk_create_proof", "zk_verify_proof",
     "zk_group_unique_id", "zk_group_create", "zk_group_destroy", "zk_group_rank", "zk_group_world", "zk_pkey_set_group",
     "zk_group_shard_plan",
     "zk_field_op", "zk_bench_modmul", "zk_bench_imad",
@@ -161,6 +167,7 @@ def load():
         "zk_proof_randoms": (sz, [vp]),
         "zk_proof_max_bytes": (sz, [vp]),
         "zk_create_proof": (i32, [vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz)]),
+        "zk_verify_proof": (i32, [C.POINTER(zk_circuit_desc), C.POINTER(zk_verifier_params), vp, vp, vp, sz, C.POINTER(i32)]),
         "zk_group_unique_id": (i32, [vp]),
         "zk_group_create": (i32, [vp, u32, u32, vp, C.POINTER(vp)]),
         "zk_group_destroy": (None, [vp]),

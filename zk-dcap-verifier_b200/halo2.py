@@ -591,6 +591,9 @@ class Circuit:
         d.lookup_inputs, d.lookup_tables = C.cast(li, C.POINTER(_abi.zk_graph)), C.cast(lt, C.POINTER(_abi.zk_graph))
         d.advice_queries, d.n_advice_queries = C.cast(aq, C.POINTER(_abi.zk_query)), len(self.cs.advice_queries)
         d.fixed_queries, d.n_fixed_queries = C.cast(fq, C.POINTER(_abi.zk_query)), len(self.cs.fixed_queries)
+        iq = (_abi.zk_query * max(1, len(self.cs.instance_queries)))(*[_abi.zk_query(c, r) for c, r in self.cs.instance_queries])
+        d.instance_queries, d.n_instance_queries = C.cast(iq, C.POINTER(_abi.zk_query)), len(self.cs.instance_queries)
+        self._keep.append(iq)
         tr = self.transcript_repr * _MONT_R % R_MOD
         for i in range(4):
             d.transcript_repr.l[i] = (tr >> (64 * i)) & 0xFFFFFFFFFFFFFFFF
@@ -757,6 +760,31 @@ class ProverKey:
         self.ctx.check(self.ctx.lib.zk_create_proof(self.h, ta, None, None, C.c_void_p(int(randoms_ptr)), n_randoms,
                                                     _ptr(self._proof_buf), self._proof_buf.size, C.byref(ln)))
         return self._proof_buf[:ln.value].tobytes()
+
+
+def verify_proof(circuit, fixed_commitments, permutation_commitments, g1, g2, s_g2, instances, proof):
+    """verify_proof::<KZGCommitmentScheme<Bn256>, VerifierSHPLONK<_>, Challenge255<_>, Blake2bRead<..>, SingleStrategy<_>>
+    (circuits/src/sgx_dcap_verifier.rs:827-843) on the host.  fixed / permutation commitments: (count, 8) G1Affine;
+    g1: (8,) G1Affine = params.g[0]; g2, s_g2: 128 uncompressed bytes each; instances: one (len, 4) array per column."""
+    lib = _abi.load()
+    cd = circuit.to_c()
+    fc = _u64(fixed_commitments, (-1, 8)) if len(fixed_commitments) else np.zeros((1, 8), np.uint64)
+    pc = _u64(permutation_commitments, (-1, 8)) if len(permutation_commitments) else np.zeros((1, 8), np.uint64)
+    vp = _abi.zk_verifier_params()
+    vp.fixed_commitments, vp.permutation_commitments = fc.ctypes.data, pc.ctypes.data
+    for i, v in enumerate(_u64(g1, (8,))):
+        vp.g1[i] = int(v)
+    b2, bs = np.frombuffer(bytes(g2), dtype=np.uint8), np.frombuffer(bytes(s_g2), dtype=np.uint8)
+    vp.g2, vp.s_g2 = b2.ctypes.data, bs.ctypes.data
+    inst = [_u64(i, (-1, 4)) for i in instances]
+    ti, ki = _ptr_table(inst)
+    lens = (C.c_uint32 * max(1, len(inst)))(*[i.shape[0] for i in inst])
+    pb = np.frombuffer(bytes(proof), dtype=np.uint8)
+    ok = C.c_int(0)
+    rc = lib.zk_verify_proof(C.byref(cd), C.byref(vp), ti, lens, _ptr(pb) if pb.size else None, pb.size, C.byref(ok))
+    if rc != 0:
+        raise ZkError("zk_verify_proof: bad arguments (status %d)" % rc)
+    return bool(ok.value)
 
 
 # ---- device-pointer variants (operands already resident in HBM; asynchronous on the context stream) -----
