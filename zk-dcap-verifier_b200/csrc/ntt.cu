@@ -40,6 +40,10 @@ const int kTileLog = env_int("ZK_NTT_TILE_LOG", kTileLogDefault, 6, 12);
 const int kMaxT = env_int("ZK_NTT_MAX_T", kMaxTDefault, 2, 10) > kTileLog ? kTileLog
                                                                            : env_int("ZK_NTT_MAX_T", kMaxTDefault, 2, 10);
 constexpr int kThreads = 256;
+#ifndef ZK_NTT_UNROLL
+#define ZK_NTT_UNROLL 1
+#endif
+constexpr int kNttUnroll = ZK_NTT_UNROLL;   // butterflies of one stage a thread works on together
 
 struct PassConsts {
   Fr pre[3];    // multiplier for input index i, selected by i mod 3 (pre_mode 1)
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(kThreads, R4 ? ZK_NTT_R4_CTAS : ZK_NTT_MIN_CTA
   }
   for (; u <= t; u++) {
     const uint32_t s = P + u, hb = t - u;             // partner distance 2^hb rows
+#pragma unroll kNttUnroll
     for (uint32_t b = threadIdx.x; b < (tile >> 1); b += kThreads) {
       uint32_t c = b & (C - 1), mm = b >> logC;
       uint32_t m_lo = mm & ((1u << hb) - 1), m_hi = mm >> hb;
