@@ -128,11 +128,11 @@ int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_ra
   return ZK_OK;
 }
 
-// Row-slice exchange of full-height columns.  Column c (c < count; `col(c)` = its device address on THIS rank, the same
-// layout on every rank) is owned by rank c / per and complete there; afterwards every rank q also holds rows
+// Row-slice exchange of full-height columns.  Column c (c < count; cols[c] = its device address on THIS rank, the same
+// layout on every rank) is owned by rank owners[c] and complete there; afterwards every rank q also holds rows
 // [q * rows - halo, (q + 1) * rows + halo) (mod height) of every column -- what its slice of h(X) reads.  One grouped
 // ncclSend / ncclRecv batch; nothing is staged.
-int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, size_t count, size_t per, size_t height, size_t halo) {
+int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, const uint32_t* owners, size_t count, size_t height, size_t halo) {
   zk_ctx* ctx = on ? on : g->ctx;
   Nccl* N = nccl();
   if (!N || !N->send || !N->recv || !N->group_start || !N->group_end) ZK_FAIL(ctx, ZK_ERR_STATE, "group: NCCL point-to-point not available");
@@ -141,7 +141,7 @@ int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, size_t co
   zk_timing_begin(ctx, "group_exchange_rows");
   int r = N->group_start();
   for (size_t c = 0; c < count && r == 0; c++) {
-    const uint32_t owner = (uint32_t)(c / per);
+    const uint32_t owner = owners[c];
     for (uint32_t q = 0; q < g->world && r == 0; q++) {
       // the peer's rows as up to two contiguous pieces of the (cyclic) column
       if (owner != g->rank && q != g->rank) continue;

@@ -32,7 +32,7 @@ int zk_evaluate_h_launch(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, con
                          const zk_fr* theta, zk_fr* d_out_ext, size_t row0, size_t row1);
 struct zk_group;
 int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank);
-int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, size_t count, size_t per, size_t height, size_t halo);
+int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, const uint32_t* owners, size_t count, size_t height, size_t halo);
 extern "C" uint32_t zk_group_rank(const zk_group* g);
 extern "C" uint32_t zk_group_world(const zk_group* g);
 extern "C" void zk_group_shard_plan(uint32_t rank, uint32_t world, size_t count, size_t n, int* mode, size_t* per, size_t* lo, size_t* hi);
@@ -87,7 +87,7 @@ struct zk_pkey {
   uint64_t sort_fallbacks = 0;
   uint32_t* d_flags = nullptr;                                  // [0] failure bits, [1..2] totals, [8..15] diff mask
   char* d_xchg = nullptr;                                       // group exchange area for commitment points
-  char *d_stage_p = nullptr, *d_stage_c = nullptr;              // group staging of coefficient forms / cosets (allocated by set_group)
+  char* d_stage_p = nullptr;                                    // group staging of coefficient forms (allocated by set_group)
   size_t stage_cols = 0;
   size_t halo_rows = 0;                                          // extended rows a slice of h(X) reads beyond its own range (0: exchange whole columns)
   char *d_points = nullptr, *d_ptrs = nullptr, *d_scalars = nullptr, *d_partial = nullptr, *d_evals = nullptr;
@@ -250,49 +250,104 @@ bool is_device_pointer(const void* p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-// lagrange_to_coeff + coeff_to_extended of `count` witness columns on domain `d` (= on d's stream): values (contiguous
-// Lagrange columns) -> polys (contiguous coefficient forms) and the cosets at slot(i).  In a group every rank transforms
-// a share of the columns into the staging buffers, which are all-gathered and copied into place.
-template <class SlotFn>
-int transform_columns(zk_pkey* K, zk_domain* d, zk_ctx* on, const char* values, char* polys, size_t count, SlotFn slot, bool contiguous) {
-  const size_t nb = K->n * 32, eb = K->ext_n * 32;
+// lagrange_to_coeff + coeff_to_extended of witness columns on domain `d` (= on d's stream): values (Lagrange) -> poly
+// (coefficients) and the coset in its evaluate_h slot.  In a group every column has an OWNER rank that transforms it;
+// the coefficient forms are all-gathered through a staging buffer (every rank needs all of them for the openings), the
+// cosets are written straight into their slots and only the row slices each rank's part of h(X) reads are exchanged.
+struct ColJob { const char* values; char* poly; zk_fr* slot; uint32_t owner; };
+int transform_jobs(zk_pkey* K, zk_domain* d, zk_ctx* on, const std::vector<ColJob>& jobs) {
+  const size_t nb = K->n * 32;
   const uint32_t world = K->group ? zk_group_world(K->group) : 1;
-  if (world <= 1 || count < 2 || !K->d_stage_c) {
-    ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)values, (zk_fr*)polys, count));
-    if (contiguous) return zk_coeff_to_extended_dev(d, (const zk_fr*)polys, slot(0), count);
-    for (size_t i = 0; i < count; i++) ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(polys + i * nb), slot(i), 1));
+  const size_t count = jobs.size();
+  if (!count) return ZK_OK;
+  if (world <= 1 || !K->d_stage_p) {
+    // batch runs of adjacent columns into one launch sequence (the cosets only when their slots are adjacent too)
+    for (size_t i = 0; i < count;) {
+      size_t j = i + 1;
+      while (j < count && jobs[j].values == jobs[i].values + (j - i) * nb && jobs[j].poly == jobs[i].poly + (j - i) * nb) j++;
+      ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)jobs[i].values, (zk_fr*)jobs[i].poly, j - i));
+      for (size_t a = i; a < j;) {
+        size_t b = a + 1;
+        while (b < j && (char*)jobs[b].slot == (char*)jobs[a].slot + (b - a) * K->ext_n * 32) b++;
+        ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)jobs[a].poly, jobs[a].slot, b - a));
+        a = b;
+      }
+      i = j;
+    }
     return ZK_OK;
   }
   const uint32_t rank = zk_group_rank(K->group);
-  const size_t per = (count + world - 1) / world;
-  const size_t lo = std::min(count, (size_t)rank * per), hi = std::min(count, (size_t)(rank + 1) * per);
-  if (per * world > K->stage_cols) ZK_FAIL(on, ZK_ERR_STATE, "prover: group staging holds %zu columns, %zu needed", K->stage_cols, per * world);
+  std::vector<size_t> owned(world, 0), kth(count);
+  for (size_t i = 0; i < count; i++) { if (jobs[i].owner >= world) ZK_FAIL(on, ZK_ERR_STATE, "prover: column owner out of range"); kth[i] = owned[jobs[i].owner]++; }
+  size_t maxown = 0;
+  for (auto c : owned) maxown = std::max(maxown, c);
+  if (maxown * world > K->stage_cols) ZK_FAIL(on, ZK_ERR_STATE, "prover: group staging holds %zu columns, %zu needed", K->stage_cols, maxown * world);
   char* sp = K->d_stage_p;
-  // coefficient forms go through the staging buffer (every rank needs all of them for the openings); the cosets are
-  // written straight into their slots and only the row slices each rank's part of h(X) reads are exchanged
-  const bool rows_only = K->halo_rows > 0 && (K->ext_n % world) == 0;
-  char* sc = rows_only ? nullptr : K->d_stage_c;
-  if (hi > lo) {
-    ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)(values + lo * nb), (zk_fr*)(sp + (size_t)rank * per * nb), hi - lo));
-    if (rows_only) {
-      if (contiguous) ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(sp + (size_t)rank * per * nb), slot(lo), hi - lo));
-      else for (size_t i = lo; i < hi; i++) ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(sp + ((size_t)rank * per + (i - lo)) * nb), slot(i), 1));
-    } else {
-      ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(sp + (size_t)rank * per * nb), (zk_fr*)(sc + (size_t)rank * per * eb), hi - lo));
+  for (size_t i = 0; i < count;) {
+    if (jobs[i].owner != rank) { i++; continue; }
+    // a run of my columns that are adjacent in memory (their staging places are adjacent by construction)
+    size_t j = i + 1;
+    while (j < count && jobs[j].owner == rank && kth[j] == kth[i] + (j - i) && jobs[j].values == jobs[i].values + (j - i) * nb) j++;
+    char* mine = sp + ((size_t)rank * maxown + kth[i]) * nb;
+    ZK_TRY(zk_lagrange_to_coeff_oop(d, (const zk_fr*)jobs[i].values, (zk_fr*)mine, j - i));
+    for (size_t a = i; a < j;) {
+      size_t b = a + 1;
+      while (b < j && (char*)jobs[b].slot == (char*)jobs[a].slot + (b - a) * K->ext_n * 32) b++;
+      ZK_TRY(zk_coeff_to_extended_dev(d, (const zk_fr*)(mine + (a - i) * nb), jobs[a].slot, b - a));
+      a = b;
     }
+    i = j;
   }
-  ZK_TRY(zk_group_allgather(K->group, on, sp, per * nb));
-  ZK_CUDA(on, cudaMemcpyAsync(polys, sp, count * nb, cudaMemcpyDeviceToDevice, on->stream));
-  if (rows_only) {
-    std::vector<char*> cols(count);
-    for (size_t i = 0; i < count; i++) cols[i] = (char*)slot(i);
-    return zk_group_exchange_rows(K->group, on, cols.data(), count, per, K->ext_n, K->halo_rows);
+  ZK_TRY(zk_group_allgather(K->group, on, sp, maxown * nb));
+  std::vector<char*> cols(count);
+  std::vector<uint32_t> owners(count);
+  for (size_t i = 0; i < count; i++) {
+    ZK_CUDA(on, cudaMemcpyAsync(jobs[i].poly, sp + ((size_t)jobs[i].owner * maxown + kth[i]) * nb, nb, cudaMemcpyDeviceToDevice, on->stream));
+    cols[i] = (char*)jobs[i].slot; owners[i] = jobs[i].owner;
   }
-  ZK_TRY(zk_group_allgather(K->group, on, sc, per * eb));
-  if (contiguous) {
-    ZK_CUDA(on, cudaMemcpyAsync(slot(0), sc, count * eb, cudaMemcpyDeviceToDevice, on->stream));
-  } else {
-    for (size_t i = 0; i < count; i++) ZK_CUDA(on, cudaMemcpyAsync(slot(i), sc + i * eb, eb, cudaMemcpyDeviceToDevice, on->stream));
+  return zk_group_exchange_rows(K->group, on, cols.data(), owners.data(), count, K->ext_n, K->halo_rows);
+}
+// contiguous columns split evenly over the group (advice, permutation z)
+template <class SlotFn>
+int transform_columns(zk_pkey* K, zk_domain* d, zk_ctx* on, const char* values, char* polys, size_t count, SlotFn slot) {
+  const size_t nb = K->n * 32;
+  const uint32_t world = K->group ? zk_group_world(K->group) : 1;
+  const size_t per = (count + world - 1) / world;
+  std::vector<ColJob> jobs(count);
+  for (size_t i = 0; i < count; i++) jobs[i] = {values + i * nb, polys + i * nb, slot(i), (uint32_t)(i / per)};
+  return transform_jobs(K, d, on, jobs);
+}
+
+// Commitments of arbitrary columns with an owner each: a rank commits the columns it owns (adjacent ones in one batch),
+// the points are all-gathered and returned in list order.  With no group everything is local.
+struct CommitJob { const char* poly; uint32_t owner; };
+int commit_jobs(zk_pkey* K, const std::vector<CommitJob>& jobs, int which, std::vector<HostPoint>* out) {
+  zk_ctx* ctx = K->ctx;
+  const size_t nb = K->n * 32, count = jobs.size();
+  const uint32_t world = K->group ? zk_group_world(K->group) : 1, rank = K->group ? zk_group_rank(K->group) : 0;
+  if (!count) return ZK_OK;
+  std::vector<size_t> owned(world, 0), kth(count);
+  for (size_t i = 0; i < count; i++) { uint32_t o = world > 1 ? jobs[i].owner : 0; kth[i] = owned[o]++; }
+  size_t maxown = 0;
+  for (auto c : owned) maxown = std::max(maxown, c);
+  zk_g1* xchg = (zk_g1*)K->d_xchg;
+  for (size_t i = 0; i < count;) {
+    uint32_t o = world > 1 ? jobs[i].owner : 0;
+    size_t j = i + 1;
+    while (j < count && (world > 1 ? jobs[j].owner : 0) == o && jobs[j].poly == jobs[i].poly + (j - i) * nb) j++;
+    if (o == rank) ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)jobs[i].poly, which, K->n, j - i, xchg + (size_t)rank * maxown + kth[i]));
+    i = j;
+  }
+  if (world > 1) ZK_TRY(zk_group_allgather(K->group, ctx, xchg, maxown * sizeof(zk_g1)));
+  std::vector<zk_g1> h((size_t)world * maxown);
+  ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), xchg, h.size() * sizeof(zk_g1), cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < count; i++) {
+    const zk_g1& p = h[(size_t)(world > 1 ? jobs[i].owner : 0) * maxown + kth[i]];
+    HostPoint q;
+    q.x = f_from_abi<Fq>(&p.x); q.y = f_from_abi<Fq>(&p.y);
+    q.identity = f_from_abi<Fq>(&p.z).is_zero();
+    out->push_back(q);
   }
   return ZK_OK;
 }
@@ -321,14 +376,16 @@ int radix_passes(zk_pkey* K, size_t usable, unsigned nsorts, const std::vector<s
   K->d_idx[0] = idx; K->d_idx[1] = alt;          // d_idx[0] always holds the current order
   return ZK_OK;
 }
-int permute_expression_pairs(zk_pkey* K, size_t usable) {
+// lookups [l0, l0 + Lloc) (all of them on one GPU; a rank's share in a group)
+int permute_expression_pairs(zk_pkey* K, size_t usable, uint32_t l0, uint32_t Lloc) {
   zk_ctx* ctx = K->ctx;
-  const uint32_t L = K->n_lookups;
-  const unsigned nsorts = 2 * L;
+  const uint32_t Ltot = K->n_lookups;
+  if (!Lloc) return ZK_OK;
+  const unsigned nsorts = 2 * Lloc;
   const size_t n = K->n;
-  char* vals = K->d_lookup;                      // planes 0 (cin) and 1 (ctab) are adjacent: 2L columns
+  char* vals = K->d_lookup;                      // planes 0 (cin) and 1 (ctab) are adjacent: Ltot columns each
   dim3 g256(blocks_for(usable, 256), nsorts);
-  ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, g256, 256, 0, (const uint4*)vals, (uint4*)K->d_keys, K->d_idx[0], usable, n);
+  ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, g256, 256, 0, (const uint4*)vals, (uint4*)K->d_keys, K->d_idx[0], usable, n, Lloc, l0, Ltot);
   ZK_CUDA(ctx, cudaMemsetAsync(K->d_masks, 0, (size_t)nsorts * 32, ctx->stream));
   ZK_LAUNCH(ctx, "lookup_sort", k_key_diff_mask, dim3(32, nsorts), 256, 0, (const uint32_t*)K->d_keys, usable, n, K->d_masks);
   std::vector<uint32_t> masks((size_t)nsorts * 8);
@@ -354,21 +411,21 @@ int permute_expression_pairs(zk_pkey* K, size_t usable) {
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (bad) {      // LSD needs the low digits first: redo from the identity order over every varying digit
       K->sort_fallbacks++;
-      ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, g256, 256, 0, (const uint4*)vals, (uint4*)K->d_keys, K->d_idx[0], usable, n);
+      ZK_LAUNCH(ctx, "lookup_sort", k_canon_keys, g256, 256, 0, (const uint4*)vals, (uint4*)K->d_keys, K->d_idx[0], usable, n, Lloc, l0, Ltot);
       ZK_TRY(radix_passes(K, usable, nsorts, varying));
       ZK_LAUNCH(ctx, "lookup_sort", k_gather_keys, g256, 256, 0, (const uint4*)K->d_keys, K->d_idx[0], (uint4*)K->d_sk, usable, n);
     }
   }
   uint32_t *rep = K->d_u32[0], *left = K->d_u32[1], *rrank = K->d_u32[2], *lrank = K->d_u32[3], *rpos = K->d_u32[4];
-  dim3 gl(blocks_for(usable, 256), L);
-  ZK_LAUNCH(ctx, "lookup_permute", k_permute_flags, gl, 256, 0, (const uint32_t*)K->d_sk, usable, n, L, rep, left, K->d_flags);
-  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", rep, rrank, usable, 0, 1, nullptr, L, usable, usable));
-  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", left, lrank, usable, 0, 1, nullptr, L, usable, usable));
-  ZK_LAUNCH(ctx, "lookup_permute", k_permute_totals, blocks_for(L, 64), 64, 0, rep, rrank, left, lrank, usable, L, K->d_totals, K->d_flags);
+  dim3 gl(blocks_for(usable, 256), Lloc);
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_flags, gl, 256, 0, (const uint32_t*)K->d_sk, usable, n, Lloc, rep, left, K->d_flags);
+  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", rep, rrank, usable, 0, 1, nullptr, Lloc, usable, usable));
+  ZK_TRY(run_scan<U32AddMonoid>(K, "lookup_permute", left, lrank, usable, 0, 1, nullptr, Lloc, usable, usable));
+  ZK_LAUNCH(ctx, "lookup_permute", k_permute_totals, blocks_for(Lloc, 64), 64, 0, rep, rrank, left, lrank, usable, Lloc, K->d_totals, K->d_flags);
   ZK_LAUNCH(ctx, "lookup_permute", k_permute_rpos, gl, 256, 0, rep, rrank, rpos, usable);
-  char* cin = K->d_lookup; char* ctab = cin + (size_t)L * n * 32; char* pin = ctab + (size_t)L * n * 32; char* ptab = pin + (size_t)L * n * 32;
+  char* cin = K->d_lookup; char* ctab = cin + (size_t)Ltot * n * 32; char* pin = ctab + (size_t)Ltot * n * 32; char* ptab = pin + (size_t)Ltot * n * 32;
   ZK_LAUNCH(ctx, "lookup_permute", k_permute_write, gl, 256, 0, (const uint4*)cin, (const uint4*)ctab, K->d_idx[0], rep, left, lrank, rpos,
-            K->d_totals, L, (uint4*)pin, (uint4*)ptab, usable, n);
+            K->d_totals, Lloc, (uint4*)pin, (uint4*)ptab, usable, n, l0);
   return ZK_OK;
 }
 
@@ -447,17 +504,16 @@ extern "C" int zk_pkey_set_group(zk_pkey* K, zk_group* g) {
   if (!K) return ZK_ERR_ARG;
   if (g && zk_group_world(g) > 16) ZK_FAIL(K->ctx, ZK_ERR_ARG, "zk_pkey_set_group: at most 16 GPUs");
   K->group = g;
-  if (g && zk_group_world(g) > 1 && !K->d_stage_c && !getenv("ZK_GROUP_NO_NTT_SHARD")) {
+  if (g && zk_group_world(g) > 1 && !K->d_stage_p && !getenv("ZK_GROUP_NO_NTT_SHARD")) {
     zk_ctx* ctx = K->ctx;
     ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-    size_t cols = std::max<size_t>(std::max<size_t>(K->n_advice, 2 * (size_t)K->n_lookups), K->n_sets) + zk_group_world(g);
-    void *p = nullptr, *q = nullptr;
+    size_t cols = std::max<size_t>(std::max<size_t>(K->n_advice, 2 * (size_t)K->n_lookups), K->n_sets) + 2 * zk_group_world(g);
+    void* p = nullptr;
     ZK_CUDA(ctx, cudaMalloc(&p, cols * K->n * 32));
-    ZK_CUDA(ctx, cudaMalloc(&q, cols * K->ext_n * 32));
-    K->allocs.push_back(p); K->allocs.push_back(q);
-    K->d_stage_p = (char*)p; K->d_stage_c = (char*)q; K->stage_cols = cols;
+    K->allocs.push_back(p);
+    K->d_stage_p = (char*)p; K->stage_cols = cols;
     // rows of the extended domain that evaluate_h reads relative to its own row: rotation * 2^(ext_k - k)
-    if (!getenv("ZK_GROUP_ALLGATHER_COSETS")) K->halo_rows = (size_t)K->max_rotation * (K->ext_n / K->n);
+    K->halo_rows = (size_t)K->max_rotation * (K->ext_n / K->n);
   }
   return ZK_OK;
 }
@@ -771,7 +827,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
         if (serialize) ZK_CUDA(ctx, cudaStreamSynchronize(up));
       }
       ZK_TRY(side(0, [&](zk_domain* d, zk_ctx* on) -> int {   // advice_polys and their cosets, concurrently with the commitments
-        return transform_columns(K, d, on, K->d_advice + i0 * nb, K->d_advice_polys + i0 * nb, cnt, [&](size_t i) { return slot_adv(i0 + (uint32_t)i); }, true);
+        return transform_columns(K, d, on, K->d_advice + i0 * nb, K->d_advice_polys + i0 * nb, cnt, [&](size_t i) { return slot_adv(i0 + (uint32_t)i); });
       }));
       ZK_TRY(commit_enqueue(K, K->d_advice + i0 * nb, cnt, ZK_BASES_G_LAGRANGE, i0));
     }
@@ -793,6 +849,10 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   // commitments, transforms and sorts of all lookup arguments are single batched calls.
   auto lk = [&](uint32_t l, int which) { return K->d_lookup + ((size_t)which * L + l) * nb; };
   auto lkp = [&](uint32_t l, int which) { return K->d_lookup_polys + ((size_t)which * L + l) * nb; };   // 0 A', 1 S', 2 Z (coefficients)
+  const uint32_t gworld = (K->group && K->d_stage_p) ? zk_group_world(K->group) : 1, grank = gworld > 1 ? zk_group_rank(K->group) : 0;
+  const uint32_t l_per = L ? (L + gworld - 1) / gworld : 1;
+  auto lookup_owner = [&](uint32_t l) { return gworld > 1 ? l / l_per : 0u; };
+  const uint32_t l_lo = std::min(L, grank * l_per), l_hi = std::min(L, (grank + 1) * l_per);
   if (L) {
     std::vector<const void*> cols(K->CL.n_slots);
     for (uint32_t i = 0; i < K->n_fixed; i++) cols[K->CL.prog.off_fixed + i] = K->d_fixed_values + i * nb;
@@ -803,26 +863,48 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     S.beta = Fr::zero(); S.gamma = Fr::zero(); S.y = Fr::zero(); S.theta = theta;
     S.delta_start = Fr::zero(); S.delta = Fr::zero(); S.one = Fr::one();
     ZK_CUDA(ctx, cudaMemsetAsync(K->d_flags, 0, 64, ctx->stream));
-    for (uint32_t l = 0; l < L; l++) {
+    // in a group every lookup argument has an owner rank that does all of its work: compression, sort / permutation,
+    // the commitments of A', S' and later Z, their transforms and the grand product
+    for (uint32_t l = l_lo; l < l_hi; l++) {
       ZK_TRY(eval_rows(K, 2 * l, S, lk(l, 0)));
       ZK_TRY(eval_rows(K, 2 * l + 1, S, lk(l, 1)));
     }
-    ZK_TRY(permute_expression_pairs(K, usable));
+    ZK_TRY(permute_expression_pairs(K, usable, l_lo, l_hi - l_lo));
     for (uint32_t l = 0; l < L; l++) {                 // RNG order: A' rows, S' rows, then the two Blinds, per lookup
-      ZK_TRY(draw_to(lk(l, 2) + usable * 32, bf + 1));
-      ZK_TRY(draw_to(lk(l, 3) + usable * 32, bf + 1));
+      if (l >= l_lo && l < l_hi) {
+        ZK_TRY(draw_to(lk(l, 2) + usable * 32, bf + 1));
+        ZK_TRY(draw_to(lk(l, 3) + usable * 32, bf + 1));
+      } else {
+        rpos += 2 * (size_t)(bf + 1);
+      }
       rpos += 2;
     }
     ZK_TRY(side(1, [&](zk_domain* d, zk_ctx* on) -> int {   // A', S' -> coefficient forms and cosets
-      return transform_columns(K, d, on, lk(0, 2), lkp(0, 0), 2 * (size_t)L,
-                               [&](size_t i) { return i < L ? slot_lk((uint32_t)i, 1) : slot_lk((uint32_t)(i - L), 2); }, false);
+      std::vector<ColJob> jobs;
+      for (uint32_t l = 0; l < L; l++) jobs.push_back({lk(l, 2), lkp(l, 0), slot_lk(l, 1), lookup_owner(l)});
+      for (uint32_t l = 0; l < L; l++) jobs.push_back({lk(l, 3), lkp(l, 1), slot_lk(l, 2), lookup_owner(l)});
+      return transform_jobs(K, d, on, jobs);
     }));
+    // status of the permutations: every rank must learn about a failure anywhere (nobody may wait in a collective)
     uint32_t flags = 0;
     ZK_CUDA(ctx, cudaMemcpyAsync(&flags, K->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (gworld > 1) {
+      uint32_t* xf = (uint32_t*)K->d_xchg;
+      std::vector<uint32_t> mine(4, 0), all(4 * (size_t)gworld);
+      mine[0] = flags;
+      ZK_CUDA(ctx, cudaMemcpyAsync(xf + 4 * grank, mine.data(), 16, cudaMemcpyHostToDevice, ctx->stream));
+      ZK_TRY(zk_group_allgather(K->group, ctx, xf, 16));
+      ZK_CUDA(ctx, cudaMemcpyAsync(all.data(), xf, all.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (uint32_t r = 0; r < gworld; r++) flags |= all[4 * r];
+    }
     if (flags & 6u) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: ConstraintSystemFailure (a lookup input is not in its table)");
+    std::vector<CommitJob> cj;
+    for (uint32_t l = 0; l < L; l++) cj.push_back({lk(l, 2), lookup_owner(l)});
+    for (uint32_t l = 0; l < L; l++) cj.push_back({lk(l, 3), lookup_owner(l)});
     std::vector<HostPoint> pts;
-    ZK_TRY(commit(K, lk(0, 2), 2 * (size_t)L, ZK_BASES_G_LAGRANGE, &pts));        // planes 2 and 3 are adjacent
+    ZK_TRY(commit_jobs(K, cj, ZK_BASES_G_LAGRANGE, &pts));
     for (uint32_t l = 0; l < L; l++) ZK_TRY(write_points({pts[l], pts[L + l]}));
   }
   Fr beta = tr.squeeze_challenge();
@@ -866,29 +948,36 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       rpos += 1;
     }
     ZK_TRY(side(2, [&](zk_domain* d, zk_ctx* on) -> int {
-      return transform_columns(K, d, on, K->d_perm_z, K->d_perm_z_polys, NS, [&](size_t i) { return slot_z((uint32_t)i); }, true);
+      return transform_columns(K, d, on, K->d_perm_z, K->d_perm_z_polys, NS, [&](size_t i) { return slot_z((uint32_t)i); });
     }));
     std::vector<HostPoint> pts;
     ZK_TRY(commit(K, K->d_perm_z, NS, ZK_BASES_G_LAGRANGE, &pts));
     ZK_TRY(write_points(pts));
   }
 
-  // ---- lookups: commit_product -------------------------------------------------------------------------------------------------
+  // ---- lookups: commit_product (own lookups only in a group) -------------------------------------------------------------------
   if (L) {
-    dim3 g(blocks_for(n, 256), L);
-    ZK_LAUNCH(ctx, "lookup_product", k_lookup_den, g, 256, 0, (const uint4*)lk(0, 2), (const uint4*)lk(0, 3), beta, gamma, (uint4*)K->d_w0, n);
-    ZK_TRY(batch_invert(K, K->d_w0, K->d_w1, (size_t)L * n));
-    ZK_LAUNCH(ctx, "lookup_product", k_lookup_num, g, 256, 0, (const uint4*)lk(0, 0), (const uint4*)lk(0, 1), beta, gamma, (uint4*)K->d_w0, n);
-    ZK_TRY(run_scan<FrMulMonoid>(K, "lookup_product", K->d_w0, lk(0, 4), n, 0, 1, nullptr, L, n, n));
+    const uint32_t Lloc = l_hi - l_lo;
+    if (Lloc) {
+      dim3 g(blocks_for(n, 256), Lloc);
+      ZK_LAUNCH(ctx, "lookup_product", k_lookup_den, g, 256, 0, (const uint4*)lk(l_lo, 2), (const uint4*)lk(l_lo, 3), beta, gamma, (uint4*)K->d_w0, n);
+      ZK_TRY(batch_invert(K, K->d_w0, K->d_w1, (size_t)Lloc * n));
+      ZK_LAUNCH(ctx, "lookup_product", k_lookup_num, g, 256, 0, (const uint4*)lk(l_lo, 0), (const uint4*)lk(l_lo, 1), beta, gamma, (uint4*)K->d_w0, n);
+      ZK_TRY(run_scan<FrMulMonoid>(K, "lookup_product", K->d_w0, lk(l_lo, 4), n, 0, 1, nullptr, Lloc, n, n));
+    }
     for (uint32_t l = 0; l < L; l++) {
-      ZK_TRY(draw_to(lk(l, 4) + (n - bf) * 32, bf));
+      if (l >= l_lo && l < l_hi) ZK_TRY(draw_to(lk(l, 4) + (n - bf) * 32, bf)); else rpos += bf;
       rpos += 1;
     }
     ZK_TRY(side(3, [&](zk_domain* d, zk_ctx* on) -> int {
-      return transform_columns(K, d, on, lk(0, 4), lkp(0, 2), L, [&](size_t i) { return slot_lk((uint32_t)i, 0); }, false);
+      std::vector<ColJob> jobs;
+      for (uint32_t l = 0; l < L; l++) jobs.push_back({lk(l, 4), lkp(l, 2), slot_lk(l, 0), lookup_owner(l)});
+      return transform_jobs(K, d, on, jobs);
     }));
+    std::vector<CommitJob> cj;
+    for (uint32_t l = 0; l < L; l++) cj.push_back({lk(l, 4), lookup_owner(l)});
     std::vector<HostPoint> pts;
-    ZK_TRY(commit(K, lk(0, 4), L, ZK_BASES_G_LAGRANGE, &pts));
+    ZK_TRY(commit_jobs(K, cj, ZK_BASES_G_LAGRANGE, &pts));
     ZK_TRY(write_points(pts));
   }
 

@@ -315,12 +315,16 @@ __global__ void __launch_bounds__(128) k_eval_rows(EvalProgram P, EvalScalars S,
 // packed with stride n (the number of sorted elements), so that the concatenation of all sorts is ONE array whose
 // radix offsets come from one global scan of hist[sort][digit][block].
 // keys = canonical (non-Montgomery) values so that limb order = numeric order (Fr: Ord)
-__global__ void __launch_bounds__(256) k_canon_keys(const uint4* v, uint4* keys, uint32_t* idx, size_t n, size_t stride) {
+// The sorts cover the lookups [l0, l0 + Lloc) of Ltot: sort s < Lloc reads column l0 + s of the input plane, sort
+// Lloc + s column l0 + s of the table plane (the planes are adjacent, Ltot columns each); keys / idx are dense in s.
+__global__ void __launch_bounds__(256) k_canon_keys(const uint4* v, uint4* keys, uint32_t* idx, size_t n, size_t stride, uint32_t Lloc,
+                                                    uint32_t l0, uint32_t Ltot) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  size_t o = (size_t)blockIdx.y * stride + i;
-  Fr::load(v + 2 * o).from_mont().store_raw(keys + 2 * o);
-  idx[(size_t)blockIdx.y * n + i] = (uint32_t)i;
+  const uint32_t s = blockIdx.y;
+  const size_t col = s < Lloc ? (size_t)l0 + s : (size_t)Ltot + l0 + (s - Lloc);
+  Fr::load(v + 2 * (col * stride + i)).from_mont().store_raw(keys + 2 * ((size_t)s * stride + i));
+  idx[(size_t)s * n + i] = (uint32_t)i;
 }
 // mask[sort][l] |= keys[i].l[l] ^ keys[0].l[l]: which bits differ anywhere in the array
 __global__ void __launch_bounds__(256) k_key_diff_mask(const uint32_t* keys_all, size_t n, size_t stride, uint32_t* mask_all) {
@@ -480,11 +484,11 @@ __global__ void __launch_bounds__(256) k_permute_rpos(const uint32_t* rep_all, c
 __global__ void __launch_bounds__(256) k_permute_write(const uint4* input_all, const uint4* table_all, const uint32_t* idx_all,
                                                        const uint32_t* rep_all, const uint32_t* left_all, const uint32_t* lrank_all,
                                                        const uint32_t* rpos_all, const uint32_t* totals, uint32_t L, uint4* pin_all,
-                                                       uint4* ptab_all, size_t n, size_t stride) {
+                                                       uint4* ptab_all, size_t n, size_t stride, uint32_t l0) {
   size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const uint32_t l = blockIdx.y;
-  const size_t o = (size_t)l * n, so = 2 * (size_t)l * stride;
+  const uint32_t l = blockIdx.y;                 // local lookup; its columns are l0 + l of each plane
+  const size_t o = (size_t)l * n, so = 2 * (size_t)(l0 + l) * stride;
   const uint4* input = input_all + so;
   const uint4* table = table_all + so;
   uint4* pin = pin_all + so;
