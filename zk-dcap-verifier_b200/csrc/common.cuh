@@ -45,6 +45,10 @@ struct zk_ctx {
   size_t srs_n = 0;
   zk_srs_set srs_g, srs_lagrange;
   bool srs_borrowed = false;    // the base sets belong to another context (zk_ctx_share_srs)
+  // internal: MSM results are left as XYZZ records (x, y, zz, zzz; 128 B) instead of normalised G1 (96 B): the prover
+  // normalises on the host (one shared inversion per batch) rather than spending a ~135 us single-thread Fermat
+  // inversion on the device after every commitment batch
+  bool msm_raw = false;
   // grow-only scratch buffers, reused across calls on this context
   zk_scratch msm_scalars, msm_bases, msm_work, msm_out, ntt_buf, ntt_buf2, misc;
   // cached twiddle tables: key = (log_n, first 8 bytes of omega...) -> device table of omega^e, e < n/2

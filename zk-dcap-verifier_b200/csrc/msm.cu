@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(128) k_msm_combine_levels(LevelPlan L, size_t 
 // of items doublings + items additions; one CTA per MSM, the items live in shared memory.
 constexpr uint32_t kFinalMaxItems = 512;
 // `items` values V_e per MSM with weight 2^(shift * e)
-__global__ void __launch_bounds__(256) k_msm_final(const uint4* sums, uint32_t items, uint32_t shift, uint4* out) {
+__global__ void __launch_bounds__(256) k_msm_final(const uint4* sums, uint32_t items, uint32_t shift, uint4* out, int raw) {
   extern __shared__ uint4 fsm[];
   size_t msm = blockIdx.x;
   const uint4* s = sums + 8 * (msm * items);
@@ -493,7 +493,10 @@ __global__ void __launch_bounds__(256) k_msm_final(const uint4* sums, uint32_t i
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) store_g1_normalised(out + 6 * msm, XYZZ::load(fsm).to_affine());
+  if (threadIdx.x == 0) {
+    if (raw) XYZZ::load(fsm).store(out + 8 * msm);          // XYZZ record, normalised by the caller
+    else store_g1_normalised(out + 6 * msm, XYZZ::load(fsm).to_affine());
+  }
 }
 
 // ---- window table: table[w][i] = 2^(c*w) * base[i] ------------------------------------------------------
@@ -533,12 +536,17 @@ __global__ void k_g1_sum(const uint4* pts, size_t count, uint4* out) {
 }
 
 // out[p] = sum over r < parts of pts[r * count + p]  (partial MSMs of the ranks of a group, one thread per output)
-__global__ void k_g1_sum_strided(const uint4* pts, size_t parts, size_t count, uint4* out) {
+__global__ void k_g1_sum_strided(const uint4* pts, size_t parts, size_t count, uint4* out, int raw) {
   size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (p >= count) return;
   XYZZ acc = XYZZ::identity();
-  for (size_t r = 0; r < parts; r++) acc = acc.add(load_g1_as_xyzz(pts + 6 * (r * count + p)));
-  store_g1_normalised(out + 6 * p, acc.to_affine());
+  if (raw) {                                 // XYZZ records in and out
+    for (size_t r = 0; r < parts; r++) acc = acc.add(XYZZ::load(pts + 8 * (r * count + p)));
+    acc.store(out + 8 * p);
+  } else {
+    for (size_t r = 0; r < parts; r++) acc = acc.add(load_g1_as_xyzz(pts + 6 * (r * count + p)));
+    store_g1_normalised(out + 6 * p, acc.to_affine());
+  }
 }
 
 uint32_t ilog2(size_t x) { uint32_t l = 0; while (((size_t)1 << (l + 1)) <= x) l++; return l; }
@@ -750,7 +758,7 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
     ZK_LAUNCH(ctx, "msm_final", k_msm_combine_levels, zk_div_up(rws, 128), 128, 0, L, rws, R);
     size_t fsmem = (size_t)P.G * 128;
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFinalMaxItems * 128)));
-    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)R, P.G, P.c, (uint4*)d_out);
+    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)R, P.G, P.c, (uint4*)d_out, ctx->msm_raw ? 1 : 0);
     return ZK_OK;
   }
   size_t rows = P.count * P.G * P.c;
@@ -767,7 +775,7 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   {
     size_t fsmem = (size_t)P.G * P.c * 128;
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFinalMaxItems * 128)));
-    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)src, P.G * P.c, 1u, (uint4*)d_out);
+    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)src, P.G * P.c, 1u, (uint4*)d_out, ctx->msm_raw ? 1 : 0);
   }
   return ZK_OK;
 }
@@ -896,7 +904,7 @@ int zk_msm_range_batch_dev(zk_ctx* ctx, const zk_fr* d_scalars, int which, size_
   return run_msm(ctx, d_scalars, s.table, P, d_out);
 }
 int zk_g1_sum_strided_dev(zk_ctx* ctx, const zk_g1* d_points, size_t parts, size_t count, zk_g1* d_out) {
-  ZK_LAUNCH(ctx, "g1_sum", k_g1_sum_strided, zk_div_up(count, 32), 32, 0, (const uint4*)d_points, parts, count, (uint4*)d_out);
+  ZK_LAUNCH(ctx, "g1_sum", k_g1_sum_strided, zk_div_up(count, 32), 32, 0, (const uint4*)d_points, parts, count, (uint4*)d_out, ctx->msm_raw ? 1 : 0);
   return ZK_OK;
 }
 

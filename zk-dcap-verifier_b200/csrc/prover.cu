@@ -203,41 +203,70 @@ int kate_divide(zk_pkey* K, char* a, uint32_t slot_z, uint32_t slot_zinv) {
 
 // commitments: `count` contiguous polynomials -> affine points on the host (normalised Jacobian from the MSM)
 struct HostPoint { Fq x, y; bool identity; };
+// MSM results inside the prover are XYZZ records (ctx->msm_raw): x = X / ZZ, y = Y / ZZZ, identity when ZZ = 0
+struct PtRaw { zk_fq x, y, zz, zzz; };
+struct RawGuard {
+  zk_ctx* c; bool old;
+  explicit RawGuard(zk_ctx* ctx) : c(ctx), old(ctx->msm_raw) { ctx->msm_raw = true; }
+  ~RawGuard() { c->msm_raw = old; }
+};
+// host normalisation of a batch with ONE field inversion (Montgomery's trick)
+void normalize_points(const PtRaw* raw, size_t count, std::vector<HostPoint>* out) {
+  std::vector<Fq> den(count), pre(count);
+  Fq acc = Fq::one();
+  for (size_t i = 0; i < count; i++) {
+    Fq zz = f_from_abi<Fq>(&raw[i].zz), zzz = f_from_abi<Fq>(&raw[i].zzz);
+    den[i] = zz * zzz;
+    pre[i] = acc;
+    if (!zz.is_zero()) acc = acc * den[i];
+  }
+  Fq inv = Fq::inv(acc);
+  std::vector<HostPoint> res(count);
+  for (size_t i = count; i-- > 0;) {
+    Fq zz = f_from_abi<Fq>(&raw[i].zz), zzz = f_from_abi<Fq>(&raw[i].zzz);
+    HostPoint q;
+    q.identity = zz.is_zero();
+    if (q.identity) { q.x = Fq::zero(); q.y = Fq::zero(); }
+    else {
+      Fq t = inv * pre[i];                     // 1 / (zz * zzz)
+      inv = inv * den[i];
+      q.x = f_from_abi<Fq>(&raw[i].x) * (t * zzz);
+      q.y = f_from_abi<Fq>(&raw[i].y) * (t * zz);
+    }
+    res[i] = q;
+  }
+  for (auto& q : res) out->push_back(q);
+}
 // Commitments of `count` contiguous polynomials into d_points[slot ..].  In a group the work is split (by column when
 // there are at least as many polynomials as GPUs, by base range otherwise) and the points are all-gathered, so every
 // rank continues with the same transcript.
 int commit_enqueue(zk_pkey* K, const char* d_polys, size_t count, int which, size_t slot) {
   zk_ctx* ctx = K->ctx;
-  zk_g1* out = (zk_g1*)K->d_points + slot;
+  PtRaw* out = (PtRaw*)K->d_points + slot;
   const uint32_t world = K->group ? zk_group_world(K->group) : 1;
-  if (world <= 1 || !count) return zk_msm_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, count, out);
+  if (world <= 1 || !count) return zk_msm_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, count, (zk_g1*)out);
   const uint32_t rank = zk_group_rank(K->group);
   int mode; size_t per, lo, hi;
   zk_group_shard_plan(rank, world, count, K->n, &mode, &per, &lo, &hi);
-  zk_g1* xchg = (zk_g1*)K->d_xchg;
+  PtRaw* xchg = (PtRaw*)K->d_xchg;
   if (mode == 0) {
-    if (hi > lo) ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)(d_polys + lo * K->n * 32), which, K->n, hi - lo, xchg + (size_t)rank * per));
-    ZK_TRY(zk_group_allgather(K->group, ctx, xchg, per * sizeof(zk_g1)));
-    ZK_CUDA(ctx, cudaMemcpyAsync(out, xchg, count * sizeof(zk_g1), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (hi > lo) ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)(d_polys + lo * K->n * 32), which, K->n, hi - lo, (zk_g1*)(xchg + (size_t)rank * per)));
+    ZK_TRY(zk_group_allgather(K->group, ctx, xchg, per * sizeof(PtRaw)));
+    ZK_CUDA(ctx, cudaMemcpyAsync(out, xchg, count * sizeof(PtRaw), cudaMemcpyDeviceToDevice, ctx->stream));
   } else {
-    if (hi > lo) ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, lo, hi - lo, count, xchg + (size_t)rank * count));
-    else ZK_CUDA(ctx, cudaMemsetAsync(xchg + (size_t)rank * count, 0, count * sizeof(zk_g1), ctx->stream));   // z = 0: identity
-    ZK_TRY(zk_group_allgather(K->group, ctx, xchg, count * sizeof(zk_g1)));
-    ZK_TRY(zk_g1_sum_strided_dev(ctx, xchg, world, count, out));
+    if (hi > lo) ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, lo, hi - lo, count, (zk_g1*)(xchg + (size_t)rank * count)));
+    else ZK_CUDA(ctx, cudaMemsetAsync(xchg + (size_t)rank * count, 0, count * sizeof(PtRaw), ctx->stream));   // zz = 0: identity
+    ZK_TRY(zk_group_allgather(K->group, ctx, xchg, count * sizeof(PtRaw)));
+    ZK_TRY(zk_g1_sum_strided_dev(ctx, (const zk_g1*)xchg, world, count, (zk_g1*)out));
   }
   return ZK_OK;
 }
 int commit_fetch(zk_pkey* K, size_t count, std::vector<HostPoint>* out) {
   zk_ctx* ctx = K->ctx;
-  std::vector<zk_g1> h(count);
-  ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), K->d_points, count * sizeof(zk_g1), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<PtRaw> h(count);
+  ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), K->d_points, count * sizeof(PtRaw), cudaMemcpyDeviceToHost, ctx->stream));
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  for (auto& p : h) {
-    HostPoint q;
-    q.x = f_from_abi<Fq>(&p.x); q.y = f_from_abi<Fq>(&p.y);
-    q.identity = f_from_abi<Fq>(&p.z).is_zero();
-    out->push_back(q);
-  }
+  normalize_points(h.data(), count, out);
   return ZK_OK;
 }
 int commit(zk_pkey* K, const char* d_polys, size_t count, int which, std::vector<HostPoint>* out) {
@@ -330,25 +359,20 @@ int commit_jobs(zk_pkey* K, const std::vector<CommitJob>& jobs, int which, std::
   for (size_t i = 0; i < count; i++) { uint32_t o = world > 1 ? jobs[i].owner : 0; kth[i] = owned[o]++; }
   size_t maxown = 0;
   for (auto c : owned) maxown = std::max(maxown, c);
-  zk_g1* xchg = (zk_g1*)K->d_xchg;
+  PtRaw* xchg = (PtRaw*)K->d_xchg;
   for (size_t i = 0; i < count;) {
     uint32_t o = world > 1 ? jobs[i].owner : 0;
     size_t j = i + 1;
     while (j < count && (world > 1 ? jobs[j].owner : 0) == o && jobs[j].poly == jobs[i].poly + (j - i) * nb) j++;
-    if (o == rank) ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)jobs[i].poly, which, K->n, j - i, xchg + (size_t)rank * maxown + kth[i]));
+    if (o == rank) ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)jobs[i].poly, which, K->n, j - i, (zk_g1*)(xchg + (size_t)rank * maxown + kth[i])));
     i = j;
   }
-  if (world > 1) ZK_TRY(zk_group_allgather(K->group, ctx, xchg, maxown * sizeof(zk_g1)));
-  std::vector<zk_g1> h((size_t)world * maxown);
-  ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), xchg, h.size() * sizeof(zk_g1), cudaMemcpyDeviceToHost, ctx->stream));
+  if (world > 1) ZK_TRY(zk_group_allgather(K->group, ctx, xchg, maxown * sizeof(PtRaw)));
+  std::vector<PtRaw> h((size_t)world * maxown), ordered(count);
+  ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), xchg, h.size() * sizeof(PtRaw), cudaMemcpyDeviceToHost, ctx->stream));
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  for (size_t i = 0; i < count; i++) {
-    const zk_g1& p = h[(size_t)(world > 1 ? jobs[i].owner : 0) * maxown + kth[i]];
-    HostPoint q;
-    q.x = f_from_abi<Fq>(&p.x); q.y = f_from_abi<Fq>(&p.y);
-    q.identity = f_from_abi<Fq>(&p.z).is_zero();
-    out->push_back(q);
-  }
+  for (size_t i = 0; i < count; i++) ordered[i] = h[(size_t)(world > 1 ? jobs[i].owner : 0) * maxown + kth[i]];
+  normalize_points(ordered.data(), count, out);
   return ZK_OK;
 }
 
@@ -659,8 +683,8 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
   KG(dev_alloc(K, &K->d_flags, 64));
   K->max_list = D.n_advice + D.n_fixed + D.n_instance + K->n_perm + K->n_sets + 3 * D.n_lookups + D.degree + 16;
   K->eval_chunks = (uint32_t)std::min<size_t>(std::max<size_t>(n / 4096, 1), 64);
-  KG(dev_alloc(K, &K->d_points, (size_t)K->max_list * sizeof(zk_g1)));
-  KG(dev_alloc(K, &K->d_xchg, (size_t)(K->max_list + 64) * 16 * sizeof(zk_g1)));
+  KG(dev_alloc(K, &K->d_points, (size_t)K->max_list * sizeof(PtRaw)));
+  KG(dev_alloc(K, &K->d_xchg, (size_t)(K->max_list + 64) * 16 * sizeof(PtRaw)));
   KG(dev_alloc(K, &K->d_ptrs, (size_t)K->max_list * sizeof(void*)));
   KG(dev_alloc(K, &K->d_scalars, (size_t)K->max_list * 32));
   KG(dev_alloc(K, &K->d_partial, (size_t)K->max_list * K->eval_chunks * 32));
@@ -714,6 +738,7 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
   }
   // ---- keygen_vk: commitments of the fixed and permutation columns ------------------------------------------------------------------
   {
+    RawGuard raw_guard(ctx);
     std::vector<HostPoint> pts;
     if (D.n_fixed) KG(commit(K, K->d_fixed_values, D.n_fixed, ZK_BASES_G_LAGRANGE, &pts));
     if (K->n_perm) KG(commit(K, K->d_sigma_values, K->n_perm, ZK_BASES_G_LAGRANGE, &pts));
@@ -740,6 +765,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: bad argument");
   if (n_randoms < zk_proof_randoms(K)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: %zu randoms supplied, %zu needed", n_randoms, zk_proof_randoms(K));
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  RawGuard raw_guard(ctx);                              // commitments come back as XYZZ records, normalised on the host
   const size_t n = K->n, nb = n * 32;
   const uint32_t bf = K->bf, A = K->n_advice, L = K->n_lookups;
   const size_t usable = n - (bf + 1);
