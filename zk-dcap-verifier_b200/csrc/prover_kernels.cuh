@@ -191,8 +191,9 @@ __global__ void __launch_bounds__(256) k_lookup_num(const uint4* cin, const uint
 }
 
 // In-place batch inversion, zeros stay zero (ff batch_invert semantics).  Each thread owns kInvChunk consecutive
-// elements: prefix products into `scratch`, one Fermat inversion, back substitution.
-constexpr int kInvChunk = 32;
+// elements: prefix products into `scratch`, one Fermat inversion (~380 multiplications, so the chunk is long enough to
+// amortise it: 3 + 380/128 multiplications per element), back substitution.
+constexpr int kInvChunk = 128;
 __global__ void __launch_bounds__(128) k_batch_invert(uint4* v, uint4* scratch, size_t n) {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t lo = t * kInvChunk, hi = lo + kInvChunk < n ? lo + kInvChunk : n;
