@@ -41,7 +41,7 @@ pub struct zk_circuit_desc {
 #[repr(C)]
 pub struct zk_verifier_params {
     pub fixed_commitments: *const zk_g1_affine, pub permutation_commitments: *const zk_g1_affine,
-    pub g1: zk_g1_affine, pub g2: *const u8, pub s_g2: *const u8,
+    pub g1: zk_g1_affine, pub g2: *const u8, pub s_g2: *const u8, pub transcript_kind: c_int,
 }
 #[repr(C)] pub struct zk_pkey { _p: [u8; 0] }
 #[repr(C)] pub struct zk_group { _p: [u8; 0] }
@@ -75,6 +75,7 @@ extern "C" {
     pub fn zk_pkey_destroy(pk: *mut zk_pkey);
     pub fn zk_pkey_vk_commitments(pk: *const zk_pkey, fixed_commitments: *mut zk_g1_affine, perm_commitments: *mut zk_g1_affine) -> c_int;
     pub fn zk_pkey_pk(pk: *mut zk_pkey) -> *mut zk_pk;
+    pub fn zk_pkey_set_transcript(pk: *mut zk_pkey, kind: c_int) -> c_int;      // 0 Blake2b (halo2), 1 EVM / Keccak (snark-verifier)
     pub fn zk_proof_randoms(pk: *const zk_pkey) -> usize;
     pub fn zk_proof_max_bytes(pk: *const zk_pkey) -> usize;
     pub fn zk_create_proof(pk: *mut zk_pkey, advice_values: *const *const zk_fr, instance_values: *const *const zk_fr,

@@ -321,6 +321,11 @@ zk_pk* zk_pkey_pk(zk_pkey* pk);
 /* The key's second context (= its second stream: the witness polynomials' transforms overlap the commitments
  * there), for zk_ctx_timing* / zk_ctx_launch_count; NULL when ZK_PROVER_STREAMS=1.  Owned by the key. */
 zk_ctx* zk_pkey_aux_ctx(zk_pkey* pk);
+/* Transcript of the key's proofs: halo2's Blake2bWrite / Challenge255 (default; circuits/src/sgx_dcap_verifier.rs:813)
+ * or snark-verifier's EvmTranscript (Keccak-256, uncompressed big-endian points; gen_evm_proof_shplonk at
+ * crates/p256-ecdsa/src/base.rs:193-199).  The Poseidon transcript of gen_proof (base.rs:200-211) is not implemented. */
+typedef enum { ZK_TRANSCRIPT_BLAKE2B = 0, ZK_TRANSCRIPT_EVM = 1 } zk_transcript_kind;
+int zk_pkey_set_transcript(zk_pkey* pk, int kind);
 /* Number of Fr::random draws one create_proof makes for this circuit. */
 size_t zk_proof_randoms(const zk_pkey* pk);
 /* Upper bound of the proof size in bytes. */
@@ -348,6 +353,7 @@ typedef struct {
   zk_g1_affine g1;
   const uint8_t* g2;
   const uint8_t* s_g2;
+  int transcript_kind;                          /* zk_transcript_kind the proof was written with */
 } zk_verifier_params;
 /* *accepted = 1 when the proof verifies, 0 otherwise (malformed proofs are rejected, not errors). */
 int zk_verify_proof(const zk_circuit_desc* circuit, const zk_verifier_params* vp,

@@ -119,6 +119,77 @@ class Blake2bRead(Blake2bWrite):
         return s
 
 
+class EvmWrite:
+    """snark-verifier `EvmTranscript<G1Affine, NativeLoader, _, Vec<u8>>` [UPSTREAM? snark-verifier
+    system/halo2/transcript/evm.rs, the transcript of gen_evm_proof_shplonk at crates/p256-ecdsa/src/base.rs:193-199]:
+    a byte buffer hashed with Keccak-256; points are absorbed / written uncompressed as big-endian x, y, scalars as
+    32 big-endian bytes; a challenge is keccak(buf ++ [1 if len(buf) == 32]) read big-endian mod r, and the digest
+    becomes the new buffer."""
+
+    def __init__(self):
+        from .keccak import keccak256
+        self._h = keccak256
+        self.buf = bytearray()
+        self.proof = bytearray()
+
+    def squeeze_challenge(self):
+        data = bytes(self.buf) + (b"\x01" if len(self.buf) == 32 else b"")
+        digest = self._h(data)
+        self.buf = bytearray(digest)
+        return int.from_bytes(digest, "big") % R
+
+    def common_point(self, pt):
+        if pt is None:
+            raise ValueError("cannot write points at infinity to the transcript")
+        self.buf += pt[0].to_bytes(32, "big") + pt[1].to_bytes(32, "big")
+
+    def common_scalar(self, s):
+        self.buf += s.to_bytes(32, "big")
+
+    def write_point(self, pt):
+        self.common_point(pt)
+        self.proof += pt[0].to_bytes(32, "big") + pt[1].to_bytes(32, "big")
+
+    def write_scalar(self, s):
+        self.common_scalar(s)
+        self.proof += s.to_bytes(32, "big")
+
+    def finalize(self):
+        return bytes(self.proof)
+
+
+class EvmRead(EvmWrite):
+    def __init__(self, proof):
+        super().__init__()
+        self.rbuf, self.pos = bytes(proof), 0
+
+    def read_point(self):
+        b = self.rbuf[self.pos:self.pos + 64]
+        if len(b) != 64:
+            raise ValueError("proof too short")
+        self.pos += 64
+        x, y = int.from_bytes(b[:32], "big"), int.from_bytes(b[32:], "big")
+        if x >= P or y >= P or (y * y - x * x * x - 3) % P:
+            raise ValueError("invalid point")
+        self.common_point((x, y))
+        return (x, y)
+
+    def read_scalar(self):
+        b = self.rbuf[self.pos:self.pos + 32]
+        if len(b) != 32:
+            raise ValueError("proof too short")
+        self.pos += 32
+        s = int.from_bytes(b, "big")
+        if s >= R:
+            raise ValueError("invalid scalar encoding")
+        self.common_scalar(s)
+        return s
+
+    @property
+    def buf_len(self):
+        return len(self.rbuf)
+
+
 class Randoms:
     """The caller's RNG, pre-drawn: element i is the i-th `Fr::random(&mut rng)` create_proof would make."""
 

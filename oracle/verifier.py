@@ -15,7 +15,7 @@ Only tests/, __graft_entry__.smoke() and bench.py's checking leg may import this
 """
 from . import pairing
 from . import pymodel as pm
-from .prover import (Blake2bRead, construct_intermediate_sets, eval_small, evaluate_vanishing_polynomial,
+from .prover import (Blake2bRead, EvmRead, construct_intermediate_sets, eval_small, evaluate_vanishing_polynomial,
                      lagrange_interpolate, rotate_omega)
 
 R = pm.R_MOD
@@ -66,19 +66,20 @@ def msm_eval(terms):
     return acc
 
 
-def verify_proof(params, vk, cs, k, instances, proof):
+def verify_proof(params, vk, cs, k, instances, proof, transcript="blake2b"):
     """params: {"g0": G1 generator used by the SRS (affine ints), "g2": G2, "s_g2": [s]G2}.
-    vk: {"fixed_commitments", "permutation_commitments", "transcript_repr"}.  Returns True / False."""
+    vk: {"fixed_commitments", "permutation_commitments", "transcript_repr"}.  transcript: "blake2b" (Blake2bRead,
+    Challenge255) or "evm" (snark-verifier EvmTranscript, Keccak-256).  Returns True / False."""
     try:
-        return _verify(params, vk, cs, k, instances, proof)
+        return _verify(params, vk, cs, k, instances, proof, transcript)
     except (ValueError, KeyError, ZeroDivisionError):
         return False
 
 
-def _verify(params, vk, cs, k, instances, proof):
+def _verify(params, vk, cs, k, instances, proof, transcript="blake2b"):
     n, bf, d = 1 << k, cs.blinding_factors(), cs.degree()
     chunk = d - 2
-    tr = Blake2bRead(proof)
+    tr = Blake2bRead(proof) if transcript == "blake2b" else EvmRead(proof)
     if len(instances) != cs.num_instance_columns:
         return False
     tr.common_scalar(vk["transcript_repr"])
@@ -213,7 +214,7 @@ def _verify(params, vk, cs, k, instances, proof):
     h1 = tr.read_point()
     u = tr.squeeze_challenge()
     h2 = tr.read_point()
-    if tr.pos != len(tr.buf):
+    if tr.pos != (len(tr.buf) if transcript == "blake2b" else tr.buf_len):
         return False
     outer, r_outer = [], 0
     z_0 = z_0_diff_inv = 0

@@ -103,8 +103,8 @@ extern "C" int evh_run(const zk_evaluator_desc* desc, const void* const* cols, c
 // `out`), 1 = write_point (64 bytes: x, y canonical little-endian), 2 = write_scalar (32 bytes canonical), 3 = common_scalar.
 // Returns the number of bytes written to `out`; the proof bytes are copied to `proof` (proof_len receives their count).
 extern "C" size_t transcript_replay(const unsigned char* ops, size_t n_ops_bytes, unsigned char* out, unsigned char* proof,
-                                    size_t* proof_len) {
-  TranscriptWrite t;
+                                    size_t* proof_len, int kind) {
+  TranscriptWrite t(kind);
   size_t pos = 0, w = 0;
   auto canon_to_mont_fr = [](const unsigned char* p) { Fr v; memcpy(v.l, p, 32); return v.to_mont(); };
   auto canon_to_mont_fq = [](const unsigned char* p) { Fq v; memcpy(v.l, p, 32); return v.to_mont(); };

@@ -120,26 +120,28 @@ def test_signed_digit_recoding(ffh, c):
         assert sum(int(x) << (c * w) for w, x in enumerate(d[:W])) == v
 
 
-def test_blake2b_transcript_host_build_matches_python(ffh):
-    """csrc/transcript.hpp (Blake2b-512 with personalisation, Challenge255 = from_bytes_wide, point compression) replayed
-    on the host against oracle/prover.py's hashlib-based transcript, across block boundaries."""
+@pytest.mark.parametrize("kind", [0, 1])
+def test_transcripts_host_build_match_python(ffh, kind):
+    """csrc/transcript.hpp -- Blake2b-512 with personalisation / Challenge255 / point compression (kind 0) and the
+    Keccak-256 EVM transcript (kind 1) -- replayed on the host against oracle/prover.py's transcripts, across block
+    boundaries."""
     import ctypes as C
     import random
     from oracle import prover as op
     from oracle import pymodel as pm
-    rnd = random.Random(7)
-    t = op.Blake2bWrite()
+    rnd = random.Random(7 + kind)
+    t = op.Blake2bWrite() if kind == 0 else op.EvmWrite()
     ops = bytearray()
     want_ch = []
     pts = [pm.ec_mul(rnd.randrange(1, pm.R_MOD), (1, 2)) for _ in range(6)]
     for step in range(60):
-        kind = rnd.choice([0, 1, 2, 2, 3])
-        if kind == 0:
+        what = rnd.choice([0, 1, 2, 2, 3])
+        if what == 0:
             ops.append(0); want_ch.append(t.squeeze_challenge())
-        elif kind == 1:
+        elif what == 1:
             p = rnd.choice(pts)
             ops.append(1); ops += p[0].to_bytes(32, "little") + p[1].to_bytes(32, "little"); t.write_point(p)
-        elif kind == 2:
+        elif what == 2:
             s = rnd.randrange(pm.R_MOD)
             ops.append(2); ops += s.to_bytes(32, "little"); t.write_scalar(s)
         else:
@@ -149,8 +151,14 @@ def test_blake2b_transcript_host_build_matches_python(ffh):
     proof = (C.c_ubyte * (len(t.proof) + 64))()
     plen = C.c_size_t()
     ffh.transcript_replay.restype = C.c_size_t
-    w = ffh.transcript_replay(bytes(ops), C.c_size_t(len(ops)), out, proof, C.byref(plen))
+    w = ffh.transcript_replay(bytes(ops), C.c_size_t(len(ops)), out, proof, C.byref(plen), C.c_int(kind))
     assert w == 32 * len(want_ch)
     got = [int.from_bytes(bytes(out[32 * i:32 * i + 32]), "little") for i in range(len(want_ch))]
     assert got == want_ch
     assert bytes(proof[:plen.value]) == t.finalize()
+
+
+def test_keccak256_known_answers():
+    from oracle.keccak import keccak256
+    assert keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert keccak256(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"

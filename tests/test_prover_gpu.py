@@ -177,3 +177,20 @@ def test_first_phase_challenge_and_instance(ctx):
     inst = [[3, 1, 4, 1, 5, 9, 2, 6]]
     got, opk = _both_provers(ctx, cs, k, fixed, advice, mapping, inst, 23)
     assert len(got) > 0
+
+
+def test_evm_transcript_proof_bytes(ctx):
+    """zk_pkey_set_transcript(EVM): Keccak-256 transcript, uncompressed big-endian points"""
+    case = pc.make_case("toy", 6, 8)
+    p = pc.params_for(6)
+    params = zk.ParamsKZG(6, p["g"], p["g_lagrange"], ctx, precompute=True)
+    key = zk.ProverKey(params, case["circ"], case["fixed"], case["mapping"])
+    key.set_transcript("evm")
+    opk = pc.oracle_key(case)
+    want = op.create_proof(orc, p, opk, case["circ"], case["advice"], case["instances_int"], case["randoms"], transcript=op.EvmWrite())
+    got = key.create_proof(case["advice"], case["instances_limbs"], case["randoms"])
+    assert got == want, "first differing item %d" % first_diff(got, want)
+    assert ov.verify_proof(pc.verifier_params(), opk["vk"], case["cs"], 6, case["instances_int"], got, transcript="evm")
+    key.set_transcript("blake2b")
+    assert key.create_proof(case["advice"], case["instances_limbs"], case["randoms"]) == \
+        op.create_proof(orc, p, opk, case["circ"], case["advice"], case["instances_int"], case["randoms"])

@@ -18,12 +18,13 @@ def g2_bytes(q):
     return b"".join(v.to_bytes(32, "little") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
 
 
-def native_verify(case, pk, instances_limbs, proof, s_g2=None):
+def native_verify(case, pk, instances_limbs, proof, s_g2=None, transcript="blake2b"):
     vp = pc.verifier_params()
     fc = pm.affine_to_limbs(pk["vk"]["fixed_commitments"])
     pcm = pm.affine_to_limbs(pk["vk"]["permutation_commitments"])
     g1 = pm.affine_to_limbs([(1, 2)])[0]
-    return zk.verify_proof(case["circ"], fc, pcm, g1, g2_bytes(vp["g2"]), g2_bytes(s_g2 or vp["s_g2"]), instances_limbs, proof)
+    return zk.verify_proof(case["circ"], fc, pcm, g1, g2_bytes(vp["g2"]), g2_bytes(s_g2 or vp["s_g2"]), instances_limbs, proof,
+                           transcript=transcript)
 
 
 @pytest.mark.parametrize("shape,k", [("toy", 5), ("qe3", 9)])
@@ -57,3 +58,17 @@ def test_native_verifier_rejects_an_unsatisfied_witness():
     adv[0][3] = adv[0][7]
     proof = op.create_proof(orc, pc.params_for(5), pk, case["circ"], adv, case["instances_int"], case["randoms"])
     assert not native_verify(case, pk, case["instances_limbs"], proof)
+
+
+def test_evm_transcript_proofs():
+    """the Keccak / EVM transcript (uncompressed big-endian points): oracle prover -> both verifiers"""
+    case = pc.make_case("toy", 5, 6)
+    pk = pc.oracle_key(case)
+    proof = op.create_proof(orc, pc.params_for(5), pk, case["circ"], case["advice"], case["instances_int"], case["randoms"],
+                            transcript=op.EvmWrite())
+    assert ov.verify_proof(pc.verifier_params(), pk["vk"], case["cs"], 5, case["instances_int"], proof, transcript="evm")
+    assert native_verify(case, pk, case["instances_limbs"], proof, transcript="evm")
+    assert not native_verify(case, pk, case["instances_limbs"], proof, transcript="blake2b")
+    bad = bytearray(proof); bad[200] ^= 2
+    assert not native_verify(case, pk, case["instances_limbs"], bytes(bad), transcript="evm")
+    assert not ov.verify_proof(pc.verifier_params(), pk["vk"], case["cs"], 5, case["instances_int"], bytes(bad), transcript="evm")

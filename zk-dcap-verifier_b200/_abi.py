@@ -59,7 +59,7 @@ class zk_circuit_desc(C.Structure):
 
 class zk_verifier_params(C.Structure):
     _fields_ = [("fixed_commitments", C.c_void_p), ("permutation_commitments", C.c_void_p),
-                ("g1", C.c_uint64 * 8), ("g2", C.c_void_p), ("s_g2", C.c_void_p)]
+                ("g1", C.c_uint64 * 8), ("g2", C.c_void_p), ("s_g2", C.c_void_p), ("transcript_kind", C.c_int)]
 
 
 class zk_kernel_stat(C.Structure):
@@ -72,6 +72,7 @@ VS_CONSTANT, VS_INTERMEDIATE, VS_FIXED, VS_ADVICE, VS_INSTANCE, VS_CHALLENGE, VS
 CALC_ADD, CALC_SUB, CALC_MUL, CALC_SQUARE, CALC_DOUBLE, CALC_NEGATE, CALC_HORNER, CALC_STORE = range(8)
 COL_ADVICE, COL_FIXED, COL_INSTANCE = range(3)
 BASES_HOST, BASES_G, BASES_G_LAGRANGE = range(3)
+TRANSCRIPTS = {"blake2b": 0, "evm": 1}
 
 # every symbol include/zkdcap_b200.h declares
 SYMBOLS = [
@@ -89,7 +90,7 @@ SYMBOLS = [
     "zk_divide_by_vanishing_poly_dev",
     "zk_pk_upload", "zk_pk_destroy", "zk_pk_domain", "zk_pk_program_stats",
     "zk_evaluate_h", "zk_evaluate_h_dev",
-    "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_pkey_aux_ctx", "zk_proof_randoms", "zk_proof_max_bytes",
+    "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_pkey_aux_ctx", "zk_pkey_set_transcript", "zk_proof_randoms", "zk_proof_max_bytes",
     "zk_create_proof", "zk_verify_proof",
     "zk_group_unique_id", "zk_group_create", "zk_group_destroy", "zk_group_rank", "zk_group_world", "zk_pkey_set_group",
     "zk_group_shard_plan",
@@ -164,6 +165,7 @@ def load():
         "zk_pkey_vk_commitments": (i32, [vp, vp, vp]),
         "zk_pkey_pk": (vp, [vp]),
         "zk_pkey_aux_ctx": (vp, [vp]),
+        "zk_pkey_set_transcript": (i32, [vp, i32]),
         "zk_proof_randoms": (sz, [vp]),
         "zk_proof_max_bytes": (sz, [vp]),
         "zk_create_proof": (i32, [vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz)]),

@@ -46,6 +46,7 @@ struct zk_pkey {
   zk_ctx* ctx = nullptr;
   zk_pk* pk = nullptr;             // evaluate_h side (cosets, compiled program); owns its own domain
   zk_domain* dom = nullptr;
+  int transcript_kind = 0;        // ZK_TRANSCRIPT_BLAKE2B / ZK_TRANSCRIPT_EVM
   zk_group* group = nullptr;      // not owned: the GPUs that share this proof's commitments and h(X) rows
   // second stream: every lagrange_to_coeff / coeff_to_extended of the witness polynomials runs here, overlapping the
   // commitments and the lookup / permutation kernels of the main stream (they only meet again at evaluate_h)
@@ -524,6 +525,12 @@ extern "C" void zk_pkey_destroy(zk_pkey* K) {
 }
 extern "C" zk_pk* zk_pkey_pk(zk_pkey* K) { return K ? K->pk : nullptr; }
 extern "C" zk_ctx* zk_pkey_aux_ctx(zk_pkey* K) { return K ? K->ctxB : nullptr; }
+extern "C" int zk_pkey_set_transcript(zk_pkey* K, int kind) {
+  if (!K) return ZK_ERR_ARG;
+  if (kind != ZK_TRANSCRIPT_BLAKE2B && kind != ZK_TRANSCRIPT_EVM) ZK_FAIL(K->ctx, ZK_ERR_ARG, "zk_pkey_set_transcript: unknown transcript kind %d", kind);
+  K->transcript_kind = kind;
+  return ZK_OK;
+}
 extern "C" int zk_pkey_set_group(zk_pkey* K, zk_group* g) {
   if (!K) return ZK_ERR_ARG;
   if (g && zk_group_world(g) > 16) ZK_FAIL(K->ctx, ZK_ERR_ARG, "zk_pkey_set_group: at most 16 GPUs");
@@ -550,7 +557,7 @@ extern "C" size_t zk_proof_max_bytes(const zk_pkey* K) {
   if (!K) return 0;
   size_t points = K->n_advice + 2 * (size_t)K->n_lookups + K->n_sets + K->n_lookups + 1 + (K->degree - 1) + 2;
   size_t scalars = K->advice_queries.size() + K->fixed_queries.size() + 1 + K->n_perm + 3 * (size_t)K->n_sets + 5 * (size_t)K->n_lookups;
-  return 32 * (points + scalars);
+  return (K->transcript_kind == ZK_TRANSCRIPT_EVM ? 64 : 32) * points + 32 * scalars;
 }
 extern "C" int zk_pkey_vk_commitments(const zk_pkey* K, zk_g1_affine* fixed_commitments, zk_g1_affine* perm_commitments) {
   if (!K) return ZK_ERR_ARG;
@@ -775,7 +782,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     rpos += count;
     return ZK_OK;
   };
-  TranscriptWrite tr;
+  TranscriptWrite tr(K->transcript_kind);
   auto write_points = [&](const std::vector<HostPoint>& pts) -> int {
     for (auto& p : pts)
       if (!tr.write_point(p.x, p.y, p.identity)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: cannot write points at infinity to the transcript");

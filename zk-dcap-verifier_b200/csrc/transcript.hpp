@@ -116,33 +116,114 @@ inline Fr fr_from_bytes_wide(const uint8_t b[64]) {
   return (lo * r2 + hi * r3).reduce();
 }
 
+// Keccak-256 (padding 0x01, as Ethereum uses), FIPS 202 permutation
+struct Keccak256 {
+  static uint64_t rol(uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+  static void f1600(uint64_t a[25]) {
+    static const uint64_t rc[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL,
+                                    0x000000000000808BULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+                                    0x000000000000008AULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000AULL,
+                                    0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+                                    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800AULL, 0x800000008000000AULL,
+                                    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    static const int rot[5][5] = {{0, 36, 3, 41, 18}, {1, 44, 10, 45, 2}, {62, 6, 43, 15, 61}, {28, 55, 25, 21, 56}, {27, 20, 39, 8, 14}};
+    for (int r = 0; r < 24; r++) {          // lane (x, y) lives at a[x + 5 y]
+      uint64_t c[5], d[5], b[25];
+      for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+      for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rol(c[(x + 1) % 5], 1);
+      for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
+      for (int x = 0; x < 5; x++)
+        for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol(a[x + 5 * y], rot[x][y]);
+      for (int x = 0; x < 5; x++)
+        for (int y = 0; y < 5; y++) a[x + 5 * y] = b[x + 5 * y] ^ ((~b[(x + 1) % 5 + 5 * y]) & b[(x + 2) % 5 + 5 * y]);
+      a[0] ^= rc[r];
+    }
+  }
+  static void hash(const uint8_t* data, size_t len, uint8_t out[32]) {
+    const size_t rate = 136;
+    std::vector<uint8_t> m(data, data + len);
+    m.push_back(0x01);
+    while (m.size() % rate) m.push_back(0);
+    m.back() |= 0x80;
+    uint64_t a[25];
+    memset(a, 0, sizeof a);
+    for (size_t off = 0; off < m.size(); off += rate) {
+      for (size_t i = 0; i < rate / 8; i++) { uint64_t w; memcpy(&w, &m[off + 8 * i], 8); a[i] ^= w; }
+      f1600(a);
+    }
+    memcpy(out, a, 32);
+  }
+};
+
+constexpr int kTranscriptBlake2b = 0, kTranscriptEvm = 1;      // == zk_transcript_kind of the C ABI
+
+// kind 0: halo2's Blake2bWrite / Challenge255 (above).  kind 1: snark-verifier's EvmTranscript ([UPSTREAM?]
+// system/halo2/transcript/evm.rs; gen_evm_proof_shplonk at crates/p256-ecdsa/src/base.rs:193-199): a byte buffer hashed
+// with Keccak-256, points uncompressed (x, y big-endian), scalars big-endian, challenge = keccak(buf ++ [1 if |buf| = 32])
+// read big-endian mod r, the digest becomes the new buffer.
 struct TranscriptWrite {
+  int kind = kTranscriptBlake2b;
   Blake2b state;
+  std::vector<uint8_t> evm_buf;
   std::vector<uint8_t> proof;
-  TranscriptWrite() : state("Halo2-Transcript") {}
+  explicit TranscriptWrite(int kind_ = kTranscriptBlake2b) : kind(kind_), state("Halo2-Transcript") {}
+  static void be32(const uint8_t le[32], uint8_t out[32]) { for (int i = 0; i < 32; i++) out[i] = le[31 - i]; }
   Fr squeeze_challenge() {
+    if (kind == kTranscriptEvm) {
+      std::vector<uint8_t> data = evm_buf;
+      if (evm_buf.size() == 32) data.push_back(1);
+      uint8_t h[32], wide[64];
+      Keccak256::hash(data.data(), data.size(), h);
+      evm_buf.assign(h, h + 32);
+      memset(wide, 0, sizeof wide);
+      be32(h, wide);                          // big-endian digest -> little-endian integer, then mod r
+      return fr_from_bytes_wide(wide);
+    }
     uint8_t p = 0, d[64];
     state.update(&p, 1);
     state.digest(d);
     return fr_from_bytes_wide(d);
   }
   void common_scalar(const Fr& s) {
-    uint8_t p = 2, b[32];
+    uint8_t b[32];
     f_to_repr(s, b);
+    if (kind == kTranscriptEvm) { uint8_t r[32]; be32(b, r); evm_buf.insert(evm_buf.end(), r, r + 32); return; }
+    uint8_t p = 2;
     state.update(&p, 1); state.update(b, 32);
   }
   void write_scalar(const Fr& s) {
     common_scalar(s);
     uint8_t b[32]; f_to_repr(s, b);
+    if (kind == kTranscriptEvm) { uint8_t r[32]; be32(b, r); proof.insert(proof.end(), r, r + 32); return; }
     proof.insert(proof.end(), b, b + 32);
   }
-  // affine point in Montgomery form; returns false for the identity (upstream: io::Error "cannot write points at
-  // infinity to the transcript").  Compressed form: x little-endian, y parity in bit 7 of byte 31 [UPSTREAM?].
-  bool write_point(const Fq& x, const Fq& y, bool identity) {
+  // absorb only (the verifier replays what it has read)
+  bool common_point(const Fq& x, const Fq& y, bool identity) {
     if (identity) return false;
-    uint8_t p = 1, bx[32], by[32];
+    uint8_t bx[32], by[32];
     f_to_repr(x, bx); f_to_repr(y, by);
+    if (kind == kTranscriptEvm) {
+      uint8_t r[32];
+      be32(bx, r); evm_buf.insert(evm_buf.end(), r, r + 32);
+      be32(by, r); evm_buf.insert(evm_buf.end(), r, r + 32);
+      return true;
+    }
+    uint8_t p = 1;
     state.update(&p, 1); state.update(bx, 32); state.update(by, 32);
+    return true;
+  }
+  // affine point in Montgomery form; returns false for the identity (upstream: io::Error "cannot write points at
+  // infinity to the transcript").  Blake2b: compressed form, x little-endian, y parity in bit 7 of byte 31 [UPSTREAM?].
+  bool write_point(const Fq& x, const Fq& y, bool identity) {
+    if (!common_point(x, y, identity)) return false;
+    uint8_t bx[32], by[32];
+    f_to_repr(x, bx); f_to_repr(y, by);
+    if (kind == kTranscriptEvm) {
+      uint8_t r[32];
+      be32(bx, r); proof.insert(proof.end(), r, r + 32);
+      be32(by, r); proof.insert(proof.end(), r, r + 32);
+      return true;
+    }
     bx[31] |= (uint8_t)((by[0] & 1) << 7);
     proof.insert(proof.end(), bx, bx + 32);
     return true;

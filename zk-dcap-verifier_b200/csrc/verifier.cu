@@ -207,7 +207,20 @@ bool g1_on_curve(const P1& p) { return p.inf || (p.y.sqr() - (p.x.sqr() * p.x + 
 struct TranscriptRead {
   TranscriptWrite t;         // state + the same absorb functions; its proof buffer is unused
   const uint8_t* buf; size_t len, pos = 0;
+  explicit TranscriptRead(int kind) : t(kind) {}
   bool read_point(P1* out) {
+    if (t.kind == ZK_TRANSCRIPT_EVM) {                           // 64 bytes: x, y big-endian
+      if (pos + 64 > len) return false;
+      uint8_t bx[32], by[32];
+      for (int i = 0; i < 32; i++) { bx[i] = buf[pos + 31 - i]; by[i] = buf[pos + 63 - i]; }
+      pos += 64;
+      if (!f_is_canonical<Fq>(bx) || !f_is_canonical<Fq>(by)) return false;
+      out->x = f_canon_bytes<Fq>(bx); out->y = f_canon_bytes<Fq>(by); out->inf = false;
+      if (out->x.is_zero() && out->y.is_zero()) return false;
+      if (!g1_on_curve(*out)) return false;
+      t.common_point(out->x, out->y, false);
+      return true;
+    }
     if (pos + 32 > len) return false;
     uint8_t b[32]; memcpy(b, buf + pos, 32); pos += 32;
     bool allz = true; for (int i = 0; i < 32; i++) allz = allz && b[i] == 0;
@@ -221,13 +234,16 @@ struct TranscriptRead {
     if (!(y.sqr() - rhs).is_zero()) return false;
     if ((y.from_mont().l[0] & 1u) != sign) y = y.neg();
     out->x = x; out->y = y; out->inf = false;
-    t.write_point(x, y, false);
+    t.common_point(x, y, false);
     return true;
   }
   bool read_scalar(Fr* out) {
     if (pos + 32 > len) return false;
-    if (!f_is_canonical<Fr>(buf + pos)) return false;
-    *out = f_canon_bytes<Fr>(buf + pos); pos += 32;
+    uint8_t b[32];
+    if (t.kind == ZK_TRANSCRIPT_EVM) for (int i = 0; i < 32; i++) b[i] = buf[pos + 31 - i];
+    else memcpy(b, buf + pos, 32);
+    if (!f_is_canonical<Fr>(b)) return false;
+    *out = f_canon_bytes<Fr>(b); pos += 32;
     t.common_scalar(*out);
     return true;
   }
@@ -327,7 +343,8 @@ extern "C" int zk_verify_proof(const zk_circuit_desc* cd, const zk_verifier_para
   const uint32_t delta_c[8] = {0xe533e9a2u, 0x870e56bbu, 0x5e963f25u, 0x5b5f898eu, 0xd4c86e71u, 0x64ec26aau, 0x22c6f0cau, 0x09226b6eu};
   Fr delta; memcpy(delta.l, delta_c, 32); delta = delta.to_mont();
 
-  TranscriptRead tr; tr.buf = proof; tr.len = proof_len;
+  if (vp->transcript_kind != ZK_TRANSCRIPT_BLAKE2B && vp->transcript_kind != ZK_TRANSCRIPT_EVM) return ZK_ERR_ARG;
+  TranscriptRead tr(vp->transcript_kind); tr.buf = proof; tr.len = proof_len;
   tr.t.common_scalar(f_from_abi<Fr>(&cd->transcript_repr));
   for (uint32_t i = 0; i < D.n_instance; i++) {
     if (instance_lens[i] > n - (bf + 1)) return ZK_OK;

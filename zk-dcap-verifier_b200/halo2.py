@@ -715,6 +715,13 @@ class ProverKey:
         except Exception:
             pass
 
+    def set_transcript(self, kind):
+        """"blake2b" = Blake2bWrite / Challenge255 (default), "evm" = snark-verifier's EvmTranscript (Keccak-256)"""
+        self.ctx.check(self.ctx.lib.zk_pkey_set_transcript(self.h, _abi.TRANSCRIPTS[kind]))
+        self.max_proof_bytes = int(self.ctx.lib.zk_proof_max_bytes(self.h))
+        if hasattr(self, "_proof_buf"):
+            del self._proof_buf
+
     def set_group(self, group):
         """Proofs of this key are computed jointly by the group's GPUs (every rank must make the same calls)."""
         self.ctx.check(self.ctx.lib.zk_pkey_set_group(self.h, group.h if group is not None else None))
@@ -762,7 +769,7 @@ class ProverKey:
         return self._proof_buf[:ln.value].tobytes()
 
 
-def verify_proof(circuit, fixed_commitments, permutation_commitments, g1, g2, s_g2, instances, proof):
+def verify_proof(circuit, fixed_commitments, permutation_commitments, g1, g2, s_g2, instances, proof, transcript="blake2b"):
     """verify_proof::<KZGCommitmentScheme<Bn256>, VerifierSHPLONK<_>, Challenge255<_>, Blake2bRead<..>, SingleStrategy<_>>
     (circuits/src/sgx_dcap_verifier.rs:827-843) on the host.  fixed / permutation commitments: (count, 8) G1Affine;
     g1: (8,) G1Affine = params.g[0]; g2, s_g2: 128 uncompressed bytes each; instances: one (len, 4) array per column."""
@@ -776,6 +783,7 @@ def verify_proof(circuit, fixed_commitments, permutation_commitments, g1, g2, s_
         vp.g1[i] = int(v)
     b2, bs = np.frombuffer(bytes(g2), dtype=np.uint8), np.frombuffer(bytes(s_g2), dtype=np.uint8)
     vp.g2, vp.s_g2 = b2.ctypes.data, bs.ctypes.data
+    vp.transcript_kind = _abi.TRANSCRIPTS[transcript]
     inst = [_u64(i, (-1, 4)) for i in instances]
     ti, ki = _ptr_table(inst)
     lens = (C.c_uint32 * max(1, len(inst)))(*[i.shape[0] for i in inst])
