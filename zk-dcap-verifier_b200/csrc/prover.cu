@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <set>
 
@@ -469,13 +470,22 @@ int eval_rows(zk_pkey* K, uint32_t gi, const EvalScalars& S, char* out) {
 }
 
 // ---- host-side helpers of SHPLONK ----------------------------------------------------------------------------------
-// coefficients (low -> high) of the polynomial of degree < m through (points, evals)
-std::vector<Fr> lagrange_interpolate(const std::vector<Fr>& pts, const std::vector<Fr>& evals) {
+// Montgomery's trick on the host (a host field inversion is ~380 emulated multiplications: worth sharing)
+void host_batch_invert(std::vector<Fr>& v) {
+  std::vector<Fr> pre(v.size());
+  Fr acc = Fr::one();
+  for (size_t i = 0; i < v.size(); i++) { pre[i] = acc; acc = acc * v[i]; }
+  Fr inv = Fr::inv(acc);
+  for (size_t i = v.size(); i-- > 0;) { Fr t = inv * pre[i]; inv = inv * v[i]; v[i] = t; }
+}
+// Lagrange basis of a point set: basis[j] = coefficients (low -> high) of prod_{i != j} (X - x_i) / prod_{i != j} (x_j - x_i).
+// Every commitment of a rotation set interpolates through the SAME points, so the basis is built once per set.
+std::vector<std::vector<Fr>> lagrange_basis(const std::vector<Fr>& pts) {
   size_t m = pts.size();
-  std::vector<Fr> out(m, Fr::zero());
+  std::vector<std::vector<Fr>> basis(m);
+  std::vector<Fr> den(m, Fr::one());
   for (size_t j = 0; j < m; j++) {
     std::vector<Fr> num(1, Fr::one());
-    Fr den = Fr::one();
     for (size_t i = 0; i < m; i++) {
       if (i == j) continue;
       std::vector<Fr> nxt(num.size() + 1, Fr::zero());
@@ -484,11 +494,21 @@ std::vector<Fr> lagrange_interpolate(const std::vector<Fr>& pts, const std::vect
         nxt[t + 1] = nxt[t + 1] + num[t];
       }
       num.swap(nxt);
-      den = den * (pts[j] - pts[i]);
+      den[j] = den[j] * (pts[j] - pts[i]);
     }
-    Fr f = evals[j] * Fr::inv(den);
-    for (size_t t = 0; t < num.size(); t++) out[t] = out[t] + num[t] * f;
+    basis[j] = num;
   }
+  if (m > 1) host_batch_invert(den);          // m == 1: the denominator is the empty product
+  for (size_t j = 0; j < m; j++)
+    for (auto& c : basis[j]) c = c * den[j];
+  return basis;
+}
+// coefficients (low -> high) of the polynomial of degree < m through (points, evals)
+std::vector<Fr> lagrange_interpolate(const std::vector<std::vector<Fr>>& basis, const std::vector<Fr>& evals) {
+  size_t m = basis.size();
+  std::vector<Fr> out(m, Fr::zero());
+  for (size_t j = 0; j < m; j++)
+    for (size_t t = 0; t < m; t++) out[t] = out[t] + basis[j][t] * evals[j];
   return out;
 }
 Fr eval_small(const std::vector<Fr>& c, const Fr& x) {
@@ -783,6 +803,15 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     return ZK_OK;
   };
   TranscriptWrite tr(K->transcript_kind);
+  // ZK_PROVER_TRACE=1: host wall-clock at the section boundaries (after a stream sync), to find host-bound gaps
+  const bool trace = getenv("ZK_PROVER_TRACE") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+    fprintf(stderr, "[zk_create_proof] %-28s %8.3f ms\n", what, ms);
+  };
   auto write_points = [&](const std::vector<HostPoint>& pts) -> int {
     for (auto& p : pts)
       if (!tr.write_point(p.x, p.y, p.identity)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: cannot write points at infinity to the transcript");
@@ -876,6 +905,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     ZK_CUDA(ctx, cudaMemcpyAsync(K->d_challenges, ch.data(), ch.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
   }
   Fr theta = tr.squeeze_challenge();
+  mark("advice committed");
 
   // ---- lookups: compress, permute, commit A' and S' ---------------------------------------------------------------------
   // d_lookup holds five planes of L columns: 0 compressed inputs, 1 compressed tables, 2 A', 3 S', 4 Z -- so that the
@@ -941,6 +971,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     for (uint32_t l = 0; l < L; l++) ZK_TRY(write_points({pts[l], pts[L + l]}));
   }
   Fr beta = tr.squeeze_challenge();
+  mark("lookups permuted");
   Fr gamma = tr.squeeze_challenge();
 
   // ---- permutation.commit --------------------------------------------------------------------------------------------------
@@ -1023,6 +1054,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     ZK_TRY(write_points(pts));
   }
   Fr y = tr.squeeze_challenge();
+  mark("products committed");
 
   // ---- h(X): every coset is in place once the second stream has drained ----------------------------------------------
   {
@@ -1054,6 +1086,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     ZK_TRY(write_points(pts));
   }
   Fr x = tr.squeeze_challenge();
+  mark("h committed");
   Fr xn = Fr::pow_u64(x, (uint64_t)n);
 
   // ---- opening points and their power tables -----------------------------------------------------------------------------------
@@ -1105,6 +1138,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     }
   }
   for (size_t i = 0; i < n_written; i++) tr.write_scalar(evals[i]);
+  mark("evaluations");
 
   // ---- queries in create_proof's order ---------------------------------------------------------------------------------------------
   std::vector<Query> queries;
@@ -1180,6 +1214,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       sets[si].evals.push_back(ev);
     }
   }
+  mark("shplonk sets (host)");
   Fr ys = tr.squeeze_challenge();
   Fr v = tr.squeeze_challenge();
   while (K->d_setacc.size() < sets.size()) {
@@ -1188,9 +1223,11 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     K->d_setacc.push_back((char*)p);
   }
   // inverse power tables of the opening points (kate_division by suffix sums)
-  for (uint32_t p = 0; p < rot_of.size(); p++) {
-    if (pt_val[p].is_zero()) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: opening point is zero");
-    ZK_TRY(build_pow_table(K, Fr::inv(pt_val[p]), 2 * p + 1));
+  {
+    std::vector<Fr> inv_pts = pt_val;
+    for (auto& p : inv_pts) if (p.is_zero()) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: opening point is zero");
+    host_batch_invert(inv_pts);
+    for (uint32_t p = 0; p < rot_of.size(); p++) ZK_TRY(build_pow_table(K, inv_pts[p], 2 * p + 1));
   }
   std::vector<std::vector<Fr>> ypow(sets.size());
   std::vector<std::vector<std::vector<Fr>>> rpoly(sets.size());
@@ -1209,12 +1246,13 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
         if (off) { pp.push_back(K->d_setacc[i]); sc.push_back(Fr::one()); }
         ZK_TRY(lincomb(K, pp, sc, K->d_setacc[i]));
       }
+      const std::vector<std::vector<Fr>> basis = lagrange_basis(pts);
       LowPoly low; memset(&low, 0, sizeof low);
       low.m = (uint32_t)pts.size();
       if (low.m > 8) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: a polynomial is opened at more than 8 points");
       for (uint32_t t = 0; t < 8; t++) low.c[t] = Fr::zero();
       for (size_t j = 0; j < rs.polys.size(); j++) {
-        rpoly[i].push_back(lagrange_interpolate(pts, rs.evals[j]));                  // low_degree_equivalent
+        rpoly[i].push_back(lagrange_interpolate(basis, rs.evals[j]));                // low_degree_equivalent
         for (uint32_t t = 0; t < low.m; t++) low.c[t] = low.c[t] + ypow[i][j] * rpoly[i][j][t];
       }
       ZK_CUDA(ctx, cudaMemcpyAsync(K->d_w0, K->d_setacc[i], nb, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1234,6 +1272,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     ZK_TRY(write_points(pts));
   }
   Fr u = tr.squeeze_challenge();
+  mark("shplonk h committed");
   {
     std::vector<const void*> pp; std::vector<Fr> sc;
     Fr vpow = Fr::one(), c0 = Fr::zero(), z0_diff = Fr::one();
@@ -1266,6 +1305,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     ZK_TRY(commit(K, K->d_lx, 1, ZK_BASES_G, &pts));
     ZK_TRY(write_points(pts));
   }
+  mark("done");
   if (rpos != zk_proof_randoms(K)) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: drew %zu randoms, expected %zu", rpos, zk_proof_randoms(K));
   if (tr.proof.size() > proof_cap) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: proof needs %zu bytes, buffer holds %zu", tr.proof.size(), proof_cap);
   memcpy(proof, tr.proof.data(), tr.proof.size());
