@@ -87,6 +87,13 @@ extern "C" {
     pub fn zk_params_write(ctx: *mut zk_ctx, g2: *const u8, s_g2: *const u8, file: *mut u8, cap: usize, len: *mut usize) -> c_int;
     pub fn zk_g1_compress(ctx: *mut zk_ctx, points: *const zk_g1_affine, n: usize, out: *mut u8) -> c_int;
     pub fn zk_g1_decompress(ctx: *mut zk_ctx, input: *const u8, n: usize, out: *mut zk_g1_affine) -> c_int;
+    /// format: 0 = halo2curves 0.3.1 compressed, 1 = halo2curves >= 0.4 compressed, 2 = SerdeFormat::RawBytes
+    pub fn zk_g1_encode(ctx: *mut zk_ctx, format: c_int, points: *const zk_g1_affine, n: usize, out: *mut u8) -> c_int;
+    pub fn zk_g1_decode(ctx: *mut zk_ctx, format: c_int, input: *const u8, n: usize, out: *mut zk_g1_affine) -> c_int;
+    pub fn zk_params_read_format(ctx: *mut zk_ctx, format: c_int, file: *const u8, len: usize, precompute_windows: c_int,
+                                 k_out: *mut u32, g2: *mut u8, s_g2: *mut u8) -> c_int;
+    pub fn zk_params_write_format(ctx: *mut zk_ctx, format: c_int, g2: *const u8, s_g2: *const u8, file: *mut u8, cap: usize,
+                                  len: *mut usize) -> c_int;
     // one proof over several GPUs (one process per GPU)
     pub fn zk_group_unique_id(id: *mut u8) -> c_int;                 // 256 bytes
     pub fn zk_group_create(ctx: *mut zk_ctx, rank: u32, world: u32, id: *const u8, out: *mut *mut zk_group) -> c_int;

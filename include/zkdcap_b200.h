@@ -120,6 +120,22 @@ int zk_ctx_share_srs(zk_ctx* dst, const zk_ctx* src);
 int zk_params_read(zk_ctx* ctx, const uint8_t* file, size_t len, int precompute_windows, uint32_t* k_out,
                    uint8_t g2[64], uint8_t s_g2[64]);
 int zk_params_write(zk_ctx* ctx, const uint8_t g2[64], const uint8_t s_g2[64], uint8_t* file, size_t cap, size_t* len);
+
+/* SerdeFormat of the two halo2 stacks the reference links (A = halo2_proofs 0.2.0 / halo2curves 0.3.1,
+ * C = halo2-axiom 0.4.2 / halo2curves-axiom, Cargo.lock:1181-1199):
+ *   ZK_SERDE_PROCESSED      compressed, parity of y in bit 7 of byte 31, identity = zeros      (halo2curves 0.3.1)
+ *   ZK_SERDE_PROCESSED_V04  compressed, parity of y in bit 6, identity flag in bit 7           (halo2curves >= 0.4; the
+ *                           encoding of the commitments in bin/assets/proof.bin, bin/src/main.rs:270-279)
+ *   ZK_SERDE_RAW_BYTES      x | y as Montgomery limbs (64 B) = zk_g1_affine; G2 elements take 128 B
+ * zk_g1_encode / zk_g1_decode take host or device point arrays and host byte buffers; *_format are zk_params_read /
+ * zk_params_write for a given format (g2 / s_g2: 64 B compressed, 128 B for RAW_BYTES). */
+enum zk_serde_format { ZK_SERDE_PROCESSED = 0, ZK_SERDE_PROCESSED_V04 = 1, ZK_SERDE_RAW_BYTES = 2 };
+int zk_g1_encode(zk_ctx* ctx, int format, const zk_g1_affine* points, size_t n, uint8_t* out);
+int zk_g1_decode(zk_ctx* ctx, int format, const uint8_t* in, size_t n, zk_g1_affine* out);
+int zk_params_read_format(zk_ctx* ctx, int format, const uint8_t* file, size_t len, int precompute_windows,
+                          uint32_t* k_out, uint8_t* g2, uint8_t* s_g2);
+int zk_params_write_format(zk_ctx* ctx, int format, const uint8_t* g2, const uint8_t* s_g2, uint8_t* file, size_t cap,
+                           size_t* len);
 /* G1Affine::to_bytes / from_bytes for n points (host or device pointers in, host out); decompression fails with
  * ZK_ERR_ARG on a non-canonical x or a point that is not on the curve. */
 int zk_g1_compress(zk_ctx* ctx, const zk_g1_affine* points, size_t n, uint8_t* out);

@@ -62,6 +62,34 @@ def decompress_point(b):
     return (x, y)
 
 
+def compress_point_v04(pt):
+    """G1Affine::to_bytes of halo2curves >= 0.4 / halo2curves-axiom [UPSTREAM?] (the halo2-axiom stack, Cargo.lock:1181-1199):
+    parity of y in bit 6 of byte 31, identity = flag in bit 7.  The sign position is pinned by the flagged commitments of
+    the reference's bin/assets/proof.bin (tests/golden/ref_proof_points.json)."""
+    if pt is None:
+        return bytes(31) + b"\x80"
+    b = bytearray(pt[0].to_bytes(32, "little"))
+    b[31] |= (pt[1] & 1) << 6
+    return bytes(b)
+
+
+def decompress_point_v04(b):
+    if b[31] & 0x80:
+        if bytes(b[:31]) != bytes(31) or b[31] != 0x80:
+            raise ValueError("invalid point encoding")
+        return None
+    sign = (b[31] >> 6) & 1
+    x = int.from_bytes(bytes(b[:31]) + bytes([b[31] & 0x3F]), "little")
+    if x >= P:
+        raise ValueError("invalid point encoding")
+    y = pow((x * x * x + 3) % P, (P + 1) // 4, P)
+    if (y * y - x * x * x - 3) % P:
+        raise ValueError("not on curve")
+    if (y & 1) != sign:
+        y = P - y
+    return (x, y)
+
+
 class Blake2bWrite:
     """Blake2bWrite<Vec<u8>, G1Affine, Challenge255<G1Affine>> (sgx_dcap_verifier.rs:813)"""
 

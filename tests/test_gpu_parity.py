@@ -306,3 +306,67 @@ def test_params_file_round_trip(ctx, orc):
     assert params.write() == data
     with pytest.raises(zk.ZkError):
         zk.ParamsKZG.read(data[:-1], ctx)
+
+
+def test_point_encodings_v04_and_raw_against_golden_proof(ctx, orc):
+    """halo2curves >= 0.4 compressed form on the commitments of the reference's golden proof (tests/golden), and
+    SerdeFormat::RawBytes"""
+    import json
+    import os
+    from oracle import prover as op
+    from oracle import pymodel as pm
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_proof_points.json")) as f:
+        g = json.load(f)
+    idx = sorted(int(i) for i in g["points"])
+    comp = np.stack([np.frombuffer(bytes.fromhex(g["chunks"][i]), dtype=np.uint8) for i in idx])
+    pts = zk.g1_decompress(comp, ctx, fmt="processed_v04")
+    want = [tuple(int(v, 16) for v in g["points"][str(i)]) for i in idx]
+    assert pm.limbs_to_affine(pts) == want
+    assert np.array_equal(zk.g1_compress(pts, ctx, fmt="processed_v04"), comp)
+    with pytest.raises(zk.ZkError):                                  # flagged chunks are not 0.3.1 encodings
+        zk.g1_decompress(comp[[idx.index(i) for i in g["flagged"]]], ctx)
+    # a mixed batch with the identity, against the oracle codec
+    mix = orc.gen_points(5, 200)
+    mix[1::2, 4:] = orc.field_op("fq", "neg", mix[1::2, 4:])          # both parities of y
+    mix[7] = 0
+    c04 = zk.g1_compress(mix, ctx, fmt="processed_v04")
+    assert [bytes(c) for c in c04] == [op.compress_point_v04(p) for p in pm.limbs_to_affine(mix)]
+    assert np.array_equal(zk.g1_decompress(c04, ctx, fmt="processed_v04"), mix)
+    bad = c04.copy()
+    bad[7, 0] = 1                                                    # identity flag with a non-zero body
+    with pytest.raises(zk.ZkError):
+        zk.g1_decompress(bad, ctx, fmt="processed_v04")
+    raw = zk.g1_compress(mix, ctx, fmt="raw_bytes")
+    assert raw.tobytes() == mix.tobytes()
+    assert np.array_equal(zk.g1_decompress(raw, ctx, fmt="raw_bytes"), mix)
+    off = mix.copy()
+    off[3, 4] ^= np.uint64(1)                                        # y off the curve
+    with pytest.raises(zk.ZkError):
+        zk.g1_decompress(zk.g1_compress(off, ctx, fmt="raw_bytes"), ctx, fmt="raw_bytes")
+
+
+@pytest.mark.parametrize("fmt", ["processed_v04", "raw_bytes"])
+def test_params_file_formats(ctx, orc, fmt):
+    from oracle import prover as op
+    from oracle import pymodel as pm
+    k = 5
+    n = 1 << k
+    g, gl = orc.gen_points(191, n), orc.gen_points(192, n)
+    g[1::2, 4:] = orc.field_op("fq", "neg", g[1::2, 4:])              # both parities of y
+    qb = 128 if fmt == "raw_bytes" else 64
+    g2 = bytes(i & 0xFF for i in range(qb)); s_g2 = bytes((i * 7) & 0xFF for i in range(qb))
+    if fmt == "raw_bytes":
+        body = g.tobytes() + gl.tobytes()
+    else:
+        body = b"".join(op.compress_point_v04(p) for p in pm.limbs_to_affine(g)) + \
+            b"".join(op.compress_point_v04(p) for p in pm.limbs_to_affine(gl))
+    data = (k).to_bytes(4, "little") + body + g2 + s_g2
+    params = zk.ParamsKZG.read(data, ctx, fmt=fmt)
+    assert params.k == k and bytes(params.g2) == g2 and bytes(params.s_g2) == s_g2
+    poly = orc.gen_scalars(193, n)
+    assert np.array_equal(orc.g1_to_affine(params.commit(poly)), orc.g1_to_affine(orc.best_multiexp(poly, g)))
+    assert np.array_equal(orc.g1_to_affine(params.commit_lagrange(poly)), orc.g1_to_affine(orc.best_multiexp(poly, gl)))
+    assert params.write(fmt=fmt) == data
+    if fmt == "processed_v04":                                       # bit 6 set: x >= p for the 0.3.1 reader
+        with pytest.raises(zk.ZkError):
+            zk.ParamsKZG.read(data, ctx, fmt="processed")

@@ -119,3 +119,30 @@ def test_unsatisfied_witness_is_rejected():
     adv[0][3] = adv[0][7]                                          # break the first gate's output cell
     proof = op.create_proof(orc, pc.params_for(5), pk, case["circ"], adv, case["instances_int"], case["randoms"])
     assert not ov.verify_proof(pc.verifier_params(), pk["vk"], case["cs"], 5, case["instances_int"], proof)
+
+
+# ---- the reference's golden proof pins the halo2curves >= 0.4 point encoding ---------------------------------------
+def _golden_points():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_proof_points.json")) as f:
+        return json.load(f)
+
+
+def test_golden_proof_point_encoding_v04():
+    from oracle import prover as op
+    g = _golden_points()
+    chunks = [bytes.fromhex(c) for c in g["chunks"]]
+    assert len(chunks) == 47 and g["flagged"] == [1, 2, 3, 4, 45, 46]
+    for i in g["flagged"]:
+        pt = op.decompress_point_v04(chunks[i])
+        assert pt == tuple(int(v, 16) for v in g["points"][str(i)])
+        assert (pt[1] * pt[1] - pt[0] ** 3 - 3) % op.P == 0 and pt[1] & 1 == 1
+        assert op.compress_point_v04(pt) == chunks[i]
+        # the 0.3.1 reader takes bit 6 for part of x and must refuse (x >= p)
+        with pytest.raises(ValueError):
+            op.decompress_point(chunks[i])
+    for i, xy in g["points"].items():
+        pt = tuple(int(v, 16) for v in xy)
+        assert op.decompress_point_v04(chunks[int(i)]) == pt and op.compress_point_v04(pt) == chunks[int(i)]
+    assert op.decompress_point_v04(op.compress_point_v04(None)) is None

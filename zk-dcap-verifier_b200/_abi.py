@@ -81,6 +81,7 @@ SYMBOLS = [
     "zk_dev_alloc", "zk_dev_free", "zk_h2d", "zk_d2h",
     "zk_srs_upload", "zk_srs_upload_dev", "zk_g1_fixed_base_mul_dev", "zk_ctx_share_srs",
     "zk_params_read", "zk_params_write", "zk_g1_compress", "zk_g1_decompress",
+    "zk_g1_encode", "zk_g1_decode", "zk_params_read_format", "zk_params_write_format",
     "zk_msm", "zk_msm_dev", "zk_msm_batch_dev", "zk_g1_sum", "zk_g1_sum_dev",
     "zk_ntt", "zk_ntt_dev",
     "zk_domain_create", "zk_domain_destroy", "zk_domain_k", "zk_domain_extended_k", "zk_domain_constants",
@@ -132,6 +133,10 @@ def load():
         "zk_params_write": (i32, [vp, vp, vp, vp, sz, C.POINTER(sz)]),
         "zk_g1_compress": (i32, [vp, vp, sz, vp]),
         "zk_g1_decompress": (i32, [vp, vp, sz, vp]),
+        "zk_g1_encode": (i32, [vp, i32, vp, sz, vp]),
+        "zk_g1_decode": (i32, [vp, i32, vp, sz, vp]),
+        "zk_params_read_format": (i32, [vp, i32, vp, sz, i32, C.POINTER(u32), vp, vp]),
+        "zk_params_write_format": (i32, [vp, i32, vp, vp, vp, sz, C.POINTER(sz)]),
         "zk_msm": (i32, [vp, vp, vp, i32, sz, vp]),
         "zk_msm_dev": (i32, [vp, vp, vp, i32, sz, vp]),
         "zk_msm_batch_dev": (i32, [vp, vp, i32, sz, sz, vp]),

@@ -159,21 +159,30 @@ def best_fft(a, omega, log_n, ctx=None):
     return a
 
 
-def g1_compress(points, ctx=None):
-    """G1Affine::to_bytes for (n, 8) points -> (n, 32) uint8"""
+# SerdeFormat: "processed" = halo2curves 0.3.1 compressed; "processed_v04" = halo2curves >= 0.4 / halo2curves-axiom
+# compressed (parity in bit 6, identity flag in bit 7); "raw_bytes" = x | y Montgomery limbs
+SERDE_FORMATS = {"processed": 0, "processed_v04": 1, "raw_bytes": 2}
+
+
+def _g1_bytes(fmt):
+    return 64 if SERDE_FORMATS[fmt] == 2 else 32
+
+
+def g1_compress(points, ctx=None, fmt="processed"):
+    """G1Affine::to_bytes (or SerdeObject::write_raw for "raw_bytes") for (n, 8) points -> (n, 32 | 64) uint8"""
     ctx = ctx or default_context()
     points = _u64(points, (-1, 8))
-    out = np.empty((points.shape[0], 32), dtype=np.uint8)
-    ctx.check(ctx.lib.zk_g1_compress(ctx.h, _ptr(points), points.shape[0], _ptr(out)))
+    out = np.empty((points.shape[0], _g1_bytes(fmt)), dtype=np.uint8)
+    ctx.check(ctx.lib.zk_g1_encode(ctx.h, SERDE_FORMATS[fmt], _ptr(points), points.shape[0], _ptr(out)))
     return out
 
 
-def g1_decompress(data, ctx=None):
-    """G1Affine::from_bytes for (n, 32) uint8 -> (n, 8) points; raises on an invalid encoding"""
+def g1_decompress(data, ctx=None, fmt="processed"):
+    """G1Affine::from_bytes for (n, 32 | 64) uint8 -> (n, 8) points; raises on an invalid encoding"""
     ctx = ctx or default_context()
-    data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 32)
+    data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, _g1_bytes(fmt))
     out = np.empty((data.shape[0], 8), dtype=np.uint64)
-    ctx.check(ctx.lib.zk_g1_decompress(ctx.h, _ptr(data), data.shape[0], _ptr(out)))
+    ctx.check(ctx.lib.zk_g1_decode(ctx.h, SERDE_FORMATS[fmt], _ptr(data), data.shape[0], _ptr(out)))
     return out
 
 
@@ -197,25 +206,35 @@ class ParamsKZG:
         self.ctx.check(self.ctx.lib.zk_srs_upload(self.ctx.h, k, _ptr(g), _ptr(gl), 1 if precompute else 0))
 
     @classmethod
-    def read(cls, data, ctx=None, precompute=True):
-        """ParamsKZG::read: `data` = bytes of a kzg_bn254_{k}.srs file; the points are decompressed on the device."""
+    def read(cls, data, ctx=None, precompute=True, fmt="processed"):
+        """ParamsKZG::read / read_custom: `data` = bytes of a kzg_bn254_{k}.srs file; compressed points are decompressed on
+        the device."""
         self = cls.__new__(cls)
         self.ctx = ctx or default_context()
         buf = np.frombuffer(bytes(data), dtype=np.uint8)
         k = C.c_uint32()
-        self.g2, self.s_g2 = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
-        self.ctx.check(self.ctx.lib.zk_params_read(self.ctx.h, _ptr(buf), buf.size, 1 if precompute else 0, C.byref(k),
-                                                   _ptr(self.g2), _ptr(self.s_g2)))
+        qb = 2 * _g1_bytes(fmt)
+        self.g2, self.s_g2 = np.zeros(qb, np.uint8), np.zeros(qb, np.uint8)
+        self.ctx.check(self.ctx.lib.zk_params_read_format(self.ctx.h, SERDE_FORMATS[fmt], _ptr(buf), buf.size,
+                                                          1 if precompute else 0, C.byref(k), _ptr(self.g2), _ptr(self.s_g2)))
         self.k, self.n = k.value, 1 << k.value
         return self
 
-    def write(self, g2=None, s_g2=None):
-        """ParamsKZG::write of the resident SRS -> bytes"""
-        out = np.empty(4 + 2 * self.n * 32 + 128, dtype=np.uint8)
+    def write(self, g2=None, s_g2=None, fmt="processed"):
+        """ParamsKZG::write / write_custom of the resident SRS -> bytes"""
+        pb = _g1_bytes(fmt)
+        out = np.empty(4 + 2 * self.n * pb + 4 * pb, dtype=np.uint8)
         ln = C.c_size_t()
-        g2 = np.ascontiguousarray(g2 if g2 is not None else getattr(self, "g2", np.zeros(64, np.uint8)), dtype=np.uint8)
-        s_g2 = np.ascontiguousarray(s_g2 if s_g2 is not None else getattr(self, "s_g2", np.zeros(64, np.uint8)), dtype=np.uint8)
-        self.ctx.check(self.ctx.lib.zk_params_write(self.ctx.h, _ptr(g2), _ptr(s_g2), _ptr(out), out.size, C.byref(ln)))
+
+        def g2_bytes(v, name):
+            v = v if v is not None else getattr(self, name, None)
+            v = np.zeros(2 * pb, np.uint8) if v is None else np.ascontiguousarray(v, dtype=np.uint8)
+            if v.size != 2 * pb:
+                raise ValueError("%s: %d bytes, the format takes %d" % (name, v.size, 2 * pb))
+            return v
+        g2, s_g2 = g2_bytes(g2, "g2"), g2_bytes(s_g2, "s_g2")
+        self.ctx.check(self.ctx.lib.zk_params_write_format(self.ctx.h, SERDE_FORMATS[fmt], _ptr(g2), _ptr(s_g2), _ptr(out),
+                                                           out.size, C.byref(ln)))
         return out[:ln.value].tobytes()
 
     def _commit(self, poly, which):
