@@ -252,9 +252,17 @@ int commit_enqueue(zk_pkey* K, const char* d_polys, size_t count, int which, siz
   zk_group_shard_plan(rank, world, count, K->n, &mode, &per, &lo, &hi);
   PtRaw* xchg = (PtRaw*)K->d_xchg;
   if (mode == 0) {
-    if (hi > lo) ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)(d_polys + lo * K->n * 32), which, K->n, hi - lo, (zk_g1*)(xchg + (size_t)rank * per)));
+    // by column, ROUND-ROBIN (column p belongs to rank p mod world): neighbouring columns of a region tend to hold the same
+    // kind of values (bits and bytes are cheap commitments, field elements expensive), contiguous ranges do not balance
+    auto owned = [&](uint32_t r) { return count > r ? (count - r + world - 1) / world : (size_t)0; };
+    if (owned(rank))
+      ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)(d_polys + (size_t)rank * K->n * 32), which, (size_t)world * K->n, 0, K->n, owned(rank),
+                                    (zk_g1*)(xchg + (size_t)rank * per)));
     ZK_TRY(zk_group_allgather(K->group, ctx, xchg, per * sizeof(PtRaw)));
-    ZK_CUDA(ctx, cudaMemcpyAsync(out, xchg, count * sizeof(PtRaw), cudaMemcpyDeviceToDevice, ctx->stream));
+    for (uint32_t r = 0; r < world; r++)
+      if (owned(r))
+        ZK_CUDA(ctx, cudaMemcpy2DAsync(out + r, (size_t)world * sizeof(PtRaw), xchg + (size_t)r * per, sizeof(PtRaw), sizeof(PtRaw), owned(r),
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
   } else {
     if (hi > lo) ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, lo, hi - lo, count, (zk_g1*)(xchg + (size_t)rank * count)));
     else ZK_CUDA(ctx, cudaMemsetAsync(xchg + (size_t)rank * count, 0, count * sizeof(PtRaw), ctx->stream));   // zz = 0: identity
