@@ -194,3 +194,125 @@ def test_evm_transcript_proof_bytes(ctx):
     key.set_transcript("blake2b")
     assert key.create_proof(case["advice"], case["instances_limbs"], case["randoms"]) == \
         op.create_proof(orc, p, opk, case["circ"], case["advice"], case["instances_int"], case["randoms"])
+
+
+# ---- random constraint systems ------------------------------------------------------------------------------------------
+def _random_expression(rng, cs_dims, depth, max_degree):
+    """random expression tree over the columns; degree kept <= max_degree"""
+    E = zk.Expression
+    nf, na, ni, nc = cs_dims
+
+    def leaf():
+        kinds = ["fixed", "advice", "advice", "const"] + (["instance"] if ni else []) + (["challenge"] if nc else [])
+        kind = kinds[rng.integers(0, len(kinds))]
+        rot = int(rng.integers(-2, 3))
+        if kind == "fixed":
+            return E.Fixed(int(rng.integers(0, nf)), rot), 1
+        if kind == "advice":
+            return E.Advice(int(rng.integers(0, na)), rot), 1
+        if kind == "instance":
+            return E.Instance(int(rng.integers(0, ni)), rot), 1
+        if kind == "challenge":
+            return E.Challenge(int(rng.integers(0, nc))), 0
+        return E.Constant(int(rng.integers(0, 1 << 62))), 0
+
+    def build(d):
+        if d == 0 or rng.integers(0, 4) == 0:
+            return leaf()
+        op_ = rng.integers(0, 5)
+        a, da = build(d - 1)
+        if op_ == 0:
+            return -a, da
+        if op_ == 1:
+            return a * int(rng.integers(1, 1 << 30)), da
+        b, db = build(d - 1)
+        if op_ == 2 and da + db <= max_degree:
+            return a * b, da + db
+        if op_ == 3:
+            return a - b, max(da, db)
+        return a + b, max(da, db)
+    return build(depth)
+
+
+def _random_circuit(seed):
+    rng = np.random.default_rng(seed)
+    E = zk.Expression
+    nf, na = int(rng.integers(3, 6)), int(rng.integers(2, 6))
+    ni, nc = int(rng.integers(0, 3)), int(rng.integers(0, 2))
+    cs = zk.ConstraintSystem(num_fixed=nf, num_advice=na, num_instance=ni, num_challenges=nc)
+    max_degree = int(rng.integers(2, 10))
+    for _ in range(int(rng.integers(1, 4))):
+        polys = []
+        for _ in range(int(rng.integers(1, 4))):
+            e, d = _random_expression(rng, (nf, na, ni, nc), 3, max_degree - 1)
+            for _ in range(int(rng.integers(0, max(1, max_degree - d)))):      # raise the degree with more column factors
+                e = e * E.Advice(int(rng.integers(0, na)), int(rng.integers(-1, 2)))
+            polys.append(E.Fixed(int(rng.integers(0, nf))) * e)
+        cs.create_gate(polys)
+    # lookups: q * advice columns into fixed table columns (fixed column 0 is the selector, the last ones are tables)
+    lookups = []
+    for _ in range(int(rng.integers(0, 4))):
+        width = int(rng.integers(1, 3))
+        a_cols = [int(c) for c in rng.choice(na, size=min(width, na), replace=False)]
+        t_cols = [int(c) for c in rng.choice(np.arange(1, nf), size=len(a_cols), replace=False)]
+        q = E.Fixed(0)
+        cs.lookup([q * E.Advice(a) for a in a_cols], [E.Fixed(t) for t in t_cols])
+        lookups.append((a_cols, t_cols))
+    cols = [(0, i) for i in range(na)] + [(1, i) for i in range(nf)] + [(2, i) for i in range(ni)]
+    for ci in rng.permutation(len(cols))[:int(rng.integers(0, len(cols) + 1))]:
+        cs.enable_equality(*cols[int(ci)])
+    return cs, lookups, rng
+
+
+@pytest.mark.parametrize("seed", list(range(101, 125)))
+def test_random_constraint_systems(ctx, seed):
+    """random gates (rotations -2..2, challenges, instances), 0-3 lookup arguments, random equality columns and random
+    copy cycles: the two provers must write the same bytes.  The gates are not satisfied (neither prover checks them);
+    lookup inputs are drawn from their tables so that permute_expression_pair succeeds."""
+    cs, lookups, rng = _random_circuit(seed)
+    k = int(rng.integers(5, 8))
+    n = 1 << k
+    usable = n - (cs.blinding_factors() + 1)
+    if usable < 4:
+        pytest.skip("degree too high for this k")
+    fixed, advice, mapping = _random_witness_case(cs, k, seed)
+    if lookups:
+        # selector column 0: random bits; every table gets the all-zero row 0 (the inputs of unselected rows)
+        one = pm.to_mont_limbs([1], pm.R_MOD)[0]
+        sel = rng.integers(0, 2, size=n).astype(bool)
+        fixed[0][:] = 0
+        fixed[0][sel] = one
+        tab_rows = int(rng.integers(2, max(3, usable // 2)))
+        claimed = set()
+        for a_cols, t_cols in lookups:
+            for t in t_cols:
+                fixed[t][0] = 0
+                fixed[t][tab_rows:] = 0
+            a_free = [a for a in a_cols if a not in claimed]
+            pick = rng.integers(0, tab_rows, size=n)
+            for a, t in zip(a_cols, t_cols):
+                if a in a_free:
+                    advice[a][sel] = fixed[t][pick][sel]
+                    claimed.add(a)
+        # a column shared by two lookups may miss its second table; rebuild consistently: every advice column used by
+        # more than one lookup is zeroed on selected rows (row 0 of every table is zero)
+        seen = {}
+        for a_cols, t_cols in lookups:
+            for a in a_cols:
+                seen[a] = seen.get(a, 0) + 1
+        shared = {a for a, c in seen.items() if c > 1}
+        for a_cols, t_cols in lookups:
+            if any(a in shared for a in a_cols):
+                for a in a_cols:
+                    advice[a][sel] = 0
+        # tables are fixed columns that may themselves be selector 0?  no: t_cols are drawn from 1..nf-1
+    # random copy cycles (2-cycles between random cells of the equality columns)
+    P = len(cs.permutation_columns)
+    if P:
+        cells = rng.permutation(P * n)[:2 * int(rng.integers(0, 3 * n // 4))]
+        for a, b in zip(cells[0::2], cells[1::2]):
+            ca, ra, cb, rb = int(a) // n, int(a) % n, int(b) // n, int(b) % n
+            mapping[ca, ra] = (cb, rb)
+            mapping[cb, rb] = (ca, ra)
+    inst = [[int(v) for v in rng.integers(0, 1 << 62, size=int(rng.integers(0, min(usable, 9))))] for _ in range(cs.num_instance_columns)]
+    _both_provers(ctx, cs, k, fixed, advice, mapping, inst, seed)
