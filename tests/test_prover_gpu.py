@@ -316,3 +316,29 @@ def test_random_constraint_systems(ctx, seed):
             mapping[cb, rb] = (ca, ra)
     inst = [[int(v) for v in rng.integers(0, 1 << 62, size=int(rng.integers(0, min(usable, 9))))] for _ in range(cs.num_instance_columns)]
     _both_provers(ctx, cs, k, fixed, advice, mapping, inst, seed)
+
+
+@pytest.mark.parametrize("seed", list(range(201, 211)))
+def test_random_satisfied_circuits(ctx, seed):
+    """random circuits with a satisfying witness: same bytes as the CPU prover, accepted by the Python verifier and by
+    zk_verify_proof; a broken gate output is rejected"""
+    from tests.test_verifier_host import native_verify
+    case = pc.random_satisfied_case(seed)
+    k = case["k"]
+    p = pc.params_for(k)
+    params = zk.ParamsKZG(k, p["g"], p["g_lagrange"], ctx, precompute=True)
+    key = zk.ProverKey(params, case["circ"], case["fixed"], case["mapping"])
+    opk = pc.oracle_key(case)
+    want = op.create_proof(orc, p, opk, case["circ"], case["advice"], case["instances_int"], case["randoms"])
+    got = key.create_proof(case["advice"], case["instances_limbs"], case["randoms"])
+    assert got == want, "first differing item %d" % first_diff(got, want)
+    assert ov.verify_proof(pc.verifier_params(), opk["vk"], case["cs"], k, case["instances_int"], got)
+    assert native_verify(case, opk, case["instances_limbs"], got)
+    fc, pcm = key.vk_commitments()
+    assert pm.limbs_to_affine(fc) == list(opk["vk"]["fixed_commitments"])
+    assert pm.limbs_to_affine(pcm) == list(opk["vk"]["permutation_commitments"])
+    if case["first_gate_rows"]:
+        adv = [a.copy() for a in case["advice"]]
+        adv[case["first_output"]][case["first_gate_rows"][0], 0] ^= np.uint64(1)
+        bad = key.create_proof(adv, case["instances_limbs"], case["randoms"])
+        assert not native_verify(case, opk, case["instances_limbs"], bad)

@@ -72,3 +72,35 @@ def test_evm_transcript_proofs():
     bad = bytearray(proof); bad[200] ^= 2
     assert not native_verify(case, pk, case["instances_limbs"], bytes(bad), transcript="evm")
     assert not ov.verify_proof(pc.verifier_params(), pk["vk"], case["cs"], 5, case["instances_int"], bytes(bad), transcript="evm")
+
+
+@pytest.mark.parametrize("seed", list(range(201, 211)))
+def test_random_satisfied_circuits_are_accepted_by_both_verifiers(seed):
+    """random gates / lookups / copy constraints WITH a satisfying witness (tests/prover_common.random_satisfied_case):
+    both verifiers accept the proof; breaking one gate output, one looked-up cell or one copied cell makes both reject"""
+    case = pc.random_satisfied_case(seed)
+    k = case["k"]
+    pk = pc.oracle_key(case)
+    proof = op.create_proof(orc, pc.params_for(k), pk, case["circ"], case["advice"], case["instances_int"], case["randoms"])
+    assert ov.verify_proof(pc.verifier_params(), pk["vk"], case["cs"], k, case["instances_int"], proof)
+    assert native_verify(case, pk, case["instances_limbs"], proof)
+    # break a gate: an output cell on a row whose selector is on
+    cs = case["cs"]
+
+    def rejected(adv):
+        bad = op.create_proof(orc, pc.params_for(k), pk, case["circ"], adv, case["instances_int"], case["randoms"])
+        return not ov.verify_proof(pc.verifier_params(), pk["vk"], cs, k, case["instances_int"], bad) and \
+            not native_verify(case, pk, case["instances_limbs"], bad)
+    if case["first_gate_rows"]:
+        adv = [a.copy() for a in case["advice"]]
+        adv[case["first_output"]][case["first_gate_rows"][0], 0] ^= np.uint64(1)
+        assert rejected(adv)
+    # break a copy constraint: one cell of a 2-cycle between advice cells
+    pcols = cs.permutation_columns
+    cyc = [(c, r) for c in range(len(pcols)) for r in range(1 << k)
+           if tuple(case["mapping"][c, r]) != (c, r) and pcols[c][0] == 0]
+    if cyc:
+        c, r = cyc[0]
+        adv = [a.copy() for a in case["advice"]]
+        adv[pcols[c][1]][r, 0] ^= np.uint64(1)
+        assert rejected(adv)
