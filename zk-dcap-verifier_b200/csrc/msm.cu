@@ -71,6 +71,61 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint4* scalars, MsmPla
   }
 }
 
+// The same two passes with the bucket counters of the MSM in SHARED memory: a CTA takes a contiguous chunk of one MSM's
+// scalars, counts its digits on chip, and global memory sees ONE atomic per (CTA, non-empty bucket) instead of one per
+// digit.  That one atomic also reserves the CTA's share of the bucket; the scatter pass (same grid, same chunks) starts its
+// shared counters at those positions and hands them out with shared-memory atomics.  The order of
+// the entries inside a bucket is arbitrary either way (the bucket sum does not depend on it).  Needs nb * 4 bytes of shared
+// memory (128 KB for the resident window table at c = 16); ncu on the global-atomic version: 73 of 78 stall cycles per issue
+// on the atomics' round trip at full occupancy (profiles/r1_fullproof_msm_digits_v7.txt).
+constexpr uint32_t kDigitsSmemThreads = 1024;
+template <class F>
+__device__ __forceinline__ void for_each_digit(const uint4* scalars, const MsmPlan& P, size_t msm, size_t i, F&& f) {
+  Fr s = Fr::load(scalars + 2 * (msm * P.sc_stride + P.base_off + i)).from_mont();
+  int carry = 0;
+  for (uint32_t w = 0; w < P.W; w++) {
+    int d = signed_digit(s.l, (int)w, (int)P.c, carry);
+    if (d == 0) continue;
+    uint32_t neg = d < 0 ? 1u : 0u;
+    uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+    uint32_t bucket = (P.G == 1 ? 0u : w * P.B) + (mag - 1);
+    uint32_t idx = (P.G == 1) ? (uint32_t)(w * P.stride + P.base_off + i) : (uint32_t)i;
+    f(bucket, idx | (neg << 31));
+  }
+}
+template <bool SCATTER>
+__global__ void __launch_bounds__(kDigitsSmemThreads, 1) k_msm_digits_smem(const uint4* scalars, MsmPlan P, uint32_t* counts,
+                                                                          const uint32_t* starts, uint32_t* entries, size_t i_begin,
+                                                                          size_t i_end, size_t chunk, uint32_t* cta_base) {
+  extern __shared__ uint32_t sh_cnt[];
+  const size_t msm = blockIdx.y;
+  const size_t lo = i_begin + blockIdx.x * chunk;
+  const size_t hi = lo + chunk < i_end ? lo + chunk : i_end;
+  const uint32_t nb = (uint32_t)P.nb;
+  // this CTA's share of every bucket starts at base[b] inside the bucket: reserved by the histogram pass (the value its one
+  // global atomic returned), read back by the scatter pass, which therefore walks its chunk only once
+  uint32_t* base = cta_base + ((i_begin / chunk + blockIdx.x) * (size_t)gridDim.y + blockIdx.y) * P.nb;   // launches start on chunk boundaries
+  if (!SCATTER) {
+    uint32_t* cnt = counts + msm * P.nb;
+    for (uint32_t b = threadIdx.x; b < nb; b += kDigitsSmemThreads) sh_cnt[b] = 0;
+    __syncthreads();
+    for (size_t i = lo + threadIdx.x; i < hi; i += kDigitsSmemThreads)
+      for_each_digit(scalars, P, msm, i, [&](uint32_t bucket, uint32_t) { atomicAdd(&sh_cnt[bucket], 1u); });
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nb; b += kDigitsSmemThreads) {
+      uint32_t v = sh_cnt[b];
+      base[b] = v ? atomicAdd(&cnt[b], v) : 0u;
+    }
+    return;
+  }
+  const uint32_t* st = starts + msm * (P.nb + 1);
+  for (uint32_t b = threadIdx.x; b < nb; b += kDigitsSmemThreads) sh_cnt[b] = st[b] + base[b];
+  __syncthreads();
+  uint32_t* ent = entries + msm * P.ent_per_msm;
+  for (size_t i = lo + threadIdx.x; i < hi; i += kDigitsSmemThreads)
+    for_each_digit(scalars, P, msm, i, [&](uint32_t bucket, uint32_t e) { ent[atomicAdd(&sh_cnt[bucket], 1u)] = e; });
+}
+
 // exclusive scan of nb counts per MSM (one CTA per MSM), writes nb+1 offsets and clears the counts
 __global__ void __launch_bounds__(1024) k_msm_scan(uint32_t* counts, uint32_t* starts, size_t nb) {
   __shared__ uint32_t part[1024];
@@ -653,21 +708,64 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   size_t off_ba_st = off_ba_cnt + align(use_ba ? cnt_bytes : 0);
   size_t off_ba_pts = off_ba_st + align(use_ba ? st_bytes : 0);
   size_t off_ba_scr = off_ba_pts + align(use_ba ? P.count * out_cap * 64 : 0);
-  size_t total = off_ba_scr + align(use_ba ? P.count * baM * ba_threads * 32 : 0);
+  // shared-memory counters when one MSM's bucket set fits (ZK_MSM_DIGITS=global keeps the per-digit global atomics)
+  static const bool digits_global = getenv("ZK_MSM_DIGITS") && !strcmp(getenv("ZK_MSM_DIGITS"), "global");
+  const size_t dsm = P.nb * 4;
+  const bool digits_smem = !digits_global && dsm <= 200 * 1024 && P.n >= 8192;
+  size_t dchunk = 0;
+  if (digits_smem) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_digits_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_digits_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    // about four CTAs per SM over the whole batch, and enough digits per CTA to pay for walking the counters
+    size_t per_msm = ((size_t)ctx->sm_count * 4 + P.count - 1) / P.count;
+    dchunk = (P.n + per_msm - 1) / per_msm;
+    if (dchunk < 4096) dchunk = 4096;
+    dchunk = (dchunk + kDigitsSmemThreads - 1) / kDigitsSmemThreads * kDigitsSmemThreads;
+  }
+  size_t off_cta = off_ba_scr + align(use_ba ? P.count * baM * ba_threads * 32 : 0);
+  size_t total = off_cta + align(digits_smem ? zk_div_up(P.n, dchunk) * P.count * P.nb * 4 : 0);
   ZK_TRY(zk_scratch_reserve(ctx, ctx->msm_work, total));
   char* w = (char*)ctx->msm_work.p;
   uint32_t* counts = (uint32_t*)(w + off_cnt);
   uint32_t* starts = (uint32_t*)(w + off_st);
   uint32_t* entries = (uint32_t*)(w + off_ent);
+  uint32_t* cta_base = (uint32_t*)(w + off_cta);
   uint4* buckets = (uint4*)(w + off_bk);
   uint4* r1 = (uint4*)(w + off_r1);
   uint4* r2 = (uint4*)(w + off_r2);
 
   ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, cnt_bytes, ctx->stream));
-  dim3 gd(zk_div_up(P.n, 256), (unsigned)P.count);
+  auto launch_digits = [&](bool scatter, size_t lo, size_t hi) -> int {
+    if (digits_smem) {
+      dim3 g(zk_div_up(hi - lo, dchunk), (unsigned)P.count);
+      if (scatter) {
+        ZK_LAUNCH(ctx, "msm_digits_scatter", k_msm_digits_smem<true>, g, kDigitsSmemThreads, dsm, (const uint4*)d_scalars, P, counts,
+                  (const uint32_t*)starts, entries, lo, hi, dchunk, cta_base);
+      } else {
+        ZK_LAUNCH(ctx, "msm_digits_hist", k_msm_digits_smem<false>, g, kDigitsSmemThreads, dsm, (const uint4*)d_scalars, P, counts,
+                  (const uint32_t*)nullptr, (uint32_t*)nullptr, lo, hi, dchunk, cta_base);
+      }
+    } else {
+      dim3 g(zk_div_up(hi - lo, 256), (unsigned)P.count);
+      if (scatter) {
+        ZK_LAUNCH(ctx, "msm_digits_scatter", k_msm_digits<true>, g, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)starts,
+                  entries, lo, hi);
+      } else {
+        ZK_LAUNCH(ctx, "msm_digits_hist", k_msm_digits<false>, g, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)nullptr,
+                  (uint32_t*)nullptr, lo, hi);
+      }
+    }
+    return ZK_OK;
+  };
   if (host_scalars && P.count == 1 && P.n >= 4096) {
     ZK_TRY(zk_copy_stream(ctx));
-    const size_t chunks = 4, per = (P.n + chunks - 1) / chunks;
+    const size_t chunks = 4;
+    size_t per = (P.n + chunks - 1) / chunks;
+    if (digits_smem) per = (per + dchunk - 1) / dchunk * dchunk;      // pieces start on chunk boundaries
     for (size_t c = 0; c < chunks; c++) {
       size_t lo = c * per, hi = lo + per < P.n ? lo + per : P.n;
       if (lo >= hi) break;
@@ -675,18 +773,15 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
                                    cudaMemcpyHostToDevice, ctx->copy_stream));
       ZK_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->copy_stream));
       ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_event, 0));
-      ZK_LAUNCH(ctx, "msm_digits_hist", k_msm_digits<false>, zk_div_up(hi - lo, 256), 256, 0, (const uint4*)d_scalars, P, counts,
-                (const uint32_t*)nullptr, (uint32_t*)nullptr, lo, hi);
+      ZK_TRY(launch_digits(false, lo, hi));
     }
   } else {
     if (host_scalars)
       ZK_CUDA(ctx, cudaMemcpyAsync((void*)d_scalars, host_scalars, P.count * P.n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZK_LAUNCH(ctx, "msm_digits_hist", k_msm_digits<false>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)nullptr,
-              (uint32_t*)nullptr, (size_t)0, P.n);
+    ZK_TRY(launch_digits(false, 0, P.n));
   }
   ZK_LAUNCH(ctx, "msm_scan", k_msm_scan, (unsigned)P.count, 1024, 0, counts, starts, P.nb);
-  ZK_LAUNCH(ctx, "msm_digits_scatter", k_msm_digits<true>, gd, 256, 0, (const uint4*)d_scalars, P, counts, (const uint32_t*)starts, entries,
-            (size_t)0, P.n);
+  ZK_TRY(launch_digits(true, 0, P.n));
   ZK_CUDA(ctx, cudaMemsetAsync(buckets, 0, bucket_bytes, ctx->stream));     // identity everywhere
   {
     uint32_t* ida = (uint32_t*)(w + off_sa_id); uint4* pta = (uint4*)(w + off_sa_pt);
