@@ -142,7 +142,7 @@ def test_best_multiexp_edge_cases(ctx, orc):
         zk.best_multiexp(sc[:5], bases[:6], ctx)
 
 
-@pytest.mark.parametrize("k,pre", [(8, True), (8, False), (12, True), (14, True), (15, False)])
+@pytest.mark.parametrize("k,pre", [(8, True), (8, False), (12, True), (14, True), (15, False), (16, True)])
 def test_params_commit_vs_oracle(ctx, orc, k, pre):
     n = 1 << k
     g, gl = orc.gen_points(100 + k, n), orc.gen_points(200 + k, n)

@@ -691,11 +691,16 @@ uint32_t table_window_bits(uint32_t k) {
   int c = (int)k - 3;
   if (c < 4) c = 4;
   if (c > 16) c = 16;
-  // W = floor(254/c) + 1 moves in steps: one more bit can remove two windows (c = 14 -> 15: 19 -> 17).  Take it when the
-  // modelled work (10 multiplications per bucket addition, c/2 * 14 per bucket in the reduction) drops by > 3 %
-  // (measured: k = 17 complete proof 53.0 -> 50.6 ms; k = 16, 18, 19 within 1 % either way).
-  auto work = [&](int cc) { return (double)(254 / cc + 1) * (double)((size_t)1 << k) * 10.0 + (double)((size_t)1 << (cc - 1)) * cc * 7.0; };
-  if (c < 16 && work(c + 1) < 0.97 * work(c)) c++;
+  if (k < 14) return (uint32_t)c;
+  // W = floor(254/c) + 1 moves in steps (c = 14 -> 15: 19 -> 17 windows).  Modelled work: 10 multiplications per bucket
+  // addition, and per bucket ~2.1 additions in the row / column reduction plus ~3 for merging the partial sums of the
+  // chunked accumulation (14 multiplications each).  The smallest c within 3 % of the minimum over [k - 3, 16] is taken.
+  // Measured complete proofs (B200, ms): k = 16: c = 13 / 14 / 15: 27.6 / 26.8 / 25.7;  k = 17: 14 / 15 / 16: 42.7 / 40.2 / 41.2;
+  // k = 18: 15 / 16: 71.4 / 70.8 -- the model picks 15, 15, 16 (and 16 from k = 19 on, the cap of the shared-memory digit sort).
+  auto work = [&](int cc) { return (double)(254 / cc + 1) * (double)((size_t)1 << k) * 10.0 + (double)((size_t)1 << (cc - 1)) * 5.1 * 14.0; };
+  double best = work(c);
+  for (int cc = c + 1; cc <= 16; cc++) best = std::min(best, work(cc));
+  while (c < 16 && work(c) > 1.03 * best) c++;
   return (uint32_t)c;
 }
 
