@@ -770,14 +770,14 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   const bool digits_smem = !digits_global && dsm <= 200 * 1024 && P.n >= 8192;
   size_t dchunk = 0;
   if (digits_smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_digits_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_digits_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
-    // about four CTAs per SM over the whole batch, and enough digits per CTA to pay for walking the counters
-    size_t per_msm = ((size_t)ctx->sm_count * 4 + P.count - 1) / P.count;
+    // per device, so not cached in a static (a process may hold contexts on several GPUs)
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_digits_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_digits_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // one CTA is resident per SM (the counters fill its shared memory).  CTAs per SM over the whole batch, measured on the
+    // complete proof (scatter ms per proof): 1: 8.6, 2: 6.9, 4: 5.2, 8: 3.7, 12: 3.3, 16-32: 3.3 -- short chunks balance the
+    // SMs and keep the CTAs' reserved ranges of a bucket close in time; below 4096 scalars walking the counters dominates
+    static const size_t waves = getenv("ZK_MSM_DIGIT_CTAS") ? (size_t)atoi(getenv("ZK_MSM_DIGIT_CTAS")) : 12;
+    size_t per_msm = ((size_t)ctx->sm_count * waves + P.count - 1) / P.count;
     dchunk = (P.n + per_msm - 1) / per_msm;
     if (dchunk < 4096) dchunk = 4096;
     dchunk = (dchunk + kDigitsSmemThreads - 1) / kDigitsSmemThreads * kDigitsSmemThreads;
