@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=3, help="1 = one stream, 3 = commitments on two streams + NTT/h(X) on a third")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-max", type=int, default=24)
+    ap.add_argument("--sweep-classes", action="store_true",
+                    help="sweep mode: also time the resident MSM on 88-bit scalars and on 90 %% zero / small scalars (SURVEY 8d config 3)")
     ap.add_argument("--inflight", type=int, default=2, help="proof mode: also measure throughput with this many proofs in flight per GPU")
     return ap.parse_args()
 
@@ -994,6 +996,33 @@ def sweep(args, zk, torch, dev, local_rank):
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             res[name + "_ms"] = ms; res[name + "_Gpts_s"] = n / (ms * 1e-3) / 1e9
+        if args.sweep_classes and k <= 24:
+            # canonical values built on the host, converted to Montgomery form by the library
+            rng = np.random.default_rng(0x5CA1A4 + k)
+            for cname in ("bits88", "small90"):
+                raw = np.zeros((n, 4), dtype=np.uint64)
+                if cname == "bits88":
+                    raw[:, 0] = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+                    raw[:, 1] = rng.integers(0, 2**24, size=n, dtype=np.uint64)
+                else:
+                    kind = rng.integers(0, 10, size=n)
+                    raw[:, 0] = np.where(kind < 5, 0, rng.integers(0, 256, size=n)).astype(np.uint64)   # 50 % zeros, 40 % bytes
+                    big = kind == 9                                                                      # 10 % full width
+                    raw[big] = rand_fr_host(rng, int(big.sum()))
+                mont = ctx.field_op("fr", "to_mont", np.ascontiguousarray(raw))
+                sc_c = torch.from_numpy(mont.view(np.int64)).to(dev)
+                fn = lambda: h2.commit_dev(params, sc_c.data_ptr(), 1, out.data_ptr(), lagrange=True)
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); e0.record()
+                for _ in range(5):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                res["msm_resident_%s_ms" % cname] = ms
+                res["msm_resident_%s_Gpts_s" % cname] = n / (ms * 1e-3) / 1e9
+                del sc_c
         omega = zk.fr_to_limbs(pow(root, 1 << (28 - k), R_MOD))
         a = rand_fr(torch, n, dev, gen)
         for _ in range(3):
