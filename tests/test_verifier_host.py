@@ -104,3 +104,18 @@ def test_random_satisfied_circuits_are_accepted_by_both_verifiers(seed):
         adv = [a.copy() for a in case["advice"]]
         adv[pcols[c][1]][r, 0] ^= np.uint64(1)
         assert rejected(adv)
+
+
+@pytest.mark.parametrize("seed", [211, 212, 213])
+def test_random_satisfied_circuits_with_the_evm_transcript(seed):
+    """the same random circuits through the Keccak / EVM transcript: both verifiers accept, neither accepts the proof
+    under the other transcript"""
+    case = pc.random_satisfied_case(seed)
+    k = case["k"]
+    pk = pc.oracle_key(case)
+    proof = op.create_proof(orc, pc.params_for(k), pk, case["circ"], case["advice"], case["instances_int"], case["randoms"],
+                            transcript=op.EvmWrite())
+    assert ov.verify_proof(pc.verifier_params(), pk["vk"], case["cs"], k, case["instances_int"], proof, transcript="evm")
+    assert native_verify(case, pk, case["instances_limbs"], proof, transcript="evm")
+    assert not native_verify(case, pk, case["instances_limbs"], proof, transcript="blake2b")
+    assert not native_verify(case, pk, case["instances_limbs"], proof[:-1], transcript="evm")
