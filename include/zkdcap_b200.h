@@ -112,6 +112,16 @@ int zk_g1_fixed_base_mul_dev(zk_ctx* ctx, const zk_g1_affine* base, const zk_fr*
  * against the SRS that `src` keeps resident; `src` must outlive `dst`'s use. */
 int zk_ctx_share_srs(zk_ctx* dst, const zk_ctx* src);
 
+/* Window width c and window count W of the resident table of base set `which` (ZK_BASES_G / ZK_BASES_G_LAGRANGE);
+ * both 0 when the SRS was uploaded without precompute_windows.  Lets callers and tests see which Pippenger
+ * configuration a commitment of this SRS runs. */
+int zk_srs_window(zk_ctx* ctx, int which, uint32_t* c_out, uint32_t* w_out);
+
+/* Work counters kept on the device: out[0] = bucket entries (non-zero signed digits, i.e. the group additions the
+ * bucket accumulation performs), out[1] = MSMs, out[2..3] reserved; since context creation or the last reset.
+ * Synchronises the context stream.  Measurement only (bench.py's integer-pipe roofline of msm_accumulate). */
+int zk_ctx_counters(zk_ctx* ctx, uint64_t out[4], int reset);
+
 /* ParamsKZG::read / write (poly/kzg/commitment.rs; halo2-base gen_srs keeps params/kzg_bn254_{k}.srs):
  *   k (u32 LE) | n compressed g | n compressed g_lagrange | g2 (64 B) | s_g2 (64 B)
  * zk_params_read decompresses the 2n points on the device (one square root in Fq each) and keeps them resident

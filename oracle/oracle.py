@@ -227,6 +227,15 @@ def gen_points(seed, n, threads=None):
     return out
 
 
+def setup_params(k, s, threads=None):
+    """ParamsKZG::setup with the known trapdoor `s` (canonical int) -> (g, g_lagrange), (n, 8) affine arrays"""
+    n = 1 << k
+    g, gl = np.empty((n, 8), dtype=np.uint64), np.empty((n, 8), dtype=np.uint64)
+    raw = np.array([(s >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+    lib().orc_setup_params(C.c_uint32(k), _p(raw), C.c_int(threads or cpu_threads()), _p(g), _p(gl))
+    return g, gl
+
+
 def evaluate_h(desc_struct, fixed_cosets, perm_cosets, l0, l_last, l_active,
                advice, instance, challenges, y, beta, gamma, theta, lookup_polys, perm_products,
                ext_n, threads=None):

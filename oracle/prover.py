@@ -382,6 +382,13 @@ def create_proof(orc, params, pk, circ, advice_values, instances, randoms, trans
     commit_c = lambda v: aff(orc.best_multiexp(v, params["g"][:len(v)], threads))
     ev = lambda poly, x: I(orc.eval_polynomial(poly, L(x)))
     note = (lambda name, v: trace.__setitem__(name, v)) if trace is not None else (lambda name, v: None)
+    import time as _time
+    _t = [_time.perf_counter()]
+
+    def section(name):                                                # wall-clock per prover section (bench.py's reference arm)
+        now = _time.perf_counter()
+        note("t_" + name, now - _t[0])
+        _t[0] = now
 
     tr.common_scalar(pk["transcript_repr"])                          # vk.hash_into
     assert len(instances) == cs.num_instance_columns
@@ -407,6 +414,7 @@ def create_proof(orc, params, pk, circ, advice_values, instances, randoms, trans
     challenges = [tr.squeeze_challenge() for _ in range(cs.num_challenges)]
     ch_l = pm.to_mont_limbs(challenges, R) if challenges else []
     theta = tr.squeeze_challenge()
+    section("advice_commitments_s")
 
     # lookups: commit_permuted
     usable = n - (bf + 1)
@@ -424,6 +432,7 @@ def create_proof(orc, params, pk, circ, advice_values, instances, randoms, trans
         lk.append({"cin": cin, "ctab": ctab, "pin": pin, "ptab": ptab, "pin_poly": pin_poly, "ptab_poly": ptab_poly})
     beta = tr.squeeze_challenge()
     gamma = tr.squeeze_challenge()
+    section("lookup_permuted_s")
 
     # permutation.commit
     chunk = d - 2
@@ -442,6 +451,7 @@ def create_proof(orc, params, pk, circ, advice_values, instances, randoms, trans
         z_polys.append(dom.lagrange_to_coeff(z))
         tr.write_point(zc)
 
+    section("permutation_product_s")
     # lookups: commit_product
     for e in lk:
         z = orc.lookup_product(k, e["cin"], e["ctab"], e["pin"], e["ptab"], L(beta), L(gamma))
@@ -451,6 +461,7 @@ def create_proof(orc, params, pk, circ, advice_values, instances, randoms, trans
         e["z_poly"] = dom.lagrange_to_coeff(z)
         tr.write_point(zc)
 
+    section("lookup_product_s")
     # vanishing.commit: random polynomial of degree n - 1 [UPSTREAM? SURVEY.md A.10 (2)]
     random_poly = rng.take(n).copy()
     rng.take(1)
@@ -462,7 +473,9 @@ def create_proof(orc, params, pk, circ, advice_values, instances, randoms, trans
     h = orc.evaluate_h(circ.desc, pk["fixed_cosets"], pk["sigma_cosets"], pk["l0"], pk["l_last"], pk["l_active_row"],
                        advice_polys, instance_polys, ch_l, L(y), L(beta), L(gamma), L(theta), flat_lookup, z_polys,
                        dom.ext_n, threads)
-    note("h_ext", h)
+    if trace is not None and trace.get("keep_h_ext", True):
+        note("h_ext", h)
+    section("evaluate_h_with_transforms_s")
     # vanishing.construct
     hc = dom.extended_to_coeff(dom.divide_by_vanishing_poly(h))
     pieces = [np.ascontiguousarray(hc[i * n:(i + 1) * n]) for i in range(hc.shape[0] // n)]
@@ -471,6 +484,7 @@ def create_proof(orc, params, pk, circ, advice_values, instances, randoms, trans
         tr.write_point(commit_c(p))
     x = tr.squeeze_challenge()
     xn = pow(x, n, R)
+    section("quotient_commitments_s")
 
     rot = lambda r: rotate_omega(k, x, r)
     advice_evals = [ev(advice_polys[c], rot(r)) for c, r in cs.advice_queries]
@@ -505,6 +519,7 @@ def create_proof(orc, params, pk, circ, advice_values, instances, randoms, trans
         for v in e["evals"]:
             tr.write_scalar(v)
 
+    section("evaluations_s")
     # queries, in create_proof's order
     polys, queries = [], []
 
@@ -533,6 +548,7 @@ def create_proof(orc, params, pk, circ, advice_values, instances, randoms, trans
     q(h_poly, x, ev(h_poly, x)); q(random_poly, x, random_eval)
 
     shplonk_create_proof(orc, params, tr, polys, queries, n, threads, commit_c)
+    section("shplonk_s")
     assert rng.pos == randoms_needed(cs, k), (rng.pos, randoms_needed(cs, k))
     return tr.finalize()
 

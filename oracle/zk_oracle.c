@@ -771,5 +771,69 @@ void orc_gen_points(u64 seed, size_t n, int threads, zk_g1_affine* out) {
   parallel_for(n, threads, genp_fn, &j);
 }
 
+
+/* ------------------------------------------------------------------------ */
+/* ParamsKZG::setup with a KNOWN trapdoor (test / benchmark SRS; [UPSTREAM]   */
+/* poly/kzg/commitment.rs: g[i] = s^i G, g_lagrange[i] = L_i(s) G with       */
+/* L_i(s) = (s^n - 1)/n * w^i / (s - w^i)).  Fixed-base comb:  */
+/* table T[j][d] = d * 2^(8j) * G, 32 mixed additions per point.             */
+typedef struct { const fr* sc; const g1a* table; zk_g1_affine* out; } fbm_job;
+static void fbm_fn(size_t lo, size_t hi, int tid, void* arg) {
+  (void)tid; fbm_job* j = (fbm_job*)arg;
+  enum { CH = 256 };
+  g1j acc[CH]; fq zs[CH];
+  for (size_t b = lo; b < hi; b += CH) {
+    size_t m = hi - b < CH ? hi - b : CH;
+    for (size_t i = 0; i < m; i++) {
+      u64 e[4]; fr_to_raw(j->sc[b + i], e);
+      g1j a = g1j_identity();
+      for (int w = 0; w < 32; w++) {
+        unsigned d = (unsigned)((e[w / 8] >> (8 * (w % 8))) & 0xff);
+        if (d) a = g1j_add_mixed(&a, &j->table[w * 256 + d]);
+      }
+      acc[i] = a; zs[i] = g1j_is_identity(&a) ? fq_R1 : a.z;
+    }
+    fq_batch_invert(zs, m);
+    for (size_t i = 0; i < m; i++) {
+      g1a r;
+      if (g1j_is_identity(&acc[i])) { r.x = fq_ZERO_; r.y = fq_ZERO_; }
+      else { fq zi2 = fq_sqr(zs[i]); r.x = fq_mul(acc[i].x, zi2); r.y = fq_mul(acc[i].y, fq_mul(zi2, zs[i])); }
+      memcpy(&j->out[b + i], &r, 64);
+    }
+  }
+}
+static void fixed_base_batch(const g1a* base, const fr* sc, size_t n, int threads, zk_g1_affine* out) {
+  g1a* table = (g1a*)malloc(sizeof(g1a) * 32 * 256);
+  g1j row = g1a_to_j(base);
+  for (int w = 0; w < 32; w++) {
+    g1j cur = g1j_identity();
+    for (int d = 1; d < 256; d++) { cur = g1j_add(&cur, &row); table[w * 256 + d] = g1j_to_affine(&cur); }
+    table[w * 256].x = fq_ZERO_; table[w * 256].y = fq_ZERO_;
+    for (int t = 0; t < 8; t++) row = g1j_double(&row);
+  }
+  fbm_job j = {sc, table, out};
+  parallel_for(n, threads, fbm_fn, &j);
+  free(table);
+}
+/* s_raw: the trapdoor as a canonical little-endian integer */
+void orc_setup_params(uint32_t k, const u64 s_raw[4], int threads, zk_g1_affine* g, zk_g1_affine* g_lagrange) {
+  ensure_init();
+  size_t n = (size_t)1 << k;
+  fr s = fr_from_raw(s_raw);
+  fr w = FR_ROOT_OF_UNITY;
+  for (uint32_t i = k; i < 28; i++) w = fr_sqr(w);
+  fr* sp = (fr*)malloc(n * 32); fr* li = (fr*)malloc(n * 32); fr* den = (fr*)malloc(n * 32);
+  fr cur = fr_R1, wp = fr_R1;
+  for (size_t i = 0; i < n; i++) { sp[i] = cur; li[i] = wp; den[i] = fr_sub(s, wp); cur = fr_mul(cur, s); wp = fr_mul(wp, w); }
+  /* cur = s^n now */
+  fr num = fr_mul(fr_sub(cur, fr_R1), fr_inv(fr_from_u64((u64)n)));
+  fr_batch_invert(den, n);
+  for (size_t i = 0; i < n; i++) li[i] = fr_mul(fr_mul(num, li[i]), den[i]);
+  g1a gen; gen.x = fq_from_u64(1); gen.y = fq_from_u64(2);
+  fixed_base_batch(&gen, sp, n, threads, g);
+  fixed_base_batch(&gen, li, n, threads, g_lagrange);
+  free(sp); free(li); free(den);
+}
+
 /* prover tail: lookup / permutation products, kate division (test infrastructure) */
 #include "prover_tail.inc.h"

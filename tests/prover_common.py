@@ -26,8 +26,11 @@ _cache = {}
 
 
 def params_for(k):
+    """ParamsKZG::setup with the tests' trapdoor: the C oracle's fixed-base comb (checked against the plain
+    double-and-add loop op.setup_params in tests/test_prover_oracle.py)."""
     if ("params", k) not in _cache:
-        _cache[("params", k)] = op.setup_params(orc, k, TRAPDOOR)
+        g, gl = orc.setup_params(k, TRAPDOOR)
+        _cache[("params", k)] = {"k": k, "n": 1 << k, "g": g, "g_lagrange": gl, "s": TRAPDOOR}
     return _cache[("params", k)]
 
 

@@ -1,0 +1,177 @@
+"""GPU parity at the PRODUCTION configuration (the sizes and window widths bench.py runs), bit-exact against the CPU
+oracle's best_multiexp / create_proof:
+
+  * resident-table MSM at k = 18, 19, 20 (window c = 16: 128 KB shared-memory digit sort, 128 x 256 row / column bucket
+    reduction) on the three scalar classes of SURVEY 8d config 3, singly and as one batch of 4
+    (BASELINE configs[2] "bit-exact vs halo2 best_multiexp"; reference call site circuits/src/sgx_dcap_verifier.rs:814-822);
+  * the same c = 16 code paths forced on small inputs (k = 13..16) through ZK_MSM_C;
+  * complete proofs, BYTES equal to the CPU prover's, on the QE3 shape at k = 13 and 15;
+  * group mode (zk_group) with a group of one GPU: bytes equal to the ungrouped proof.
+"""
+import contextlib
+import os
+import random
+
+import numpy as np
+import pytest
+
+import zkdcap_b200 as zk
+from oracle import pymodel as pm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return zk.Context(0)
+
+
+def affine(orc, g1):
+    return orc.g1_to_affine(np.asarray(g1).reshape(-1, 12))
+
+
+@contextlib.contextmanager
+def env(**kv):
+    old = {k: os.environ.get(k) for k in kv}
+    os.environ.update({k: str(v) for k, v in kv.items()})
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def scalar_classes(orc, n, seed):
+    """(i) uniform, (ii) 88-bit bounded, (iii) 90 % zeros / small (< 2^8) + 10 % full width"""
+    rng = np.random.default_rng(seed)
+    uniform = orc.gen_scalars(seed, n)
+    raw = np.zeros((n, 4), dtype=np.uint64)
+    raw[:, 0] = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    raw[:, 1] = rng.integers(0, 2**24, size=n, dtype=np.uint64)
+    bits88 = orc.field_op("fr", "from_raw", raw)
+    kind = rng.integers(0, 10, size=n)
+    raw = np.zeros((n, 4), dtype=np.uint64)
+    raw[:, 0] = np.where(kind < 5, 0, rng.integers(0, 256, size=n)).astype(np.uint64)
+    small = orc.field_op("fr", "from_raw", raw)
+    big = kind == 9
+    small[big] = orc.gen_scalars(seed + 1, int(big.sum()))
+    return {"uniform": uniform, "bits88": bits88, "small90": small, "uniform2": orc.gen_scalars(seed + 2, n)}
+
+
+def commit_batch(ctx, n, cols, which=2):
+    import ctypes as C
+    lib = ctx.lib
+    cnt = len(cols)
+    flat = np.ascontiguousarray(np.stack(cols)).reshape(cnt * n, 4)
+    d_s, d_o = C.c_void_p(), C.c_void_p()
+    ctx.check(lib.zk_dev_alloc(ctx.h, flat.nbytes, C.byref(d_s)))
+    ctx.check(lib.zk_dev_alloc(ctx.h, cnt * 96, C.byref(d_o)))
+    ctx.check(lib.zk_h2d(ctx.h, d_s, flat.ctypes.data_as(C.c_void_p), flat.nbytes))
+    ctx.check(lib.zk_msm_batch_dev(ctx.h, d_s, which, n, cnt, d_o))
+    out = np.empty((cnt, 12), dtype=np.uint64)
+    ctx.check(lib.zk_d2h(ctx.h, out.ctypes.data_as(C.c_void_p), d_o, out.nbytes))
+    ctx.check(lib.zk_dev_free(ctx.h, d_s)); ctx.check(lib.zk_dev_free(ctx.h, d_o))
+    return out
+
+
+def window_bits(ctx, which=2):
+    import ctypes as C
+    c, w = C.c_uint32(), C.c_uint32()
+    ctx.check(ctx.lib.zk_srs_window(ctx.h, which, C.byref(c), C.byref(w)))
+    return c.value, w.value
+
+
+@pytest.mark.parametrize("k", [18, 19, 20])
+def test_resident_msm_production_window(ctx, orc, k):
+    n = 1 << k
+    g = orc.gen_points(0x5CA1A4 + k, n)
+    params = zk.ParamsKZG(k, g, g, ctx, precompute=True)
+    c, W = window_bits(ctx)
+    assert c == 16 and W == 16, "bench sizes run the c = 16 window table"
+    cls = scalar_classes(orc, n, 0x5CA1A4 + k)
+    names = list(cls)
+    want = {nm: affine(orc, orc.best_multiexp(cls[nm], g)) for nm in names}
+    for nm in names[:3]:                                                   # singly (count = 1 plan, host-pointer call)
+        assert np.array_equal(affine(orc, params.commit_lagrange(cls[nm])), want[nm]), nm
+    got = commit_batch(ctx, n, [cls[nm] for nm in names])                  # one batch of 4 resident columns
+    for i, nm in enumerate(names):
+        assert np.array_equal(affine(orc, got[i]), want[nm]), "batch column %s" % nm
+    m = n - 12345                                                          # a shorter polynomial on the same table
+    assert np.array_equal(affine(orc, params.commit(cls["uniform"][:m])), affine(orc, orc.best_multiexp(cls["uniform"][:m], g[:m])))
+    del params
+
+
+@pytest.mark.parametrize("k", [13, 14, 15, 16])
+def test_window16_forced_on_small_inputs(ctx, orc, k):
+    """ZK_MSM_C=16 makes k = 13..16 take the code path of the bench sizes: 2^15 counters in shared memory, nR = 128,
+    nC = 256, W = 16 table rows."""
+    n = 1 << k
+    g = orc.gen_points(0xC16 + k, n)
+    g[5] = g[4]
+    with env(ZK_MSM_C=16):
+        params = zk.ParamsKZG(k, g, g, ctx, precompute=True)
+    assert window_bits(ctx) == (16, 16)
+    cls = scalar_classes(orc, n, 0xC16 + k)
+    cls["ones"] = pm.to_mont_limbs([1] * n, pm.R_MOD)
+    cls["top"] = pm.to_mont_limbs([pm.R_MOD - 1 - i for i in range(n)], pm.R_MOD)
+    names = list(cls)
+    want = {nm: affine(orc, orc.best_multiexp(cls[nm], g)) for nm in names}
+    for nm in names:
+        assert np.array_equal(affine(orc, params.commit_lagrange(cls[nm])), want[nm]), nm
+    got = commit_batch(ctx, n, [cls[nm] for nm in names])
+    for i, nm in enumerate(names):
+        assert np.array_equal(affine(orc, got[i]), want[nm]), "batch column %s" % nm
+    del params
+
+
+@pytest.mark.parametrize("k", [13, 15])
+def test_qe3_proof_bytes_at_larger_k(ctx, k):
+    """k = 15 reaches every multi-pass code path of the bench size: two-pass NTTs (2^15, 2^17 extended), chunked digit
+    sort, partial-slot levels, the 8-bit radix sort over > 2^13 rows."""
+    from oracle import oracle as orc
+    from oracle import prover as op
+    from oracle import verifier as ov
+    from tests import prover_common as pc
+    case = pc.make_case("qe3", k, 5)
+    p = pc.params_for(k)
+    params = zk.ParamsKZG(k, p["g"], p["g_lagrange"], ctx, precompute=True)
+    key = zk.ProverKey(params, case["circ"], case["fixed"], case["mapping"])
+    opk = op.keygen(orc, p, case["circ"], case["fixed"], case["mapping"], case["circ"].transcript_repr)
+    fc, pcm = key.vk_commitments()
+    assert pm.limbs_to_affine(fc) == opk["vk"]["fixed_commitments"]
+    assert pm.limbs_to_affine(pcm) == opk["vk"]["permutation_commitments"]
+    want = op.create_proof(orc, p, opk, case["circ"], case["advice"], case["instances_int"], case["randoms"])
+    got = key.create_proof(case["advice"], case["instances_limbs"], case["randoms"])
+    assert got == want
+    assert ov.verify_proof(pc.verifier_params(), opk["vk"], case["cs"], k, case["instances_int"], got)
+
+
+@pytest.mark.parametrize("shape,k", [("toy", 6), ("qe3", 11)])
+def test_group_of_one_gives_the_same_bytes(ctx, shape, k):
+    """zk_group with world = 1: every sharding branch of csrc/prover.cu / group.cu runs (shard plans, NCCL all-gathers
+    of one rank, row exchange) and the proof bytes must not change."""
+    import torch  # noqa: F401  (loads the libnccl.so.2 the library binds at run time)
+    from oracle import oracle as orc
+    from oracle import prover as op
+    from tests import prover_common as pc
+    case = pc.make_case(shape, k, 7)
+    p = pc.params_for(k)
+    params = zk.ParamsKZG(k, p["g"], p["g_lagrange"], ctx, precompute=True)
+    key = zk.ProverKey(params, case["circ"], case["fixed"], case["mapping"])
+    plain = key.create_proof(case["advice"], case["instances_limbs"], case["randoms"])
+    try:
+        uid = zk.Group.unique_id()
+    except zk.ZkError:
+        pytest.skip("NCCL not loadable")
+    grp = zk.Group(ctx, 0, 1, uid)
+    key.set_group(grp)
+    grouped = key.create_proof(case["advice"], case["instances_limbs"], case["randoms"])
+    key.set_group(None)
+    again = key.create_proof(case["advice"], case["instances_limbs"], case["randoms"])
+    grp.close()
+    assert grouped == plain and again == plain
+    opk = op.keygen(orc, p, case["circ"], case["fixed"], case["mapping"], case["circ"].transcript_repr)
+    assert plain == op.create_proof(orc, p, opk, case["circ"], case["advice"], case["instances_int"], case["randoms"])

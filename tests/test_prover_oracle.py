@@ -146,3 +146,11 @@ def test_golden_proof_point_encoding_v04():
         pt = tuple(int(v, 16) for v in xy)
         assert op.decompress_point_v04(chunks[int(i)]) == pt and op.compress_point_v04(pt) == chunks[int(i)]
     assert op.decompress_point_v04(op.compress_point_v04(None)) is None
+
+
+def test_fast_setup_matches_the_plain_loop():
+    """orc.setup_params (fixed-base comb in C) against op.setup_params (one double-and-add product per point)"""
+    for k in (3, 6):
+        slow = op.setup_params(orc, k, pc.TRAPDOOR)
+        g, gl = orc.setup_params(k, pc.TRAPDOOR)
+        assert np.array_equal(g, slow["g"]) and np.array_equal(gl, slow["g_lagrange"])

@@ -79,7 +79,7 @@ SYMBOLS = [
     "zk_ctx_create", "zk_ctx_destroy", "zk_last_error", "zk_ctx_sync", "zk_version",
     "zk_ctx_timing", "zk_ctx_timing_reset", "zk_ctx_timing_read", "zk_ctx_launch_count",
     "zk_dev_alloc", "zk_dev_free", "zk_h2d", "zk_d2h",
-    "zk_srs_upload", "zk_srs_upload_dev", "zk_g1_fixed_base_mul_dev", "zk_ctx_share_srs",
+    "zk_srs_upload", "zk_srs_upload_dev", "zk_g1_fixed_base_mul_dev", "zk_ctx_share_srs", "zk_srs_window", "zk_ctx_counters",
     "zk_params_read", "zk_params_write", "zk_g1_compress", "zk_g1_decompress",
     "zk_g1_encode", "zk_g1_decode", "zk_params_read_format", "zk_params_write_format",
     "zk_msm", "zk_msm_dev", "zk_msm_batch_dev", "zk_g1_sum", "zk_g1_sum_dev",
@@ -129,6 +129,8 @@ def load():
         "zk_srs_upload_dev": (i32, [vp, u32, vp, vp, i32]),
         "zk_g1_fixed_base_mul_dev": (i32, [vp, vp, vp, sz, vp]),
         "zk_ctx_share_srs": (i32, [vp, vp]),
+        "zk_srs_window": (i32, [vp, i32, C.POINTER(u32), C.POINTER(u32)]),
+        "zk_ctx_counters": (i32, [vp, C.POINTER(C.c_uint64), i32]),
         "zk_params_read": (i32, [vp, vp, sz, i32, C.POINTER(u32), vp, vp]),
         "zk_params_write": (i32, [vp, vp, vp, vp, sz, C.POINTER(sz)]),
         "zk_g1_compress": (i32, [vp, vp, sz, vp]),

@@ -39,6 +39,7 @@ extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   free_scratch(ctx->msm_out); free_scratch(ctx->ntt_buf); free_scratch(ctx->ntt_buf2); free_scratch(ctx->misc);
   if (!ctx->srs_borrowed) { free_srs(ctx->srs_g); free_srs(ctx->srs_lagrange); }
   for (auto& t : ctx->twiddles) cudaFree(t.table);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

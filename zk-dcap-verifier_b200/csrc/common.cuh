@@ -54,6 +54,9 @@ struct zk_ctx {
   // cached twiddle tables: key = (log_n, first 8 bytes of omega...) -> device table of omega^e, e < n/2
   struct tw_entry { uint32_t log_n; zk_fr omega; void* table; };
   std::vector<tw_entry> twiddles;
+  // device-side work counters (zk_ctx_counters): [0] bucket entries = non-zero signed digits sorted into buckets, i.e. the
+  // group additions the accumulation performs, [1] MSMs
+  unsigned long long* d_counters = nullptr;
 };
 
 #define ZK_FAIL(ctx, code, ...)                                  \

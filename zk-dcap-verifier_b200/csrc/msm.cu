@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kDigitsSmemThreads, 1) k_msm_digits_smem(const
 }
 
 // exclusive scan of nb counts per MSM (one CTA per MSM), writes nb+1 offsets and clears the counts
-__global__ void __launch_bounds__(1024) k_msm_scan(uint32_t* counts, uint32_t* starts, size_t nb) {
+__global__ void __launch_bounds__(1024) k_msm_scan(uint32_t* counts, uint32_t* starts, size_t nb, unsigned long long* counters) {
   __shared__ uint32_t part[1024];
   size_t msm = blockIdx.x;
   uint32_t* cnt = counts + msm * nb;
@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(1024) k_msm_scan(uint32_t* counts, uint32_t* s
   }
   uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0;
   for (size_t b = lo; b < hi; b++) { uint32_t c = cnt[b]; st[b] = run; run += c; cnt[b] = 0; }
-  if (threadIdx.x == 1023) st[nb] = part[1023];
+  if (threadIdx.x == 1023) {
+    st[nb] = part[1023];
+    if (counters) { atomicAdd(counters, (unsigned long long)part[1023]); atomicAdd(counters + 1, 1ull); }
+  }
 }
 
 // ---- 3: bucket accumulation -------------------------------------------------------------------------
@@ -836,7 +839,11 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
       ZK_CUDA(ctx, cudaMemcpyAsync((void*)d_scalars, host_scalars, P.count * P.n * 32, cudaMemcpyHostToDevice, ctx->stream));
     ZK_TRY(launch_digits(false, 0, P.n));
   }
-  ZK_LAUNCH(ctx, "msm_scan", k_msm_scan, (unsigned)P.count, 1024, 0, counts, starts, P.nb);
+  if (!ctx->d_counters) {
+    ZK_CUDA(ctx, cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+    ZK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  }
+  ZK_LAUNCH(ctx, "msm_scan", k_msm_scan, (unsigned)P.count, 1024, 0, counts, starts, P.nb, ctx->d_counters);
   ZK_TRY(launch_digits(true, 0, P.n));
   ZK_CUDA(ctx, cudaMemsetAsync(buckets, 0, bucket_bytes, ctx->stream));     // identity everywhere
   {
@@ -848,7 +855,7 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
       uint4* opts = (uint4*)(w + off_ba_pts); uint4* scr = (uint4*)(w + off_ba_scr);
       dim3 gc(zk_div_up(P.nb, 256), (unsigned)P.count);
       ZK_LAUNCH(ctx, "msm_pair_counts", k_pair_counts, gc, 256, 0, (const uint32_t*)starts, P.nb, ocnt);
-      ZK_LAUNCH(ctx, "msm_scan", k_msm_scan, (unsigned)P.count, 1024, 0, ocnt, ost, P.nb);
+      ZK_LAUNCH(ctx, "msm_scan", k_msm_scan, (unsigned)P.count, 1024, 0, ocnt, ost, P.nb, (unsigned long long*)nullptr);
       dim3 gb(ba_grid, (unsigned)P.count);
       ZK_LAUNCH(ctx, "msm_pair_add", k_pair_add, gb, kPairThreads, 0, (const uint4*)d_points, (const uint32_t*)entries,
                 (const uint32_t*)starts, (const uint32_t*)ost, P, baM, out_cap, opts, scr);
@@ -1021,6 +1028,28 @@ extern "C" int zk_srs_upload_dev(zk_ctx* ctx, uint32_t k, const zk_g1_affine* d_
   }
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->srs_k = k; ctx->srs_n = n; ctx->srs_borrowed = false;
+  return ZK_OK;
+}
+
+// out[0] = bucket entries (non-zero signed digits = group additions of the accumulation), out[1] = MSMs run on this
+// context since creation / the last reset.  Synchronises the context stream.
+extern "C" int zk_ctx_counters(zk_ctx* ctx, uint64_t out[4], int reset) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!out) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_ctx_counters: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  memset(out, 0, 4 * sizeof(uint64_t));
+  if (!ctx->d_counters) return ZK_OK;
+  ZK_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_counters, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (reset) ZK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZK_OK;
+}
+
+extern "C" int zk_srs_window(zk_ctx* ctx, int which, uint32_t* c_out, uint32_t* w_out) {
+  if (!ctx) return ZK_ERR_ARG;
+  if (!c_out || !w_out || (which != ZK_BASES_G && which != ZK_BASES_G_LAGRANGE)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_srs_window: bad argument");
+  const zk_srs_set& s = which == ZK_BASES_G ? ctx->srs_g : ctx->srs_lagrange;
+  *c_out = s.table ? (uint32_t)s.table_c : 0u; *w_out = s.table ? (uint32_t)s.table_w : 0u;
   return ZK_OK;
 }
 

@@ -104,6 +104,12 @@ class Context:
     def launch_count(self):
         return int(self.lib.zk_ctx_launch_count(self.h))
 
+    def counters(self, reset=False):
+        """{"msm_bucket_entries": ..., "msms": ...} since creation / the last reset (device-side counters)"""
+        out = (C.c_uint64 * 4)()
+        self.check(self.lib.zk_ctx_counters(self.h, out, 1 if reset else 0))
+        return {"msm_bucket_entries": int(out[0]), "msms": int(out[1])}
+
     def bench_modmul(self, field=0, iters=2000):
         out = C.c_double()
         self.check(self.lib.zk_bench_modmul(self.h, field, iters, C.byref(out)))
