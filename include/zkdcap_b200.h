@@ -381,6 +381,12 @@ typedef struct {
   const uint8_t* s_g2;
   int transcript_kind;                          /* zk_transcript_kind the proof was written with */
 } zk_verifier_params;
+/* ParamsKZG.g2 / s_g2 between the SRS file encodings (zk_params_read* returns them as the file holds them: 64 compressed
+ * bytes for the PROCESSED formats, 128 bytes of Montgomery limbs for RAW_BYTES) and the 128 uncompressed canonical bytes
+ * zk_verify_proof consumes.  Host code (one Fq2 square root).  Errors: encodings off the curve / not canonical. */
+int zk_g2_decode(int format, const uint8_t* in, uint8_t out_uncompressed[128]);
+int zk_g2_encode(int format, const uint8_t in_uncompressed[128], uint8_t* out);
+
 /* *accepted = 1 when the proof verifies, 0 otherwise (malformed proofs are rejected, not errors). */
 int zk_verify_proof(const zk_circuit_desc* circuit, const zk_verifier_params* vp,
                     const zk_fr* const* instance_values, const uint32_t* instance_lens,

@@ -175,3 +175,35 @@ def test_group_of_one_gives_the_same_bytes(ctx, shape, k):
     assert grouped == plain and again == plain
     opk = op.keygen(orc, p, case["circ"], case["fixed"], case["mapping"], case["circ"].transcript_repr)
     assert plain == op.create_proof(orc, p, opk, case["circ"], case["advice"], case["instances_int"], case["randoms"])
+
+
+@pytest.mark.parametrize("fmt", ["processed", "raw_bytes"])
+def test_srs_file_to_verified_proof(ctx, fmt):
+    """ParamsKZG::read of a kzg_bn254_k.srs image (G1 sets AND the G2 fields), keygen, create_proof, verify_proof with
+    the file's own g2 / s_g2 (the file encodings must be decoded before they reach the verifier)."""
+    from oracle import oracle as orc
+    from oracle import prover as op
+    from tests import prover_common as pc
+    from tests.test_verifier_host import g2_bytes
+    k = 6
+    case = pc.make_case("toy", k, 9)
+    p = pc.params_for(k)
+    vp = pc.verifier_params()
+    g2f, sg2f = zk.g2_encode(g2_bytes(vp["g2"]), fmt), zk.g2_encode(g2_bytes(vp["s_g2"]), fmt)
+    if fmt == "raw_bytes":
+        body = p["g"].tobytes() + p["g_lagrange"].tobytes()
+    else:
+        body = b"".join(op.compress_point(q) for q in pm.limbs_to_affine(p["g"])) + \
+            b"".join(op.compress_point(q) for q in pm.limbs_to_affine(p["g_lagrange"]))
+    data = (k).to_bytes(4, "little") + body + g2f + sg2f
+    params = zk.ParamsKZG.read(data, ctx, fmt=fmt)
+    assert params.g2_uncompressed == g2_bytes(vp["g2"]) and params.s_g2_uncompressed == g2_bytes(vp["s_g2"])
+    key = zk.ProverKey(params, case["circ"], case["fixed"], case["mapping"])
+    proof = key.create_proof(case["advice"], case["instances_limbs"], case["randoms"])
+    fc, pcm = key.vk_commitments()
+    g1 = pm.affine_to_limbs([(1, 2)])[0]
+    assert zk.verify_proof(case["circ"], fc, pcm, g1, params.g2_uncompressed, params.s_g2_uncompressed, case["instances_limbs"], proof)
+    with pytest.raises(zk.ZkError):
+        zk.verify_proof(case["circ"], fc, pcm, g1, params.g2, params.s_g2, case["instances_limbs"], proof) if fmt != "raw_bytes" else \
+            zk.verify_proof(case["circ"], fc, pcm, g1, params.g2[:64], params.s_g2[:64], case["instances_limbs"], proof)
+    assert params.write(fmt=fmt) == data

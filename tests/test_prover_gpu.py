@@ -163,6 +163,28 @@ def test_circuit_with_permutation_only(ctx):
     assert ov.verify_proof(pc.verifier_params(), opk["vk"], cs, k, [], got)
 
 
+def test_rotations_that_wrap_onto_the_same_opening_point(ctx):
+    """at small n two rotations can be congruent mod n (here Advice(0, 1) and Advice(0, -7) at n = 8, and
+    -(bf + 1) = -6 = 2 mod 8 against the query rotation 2).  halo2 keys opening points by their field value, so the two
+    rotations share one point; the device prover used to refuse such circuits."""
+    E = zk.Expression
+    cs = zk.ConstraintSystem(num_fixed=2, num_advice=2)
+    cs.create_gate([E.Fixed(0) * (E.Advice(0, 1) - E.Advice(0, -7)), E.Fixed(0) * (E.Advice(1, 2) - E.Advice(1, 2))])
+    cs.enable_equality(0, 0)
+    cs.enable_equality(0, 1)
+    cs.enable_equality(1, 1)                 # degree 3 -> one column per permutation set -> three sets, x_last is opened
+    k = 3
+    assert (-(cs.blinding_factors() + 1)) % (1 << k) in {r % (1 << k) for _, r in cs.advice_queries}
+    fixed, advice, mapping = _random_witness_case(cs, k, 31)
+    got, opk = _both_provers(ctx, cs, k, fixed, advice, mapping, [], 31)
+    assert ov.verify_proof(pc.verifier_params(), opk["vk"], cs, k, [], got)
+    from tests.test_verifier_host import g2_bytes
+    fc = pm.affine_to_limbs(opk["vk"]["fixed_commitments"]); pcm = pm.affine_to_limbs(opk["vk"]["permutation_commitments"])
+    vp = pc.verifier_params()
+    assert zk.verify_proof(zk.Circuit(cs, k, transcript_repr=1000 + 31), fc, pcm, pm.affine_to_limbs([(1, 2)])[0], g2_bytes(vp["g2"]),
+                           g2_bytes(vp["s_g2"]), [], got)
+
+
 def test_first_phase_challenge_and_instance(ctx):
     """shapes.toy_shape(): a gate that reads a challenge and an instance column, instance column in the permutation"""
     cs = pc.shapes.toy_shape()

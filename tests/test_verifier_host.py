@@ -119,3 +119,56 @@ def test_random_satisfied_circuits_with_the_evm_transcript(seed):
     assert native_verify(case, pk, case["instances_limbs"], proof, transcript="evm")
     assert not native_verify(case, pk, case["instances_limbs"], proof, transcript="blake2b")
     assert not native_verify(case, pk, case["instances_limbs"], proof[:-1], transcript="evm")
+
+
+# ---- ParamsKZG.g2 / s_g2 encodings (csrc/verifier.cu: zk_g2_decode / zk_g2_encode) -------------------------------------------
+def _g2_compress(q, v04=False):
+    """[UPSTREAM? halo2curves G2Affine::to_bytes] x.c0 | x.c1 little-endian, parity of y.c0 in bit 7 (0.3.1) / bit 6 (>= 0.4)"""
+    b = bytearray(q[0][0].to_bytes(32, "little") + q[0][1].to_bytes(32, "little"))
+    b[63] |= (q[1][0] & 1) << (6 if v04 else 7)
+    return bytes(b)
+
+
+def test_g2_encodings_round_trip():
+    from oracle import pairing
+    rnd = random.Random(5)
+    pts = [pairing.G2_GEN, pairing.g2_mul(pc.TRAPDOOR, pairing.G2_GEN)] + [pairing.g2_mul(rnd.randrange(pm.R_MOD), pairing.G2_GEN) for _ in range(6)]
+    negs = [(q[0], ((-q[1][0]) % pm.P_MOD, (-q[1][1]) % pm.P_MOD)) for q in pts]
+    for q in pts + negs:
+        want = g2_bytes(q)
+        for fmt, v04 in (("processed", False), ("processed_v04", True)):
+            enc = _g2_compress(q, v04)
+            assert zk.g2_decode(enc, fmt) == want
+            assert zk.g2_encode(want, fmt) == enc
+        raw = b"".join(pm.to_mont_limbs([v], pm.P_MOD)[0].tobytes() for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
+        assert zk.g2_decode(raw, "raw_bytes") == want and zk.g2_encode(want, "raw_bytes") == raw
+    # x with no point on the twist, a non-canonical coordinate, wrong lengths
+    x = 5
+    bad = None
+    while bad is None:
+        cand = x.to_bytes(32, "little") + bytes(32)
+        try:
+            zk.g2_decode(cand, "processed")
+        except zk.ZkError:
+            bad = cand
+        x += 1
+    with pytest.raises(zk.ZkError):
+        zk.g2_decode(pm.P_MOD.to_bytes(32, "little") + bytes(32), "processed")
+    with pytest.raises(zk.ZkError):
+        zk.g2_decode(bytes(128), "processed")
+    with pytest.raises(zk.ZkError):
+        zk.g2_encode(bytes(127) + b"\x01", "processed")          # not on the curve
+
+
+def test_verify_proof_rejects_file_encoded_g2():
+    """the 64-byte compressed (or Montgomery-limb) g2 of an SRS file must not reach zk_verify_proof"""
+    case = pc.make_case("toy", 5, 3)
+    pk = pc.oracle_key(case)
+    proof = op.create_proof(orc, pc.params_for(5), pk, case["circ"], case["advice"], case["instances_int"], case["randoms"])
+    vp = pc.verifier_params()
+    fc = pm.affine_to_limbs(pk["vk"]["fixed_commitments"]); pcm = pm.affine_to_limbs(pk["vk"]["permutation_commitments"])
+    g1 = pm.affine_to_limbs([(1, 2)])[0]
+    c2, cs2 = _g2_compress(vp["g2"]), _g2_compress(vp["s_g2"])
+    with pytest.raises(zk.ZkError, match="128 uncompressed bytes"):
+        zk.verify_proof(case["circ"], fc, pcm, g1, c2, cs2, case["instances_limbs"], proof)
+    assert zk.verify_proof(case["circ"], fc, pcm, g1, zk.g2_decode(c2), zk.g2_decode(cs2), case["instances_limbs"], proof)

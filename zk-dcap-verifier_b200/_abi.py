@@ -92,7 +92,7 @@ SYMBOLS = [
     "zk_pk_upload", "zk_pk_destroy", "zk_pk_domain", "zk_pk_program_stats",
     "zk_evaluate_h", "zk_evaluate_h_dev",
     "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_pkey_aux_ctx", "zk_pkey_set_transcript", "zk_proof_randoms", "zk_proof_max_bytes",
-    "zk_create_proof", "zk_verify_proof",
+    "zk_create_proof", "zk_verify_proof", "zk_g2_decode", "zk_g2_encode",
     "zk_group_unique_id", "zk_group_create", "zk_group_destroy", "zk_group_rank", "zk_group_world", "zk_pkey_set_group",
     "zk_group_shard_plan",
     "zk_field_op", "zk_bench_modmul", "zk_bench_imad",
@@ -177,6 +177,8 @@ def load():
         "zk_proof_max_bytes": (sz, [vp]),
         "zk_create_proof": (i32, [vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz)]),
         "zk_verify_proof": (i32, [C.POINTER(zk_circuit_desc), C.POINTER(zk_verifier_params), vp, vp, vp, sz, C.POINTER(i32)]),
+        "zk_g2_decode": (i32, [i32, vp, vp]),
+        "zk_g2_encode": (i32, [i32, vp, vp]),
         "zk_group_unique_id": (i32, [vp]),
         "zk_group_create": (i32, [vp, u32, u32, vp, C.POINTER(vp)]),
         "zk_group_destroy": (None, [vp]),

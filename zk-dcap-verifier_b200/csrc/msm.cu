@@ -713,7 +713,12 @@ uint32_t table_window_bits(uint32_t k) {
 int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmPlan& P, void* d_out,
             const void* host_scalars = nullptr) {
   if (P.n == 0) {
-    // empty sum = identity
+    // empty sum = identity: `count` records of the form the caller expects -- XYZZ (128 B, all zero) inside the prover /
+    // group paths (ctx->msm_raw), normalised G1 (0, 1, 0) at the public ABI
+    if (ctx->msm_raw) {
+      ZK_CUDA(ctx, cudaMemsetAsync(d_out, 0, P.count * 128, ctx->stream));
+      return ZK_OK;
+    }
     std::vector<zk_g1> ids(P.count);
     memset(ids.data(), 0, ids.size() * sizeof(zk_g1));
     // Montgomery one for y
@@ -988,25 +993,47 @@ int build_table(zk_ctx* ctx, zk_srs_set& s, size_t n, uint32_t k) {
 
 }  // namespace
 
+// Both base sets (and their window tables) are built into locals and swapped into the context only when everything
+// succeeded: a failed allocation leaves the previous SRS untouched (and nothing leaked).
+static int srs_install(zk_ctx* ctx, uint32_t k, const zk_g1_affine* g, const zk_g1_affine* g_lagrange, int precompute_windows,
+                       cudaMemcpyKind kind) {
+  size_t n = (size_t)1 << k;
+  zk_srs_set fresh[2];
+  const zk_g1_affine* src[2] = {g, g_lagrange};
+  int rc = ZK_OK;
+  for (int i = 0; i < 2 && rc == ZK_OK; i++) {
+    if (cudaMalloc(&fresh[i].bases, n * 64) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->err = "zk_srs_upload: cannot allocate the base set"; rc = ZK_ERR_OOM; break;
+    }
+    if (cudaMemcpyAsync(fresh[i].bases, src[i], n * 64, kind, ctx->stream) != cudaSuccess) {
+      ctx->err = std::string("zk_srs_upload: copy: ") + cudaGetErrorString(cudaGetLastError()); rc = ZK_ERR_CUDA; break;
+    }
+    if (precompute_windows) rc = build_table(ctx, fresh[i], n, k);
+  }
+  if (rc == ZK_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->err = std::string("zk_srs_upload: ") + cudaGetErrorString(cudaGetLastError()); rc = ZK_ERR_CUDA;
+  }
+  if (rc != ZK_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& f : fresh) { if (f.bases) cudaFree(f.bases); if (f.table) cudaFree(f.table); }
+    return rc;
+  }
+  zk_srs_set* sets[2] = {&ctx->srs_g, &ctx->srs_lagrange};
+  for (int i = 0; i < 2; i++) {
+    if (!ctx->srs_borrowed) { if (sets[i]->bases) cudaFree(sets[i]->bases); if (sets[i]->table) cudaFree(sets[i]->table); }
+    *sets[i] = fresh[i];
+  }
+  ctx->srs_k = k; ctx->srs_n = n; ctx->srs_borrowed = false;
+  return ZK_OK;
+}
+
 extern "C" int zk_srs_upload(zk_ctx* ctx, uint32_t k, const zk_g1_affine* g, const zk_g1_affine* g_lagrange,
                              int precompute_windows) {
   if (!ctx) return ZK_ERR_ARG;
   if (!g || !g_lagrange || k > 27) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_srs_upload: bad argument");
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-  size_t n = (size_t)1 << k;
-  zk_srs_set* sets[2] = {&ctx->srs_g, &ctx->srs_lagrange};
-  const zk_g1_affine* src[2] = {g, g_lagrange};
-  for (int i = 0; i < 2; i++) {
-    if (!ctx->srs_borrowed && sets[i]->bases) cudaFree(sets[i]->bases);
-    if (!ctx->srs_borrowed && sets[i]->table) cudaFree(sets[i]->table);
-    *sets[i] = zk_srs_set();
-    ZK_CUDA(ctx, cudaMalloc(&sets[i]->bases, n * 64));
-    ZK_CUDA(ctx, cudaMemcpyAsync(sets[i]->bases, src[i], n * 64, cudaMemcpyHostToDevice, ctx->stream));
-    if (precompute_windows) ZK_TRY(build_table(ctx, *sets[i], n, k));
-  }
-  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->srs_k = k; ctx->srs_n = n; ctx->srs_borrowed = false;
-  return ZK_OK;
+  return srs_install(ctx, k, g, g_lagrange, precompute_windows, cudaMemcpyHostToDevice);
 }
 
 // Same as zk_srs_upload with the two base sets already in device memory (copied).
@@ -1015,20 +1042,7 @@ extern "C" int zk_srs_upload_dev(zk_ctx* ctx, uint32_t k, const zk_g1_affine* d_
   if (!ctx) return ZK_ERR_ARG;
   if (!d_g || !d_g_lagrange || k > 27) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_srs_upload_dev: bad argument");
   ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-  size_t n = (size_t)1 << k;
-  zk_srs_set* sets[2] = {&ctx->srs_g, &ctx->srs_lagrange};
-  const zk_g1_affine* src[2] = {d_g, d_g_lagrange};
-  for (int i = 0; i < 2; i++) {
-    if (!ctx->srs_borrowed && sets[i]->bases) cudaFree(sets[i]->bases);
-    if (!ctx->srs_borrowed && sets[i]->table) cudaFree(sets[i]->table);
-    *sets[i] = zk_srs_set();
-    ZK_CUDA(ctx, cudaMalloc(&sets[i]->bases, n * 64));
-    ZK_CUDA(ctx, cudaMemcpyAsync(sets[i]->bases, src[i], n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (precompute_windows) ZK_TRY(build_table(ctx, *sets[i], n, k));
-  }
-  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->srs_k = k; ctx->srs_n = n; ctx->srs_borrowed = false;
-  return ZK_OK;
+  return srs_install(ctx, k, d_g, d_g_lagrange, precompute_windows, cudaMemcpyDeviceToDevice);
 }
 
 // out[0] = bucket entries (non-zero signed digits = group additions of the accumulation), out[1] = MSMs run on this

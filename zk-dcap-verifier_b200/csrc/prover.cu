@@ -1100,12 +1100,18 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   // ---- opening points and their power tables -----------------------------------------------------------------------------------
   std::vector<int32_t> rot_of;                        // point index -> rotation
   std::vector<Fr> pt_val;
+  // Points are keyed by their field VALUE, as halo2's construct_intermediate_sets (BTreeSet of points) and the verifier do:
+  // two rotations that are congruent mod n (small circuits: -(bf + 1) or a query rotation wrapping onto another) are one
+  // opening point.
+  std::vector<int32_t> rot_seen; std::vector<uint32_t> rot_point;      // rotation -> point index (cache)
   auto point_of = [&](int32_t r) -> uint32_t {
-    for (uint32_t i = 0; i < rot_of.size(); i++) if (rot_of[i] == r) return i;
-    rot_of.push_back(r);
+    for (uint32_t i = 0; i < rot_seen.size(); i++) if (rot_seen[i] == r) return rot_point[i];
     Fr v = x * (r >= 0 ? Fr::pow_u64(K->omega, (uint64_t)r) : Fr::pow_u64(K->omega_inv, (uint64_t)(-(int64_t)r)));
-    pt_val.push_back(v);
-    return (uint32_t)rot_of.size() - 1;
+    uint32_t idx = (uint32_t)pt_val.size();
+    for (uint32_t i = 0; i < pt_val.size(); i++) if (fr_same(pt_val[i], v)) { idx = i; break; }
+    if (idx == pt_val.size()) { rot_of.push_back(r); pt_val.push_back(v); }
+    rot_seen.push_back(r); rot_point.push_back(idx);
+    return idx;
   };
   struct EvalReq { const void* poly; uint32_t point; };
   std::vector<EvalReq> reqs;
@@ -1189,8 +1195,6 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     for (uint32_t i = 0; i < ord.size(); i++) ord[i] = i;
     std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return fr_less(pt_val[a], pt_val[b]); });
     for (uint32_t i = 0; i < ord.size(); i++) pt_rank[ord[i]] = i;
-    for (uint32_t i = 0; i + 1 < ord.size(); i++)
-      if (fr_same(pt_val[ord[i]], pt_val[ord[i + 1]])) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: two rotations give the same opening point");
   }
   std::vector<std::pair<const void*, std::set<uint32_t>>> commitment_sets;          // (poly, ranks of its points)
   for (auto& q : queries) {

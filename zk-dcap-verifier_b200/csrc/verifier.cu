@@ -302,6 +302,55 @@ Fr graph_at_point(const zk_graph& g, EvalCtx& E, const Fr& prev) {
   return last;
 }
 
+// The circuit description comes from the caller: every index graph_at_point / zk_verify_proof will follow is checked up
+// front (the prover side rejects the same things in compile_graph / zk_keygen), so a malformed description is an argument
+// error, never an out-of-bounds read.
+bool source_ok(const zk_value_source& s, const zk_graph& g, const zk_evaluator_desc& D) {
+  switch (s.kind) {
+    case ZK_VS_CONSTANT: return s.a < g.n_constants && g.constants;
+    case ZK_VS_INTERMEDIATE: return s.a <= g.num_intermediates;
+    case ZK_VS_FIXED: return s.a < D.n_fixed && s.b < g.n_rotations;
+    case ZK_VS_ADVICE: return s.a < D.n_advice && s.b < g.n_rotations;
+    case ZK_VS_INSTANCE: return s.a < D.n_instance && s.b < g.n_rotations;
+    case ZK_VS_CHALLENGE: case ZK_VS_BETA: case ZK_VS_GAMMA: case ZK_VS_THETA: case ZK_VS_Y: case ZK_VS_PREVIOUS_VALUE: return true;
+    default: return false;
+  }
+}
+bool graph_ok(const zk_graph& g, const zk_evaluator_desc& D) {
+  if ((g.n_calcs && !g.calcs) || (g.n_rotations && !g.rotations) || (g.n_horner_parts && !g.horner_parts)) return false;
+  for (uint32_t i = 0; i < g.n_calcs; i++) {
+    const zk_calculation& c = g.calcs[i];
+    if (c.target > g.num_intermediates || c.kind > ZK_CALC_STORE || !source_ok(c.a, g, D)) return false;
+    const bool binary = c.kind == ZK_CALC_ADD || c.kind == ZK_CALC_SUB || c.kind == ZK_CALC_MUL || c.kind == ZK_CALC_HORNER;
+    if (binary && !source_ok(c.b, g, D)) return false;
+    if (c.kind == ZK_CALC_HORNER) {
+      if ((uint64_t)c.parts_off + c.parts_len > g.n_horner_parts) return false;
+      for (uint32_t p = 0; p < c.parts_len; p++) if (!source_ok(g.horner_parts[c.parts_off + p], g, D)) return false;
+    }
+  }
+  return true;
+}
+bool circuit_ok(const zk_circuit_desc* cd, const zk_verifier_params* vp) {
+  const zk_evaluator_desc& D = cd->ev;
+  if ((D.n_fixed && !vp->fixed_commitments) || (D.n_perm_columns && (!vp->permutation_commitments || !D.perm_columns))) return false;
+  if ((D.n_lookups && (!D.lookups || !cd->lookup_inputs || !cd->lookup_tables))) return false;
+  if ((cd->n_advice_queries && !cd->advice_queries) || (cd->n_fixed_queries && !cd->fixed_queries) ||
+      (cd->n_instance_queries && !cd->instance_queries)) return false;
+  for (uint32_t q = 0; q < cd->n_advice_queries; q++) if (cd->advice_queries[q].column >= D.n_advice) return false;
+  for (uint32_t q = 0; q < cd->n_fixed_queries; q++) if (cd->fixed_queries[q].column >= D.n_fixed) return false;
+  for (uint32_t q = 0; q < cd->n_instance_queries; q++) if (cd->instance_queries[q].column >= D.n_instance) return false;
+  for (uint32_t c = 0; c < D.n_perm_columns; c++) {
+    const zk_column& pc = D.perm_columns[c];
+    const uint32_t lim = pc.column_type == ZK_COL_ADVICE ? D.n_advice : pc.column_type == ZK_COL_FIXED ? D.n_fixed :
+                         pc.column_type == ZK_COL_INSTANCE ? D.n_instance : 0;
+    if (pc.index >= lim) return false;
+  }
+  if (!graph_ok(D.custom_gates, D)) return false;
+  for (uint32_t l = 0; l < D.n_lookups; l++)
+    if (!graph_ok(D.lookups[l], D) || !graph_ok(cd->lookup_inputs[l], D) || !graph_ok(cd->lookup_tables[l], D)) return false;
+  return true;
+}
+
 std::vector<Fr> lagrange_interp(const std::vector<Fr>& pts, const std::vector<Fr>& evals) {
   size_t m = pts.size();
   std::vector<Fr> out(m, Fr::zero());
@@ -324,6 +373,93 @@ Fr eval_small_poly(const std::vector<Fr>& c, const Fr& x) { Fr a = Fr::zero(); f
 
 }  // namespace
 
+// ---- G2 encodings (ParamsKZG.g2 / s_g2 as the SRS files hold them) -> the verifier's uncompressed form -----------------
+// [UPSTREAM? halo2curves G2Affine::to_bytes, same macro as G1]: x = (c0, c1) as 2 x 32 little-endian bytes; the flag bits
+// live in the last byte (byte 63): 0.3.1 -- parity of y's first byte (y.c0) in bit 7, identity = zeros; >= 0.4 -- parity in
+// bit 6, identity flag in bit 7.  RawBytes = x.c0, x.c1, y.c0, y.c1 as Montgomery limbs (128 B).
+namespace {
+bool fq_sqrt(const Fq& a, Fq* out) {                 // p = 3 mod 4: a^((p+1)/4)
+  uint32_t e[8] = {FqParams::M0 + 1, FqParams::M1, FqParams::M2, FqParams::M3, FqParams::M4, FqParams::M5, FqParams::M6, FqParams::M7};
+  for (int i = 0; i < 8; i++) e[i] = (e[i] >> 2) | (i < 7 ? (e[i + 1] << 30) : 0);
+  Fq r = Fq::pow(a, e);
+  if (!((r * r) - a).is_zero()) return false;
+  *out = r;
+  return true;
+}
+bool f2_sqrt(const Fq2& a, Fq2* out) {
+  Fq two_inv = Fq::inv(fq_small(2));
+  Fq2 r;
+  if (a.c1.is_zero()) {
+    Fq t;
+    if (fq_sqrt(a.c0, &t)) r = f2(t, Fq::zero());
+    else if (fq_sqrt(a.c0.neg(), &t)) r = f2(Fq::zero(), t);
+    else return false;
+  } else {
+    Fq n;
+    if (!fq_sqrt(a.c0 * a.c0 + a.c1 * a.c1, &n)) return false;
+    Fq x0;
+    if (!fq_sqrt((a.c0 + n) * two_inv, &x0) && !fq_sqrt((a.c0 - n) * two_inv, &x0)) return false;
+    r = f2(x0, a.c1 * Fq::inv(x0 + x0));
+  }
+  if (!f2_eq(f2_mul(r, r), a)) return false;
+  *out = r;
+  return true;
+}
+Fq2 g2_b() { return f2_mul(f2(fq_small(3), Fq::zero()), f2_inv(f2(fq_small(9), Fq::one()))); }
+void put_canon(uint8_t* o, const Fq& v) { Fq c = v.from_mont(); memcpy(o, c.l, 32); }
+}  // namespace
+
+extern "C" int zk_g2_decode(int format, const uint8_t* in, uint8_t out[128]) {
+  if (!in || !out) return ZK_ERR_ARG;
+  if (format == ZK_SERDE_RAW_BYTES) {
+    Fq v[4];
+    for (int i = 0; i < 4; i++) {
+      if (!f_is_canonical<Fq>(in + 32 * i)) return ZK_ERR_ARG;      // Montgomery limbs are < p too
+      memcpy(v[i].l, in + 32 * i, 32);
+    }
+    G2 q; q.inf = false; q.x = f2(v[0], v[1]); q.y = f2(v[2], v[3]);
+    if (!g2_on_curve(q)) return ZK_ERR_ARG;
+    for (int i = 0; i < 4; i++) put_canon(out + 32 * i, v[i]);
+    return ZK_OK;
+  }
+  if (format != ZK_SERDE_PROCESSED && format != ZK_SERDE_PROCESSED_V04) return ZK_ERR_ARG;
+  uint8_t b[64];
+  memcpy(b, in, 64);
+  const bool v04 = format == ZK_SERDE_PROCESSED_V04;
+  int sign;
+  if (v04) {
+    if (b[63] & 0x80) return ZK_ERR_ARG;              // the identity is no SRS element
+    sign = (b[63] >> 6) & 1; b[63] &= 0x3F;
+  } else {
+    sign = b[63] >> 7; b[63] &= 0x7F;
+  }
+  if (!f_is_canonical<Fq>(b) || !f_is_canonical<Fq>(b + 32)) return ZK_ERR_ARG;
+  Fq2 x = f2(f_canon_bytes<Fq>(b), f_canon_bytes<Fq>(b + 32));
+  Fq2 y;
+  if (!f2_sqrt(f2_add(f2_mul(f2_mul(x, x), x), g2_b()), &y)) return ZK_ERR_ARG;
+  if ((int)(y.c0.from_mont().l[0] & 1) != sign) y = f2_neg(y);
+  put_canon(out, x.c0); put_canon(out + 32, x.c1); put_canon(out + 64, y.c0); put_canon(out + 96, y.c1);
+  return ZK_OK;
+}
+
+extern "C" int zk_g2_encode(int format, const uint8_t in[128], uint8_t* out) {
+  if (!in || !out) return ZK_ERR_ARG;
+  for (int i = 0; i < 4; i++) if (!f_is_canonical<Fq>(in + 32 * i)) return ZK_ERR_ARG;
+  G2 q; q.inf = false;
+  q.x = f2(f_canon_bytes<Fq>(in), f_canon_bytes<Fq>(in + 32)); q.y = f2(f_canon_bytes<Fq>(in + 64), f_canon_bytes<Fq>(in + 96));
+  if (!g2_on_curve(q)) return ZK_ERR_ARG;
+  if (format == ZK_SERDE_RAW_BYTES) {
+    memcpy(out, q.x.c0.reduce().l, 32); memcpy(out + 32, q.x.c1.reduce().l, 32);
+    memcpy(out + 64, q.y.c0.reduce().l, 32); memcpy(out + 96, q.y.c1.reduce().l, 32);
+    return ZK_OK;
+  }
+  if (format != ZK_SERDE_PROCESSED && format != ZK_SERDE_PROCESSED_V04) return ZK_ERR_ARG;
+  memcpy(out, in, 64);
+  const uint8_t sign = in[64] & 1;                    // parity of y.c0
+  out[63] |= (uint8_t)(sign << (format == ZK_SERDE_PROCESSED_V04 ? 6 : 7));
+  return ZK_OK;
+}
+
 extern "C" int zk_verify_proof(const zk_circuit_desc* cd, const zk_verifier_params* vp, const zk_fr* const* instance_values,
                                const uint32_t* instance_lens, const uint8_t* proof, size_t proof_len, int* accepted) {
   if (!cd || !vp || (!proof && proof_len) || !accepted || !vp->g2 || !vp->s_g2 || (cd->ev.n_instance && (!instance_values || !instance_lens)))
@@ -332,6 +468,7 @@ extern "C" int zk_verify_proof(const zk_circuit_desc* cd, const zk_verifier_para
   const zk_evaluator_desc& D = cd->ev;
   const uint32_t k = D.k, bf = D.blinding_factors, d = D.degree, chunk = d - 2;
   if (d < 3 || k > 27) return ZK_ERR_ARG;
+  if (!circuit_ok(cd, vp)) return ZK_ERR_ARG;
   const uint64_t n = (uint64_t)1 << k;
   const uint32_t L = D.n_lookups, NP = D.n_perm_columns, NS = NP ? (NP + chunk - 1) / chunk : 0;
   // omega of the domain: ROOT_OF_UNITY^(2^(28-k))

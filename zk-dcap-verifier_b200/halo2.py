@@ -200,6 +200,28 @@ def g1_sum(points, ctx=None):
     return out
 
 
+def g2_decode(data, fmt="processed"):
+    """ParamsKZG.g2 / s_g2 as an SRS file holds them (64 compressed bytes, or 128 bytes of Montgomery limbs for
+    "raw_bytes") -> the 128 uncompressed canonical bytes verify_proof takes"""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    if buf.size != 2 * _g1_bytes(fmt):
+        raise ZkError("g2_decode: %d bytes, format %s takes %d" % (buf.size, fmt, 2 * _g1_bytes(fmt)))
+    out = np.empty(128, dtype=np.uint8)
+    if _abi.load().zk_g2_decode(SERDE_FORMATS[fmt], _ptr(buf), _ptr(out)) != 0:
+        raise ZkError("g2_decode: not a G2 point encoding")
+    return out.tobytes()
+
+
+def g2_encode(uncompressed, fmt="processed"):
+    buf = np.frombuffer(bytes(uncompressed), dtype=np.uint8)
+    if buf.size != 128:
+        raise ZkError("g2_encode: 128 uncompressed bytes expected")
+    out = np.empty(2 * _g1_bytes(fmt), dtype=np.uint8)
+    if _abi.load().zk_g2_encode(SERDE_FORMATS[fmt], _ptr(buf), _ptr(out)) != 0:
+        raise ZkError("g2_encode: not a G2 point")
+    return out.tobytes()
+
+
 # ---- poly/kzg/commitment.rs -----------------------------------------------------------------------
 class ParamsKZG:
     """ParamsKZG { k, n, g, g_lagrange } with both base sets resident in HBM."""
@@ -224,6 +246,11 @@ class ParamsKZG:
         self.ctx.check(self.ctx.lib.zk_params_read_format(self.ctx.h, SERDE_FORMATS[fmt], _ptr(buf), buf.size,
                                                           1 if precompute else 0, C.byref(k), _ptr(self.g2), _ptr(self.s_g2)))
         self.k, self.n = k.value, 1 << k.value
+        # the verifier's form (128 uncompressed canonical bytes); None when the file's G2 fields are not curve points
+        try:
+            self.g2_uncompressed, self.s_g2_uncompressed = g2_decode(self.g2, fmt), g2_decode(self.s_g2, fmt)
+        except ZkError:
+            self.g2_uncompressed = self.s_g2_uncompressed = None
         return self
 
     def write(self, g2=None, s_g2=None, fmt="processed"):
@@ -807,6 +834,9 @@ def verify_proof(circuit, fixed_commitments, permutation_commitments, g1, g2, s_
     for i, v in enumerate(_u64(g1, (8,))):
         vp.g1[i] = int(v)
     b2, bs = np.frombuffer(bytes(g2), dtype=np.uint8), np.frombuffer(bytes(s_g2), dtype=np.uint8)
+    if b2.size != 128 or bs.size != 128:
+        raise ZkError("verify_proof: g2 / s_g2 must be 128 uncompressed bytes each (got %d / %d); decode the SRS file's "
+                      "fields with g2_decode() or use ParamsKZG.read(...).g2_uncompressed" % (b2.size, bs.size))
     vp.g2, vp.s_g2 = b2.ctypes.data, bs.ctypes.data
     vp.transcript_kind = _abi.TRANSCRIPTS[transcript]
     inst = [_u64(i, (-1, 4)) for i in instances]
