@@ -187,6 +187,146 @@ __global__ void __launch_bounds__(kThreads, R4 ? ZK_NTT_R4_CTAS : ZK_NTT_MIN_CTA
   }
 }
 
+// ---- warp-resident pass -----------------------------------------------------------------------------------------------
+// The same pass (t <= 7 stages of the DIF network, same twiddles, same digit-reversed write-back) with NO shared memory
+// and NO barrier: a warp owns 128 points = 2^t rows x 2^(7-t) adjacent columns, four per lane.  Point q (7 bits: row in the
+// top t bits, column below) starts in register q >> 5 of lane q & 31.  Stages 1 and 2 pair registers of one lane; every
+// later stage first swaps the lane bit it needs with the upper register bit (each lane keeps the half it owns and receives
+// the other half from its partner, 16 SHFL), so that again both operands of a butterfly sit in one lane and every lane
+// performs two full butterflies per stage (no lane computes a product that is thrown away).  Warps never wait for each
+// other, so the multiplier pipe is fed by whichever warps are in their arithmetic phase (the shared-memory version
+// synchronises the 8 warps of a CTA seven times per pass: ncu showed the pipe idle 26 % of the time,
+// profiles/r1_fullproof_ntt_pass_v5.txt).  The last stage of the last pass has only trivial twiddles and is done with
+// additions alone.
+__device__ __forceinline__ uint32_t ntt_w_logical(uint32_t lane, uint32_t a, uint32_t u_done) {
+  // logical point index of register `a` of `lane` after the exchanges of stages 3..u_done
+  uint32_t q = (a & 1u) << 5;
+  const uint32_t r1 = (a >> 1) & 1u;
+  if (u_done < 3) return q | (r1 << 6) | lane;
+  const uint32_t low = 7 - u_done;                       // lane bits below `low` still hold their own index bit
+  q |= r1 << low;
+  q |= ((lane >> 4) & 1u) << 6;
+  q |= ((lane & 0xFu) >> low) << (low + 1);              // lane bit b in [low, 3] holds index bit b + 1
+  q |= lane & ((1u << low) - 1u);
+  return q;
+}
+__device__ __forceinline__ Fr ntt_w_twiddle(const PassArgs& A, uint32_t qx, uint32_t u, uint32_t cw_log, size_t rest0) {
+  const uint32_t hb = A.t - u, halfN_sh = A.L - 1;
+  const size_t m_lo = (qx >> cw_log) & ((1u << hb) - 1u);
+  const size_t c = qx & ((1u << cw_log) - 1u);
+  const size_t j = (m_lo << (A.L - A.s0 - A.t)) + ((rest0 + c) >> A.s0);
+  const size_t ex = j << (A.s0 + u - 1);
+  // omega^-ex = -omega^(N/2 - ex); ex = 0 maps to table[0] = 1 (the caller negates through (y - x) only when ex != 0)
+  const size_t idx = (A.inverse && ex) ? (((size_t)1 << halfN_sh) - ex) : ex;
+  return Fr::load(A.tw + 2 * (idx << A.tw_shift));
+}
+__device__ __forceinline__ void ntt_w_butterfly(Fr& x, Fr& y, const Fr& w, bool negate) {
+  Fr s = x + y, d = negate ? (y - x) : (x - y);
+  x = s;
+  y = d * w;
+}
+constexpr int kWarpPassMaxT = 7;
+// coset / 1/N scaling on the first load and the last store: called, not inlined (8 more copies of the multiplier would
+// triple the kernel's code size for a path only the first and last pass take)
+__device__ __noinline__ Fr ntt_w_scale(Fr a, Fr b) { return a * b; }
+constexpr int kWarpPassThreads = 128;     // 4 independent warps per CTA, 5 CTAs per SM at <= 102 registers
+__global__ void __launch_bounds__(kWarpPassThreads, 5) k_ntt_pass_w(PassArgs A, PassConsts K) {
+  const uint32_t lane = threadIdx.x & 31u, T = A.t, L = A.L, P = A.s0;
+  const uint32_t cw_log = 7 - T, cw_mask = (1u << cw_log) - 1u;
+  const size_t warp = (size_t)blockIdx.x * (kWarpPassThreads / 32) + (threadIdx.x >> 5);
+  const size_t rest0 = warp << cw_log;
+  const uint32_t row_sh = L - T;
+  const uint4* in = A.in + 2 * (size_t)blockIdx.y * A.in_stride;
+  uint4* out = A.out + 2 * (size_t)blockIdx.y * A.out_stride;
+  Fr v[4];
+#pragma unroll
+  for (uint32_t a = 0; a < 4; a++) {
+    const uint32_t q = (a << 5) | lane;
+    const size_t elem = ((size_t)(q >> cw_log) << row_sh) + rest0 + (q & cw_mask);
+    v[a] = Fr::zero();
+    if (elem < A.n_in) {
+      v[a] = Fr::load(in + 2 * elem);
+      if (A.pre_mode) {
+        const uint32_t r3 = (uint32_t)(elem % 3);
+        if (r3 == 1) v[a] = ntt_w_scale(v[a], K.pre[1]);
+        else if (r3 == 2) v[a] = ntt_w_scale(v[a], K.pre[2]);
+      }
+    }
+  }
+  const bool inv = A.inverse != 0;
+  // the negation of the inverse direction applies only where the exponent is non-zero: (y - x) * omega^(N/2 - ex)
+  auto neg_for = [&](uint32_t qx, uint32_t u) -> bool {
+    if (!inv) return false;
+    const uint32_t hb = T - u;
+    const size_t m_lo = (qx >> cw_log) & ((1u << hb) - 1u);
+    return (m_lo << (L - P - T)) + ((rest0 + (qx & cw_mask)) >> P) != 0;
+  };
+  // stage 1: register bit 1
+  if (T >= 1) {
+    if (P + 1 == L) {
+      Fr s0 = v[0] + v[2], d0 = v[0] - v[2], s1 = v[1] + v[3], d1 = v[1] - v[3];
+      v[0] = s0; v[2] = d0; v[1] = s1; v[3] = d1;
+    } else {
+      const uint32_t q0 = ntt_w_logical(lane, 0, 1), q1 = ntt_w_logical(lane, 1, 1);
+      Fr w0 = ntt_w_twiddle(A, q0, 1, cw_log, rest0), w1 = ntt_w_twiddle(A, q1, 1, cw_log, rest0);
+      ntt_w_butterfly(v[0], v[2], w0, neg_for(q0, 1));
+      ntt_w_butterfly(v[1], v[3], w1, neg_for(q1, 1));
+    }
+  }
+  // stage 2: register bit 0
+  if (T >= 2) {
+    if (P + 2 == L) {
+      Fr s0 = v[0] + v[1], d0 = v[0] - v[1], s1 = v[2] + v[3], d1 = v[2] - v[3];
+      v[0] = s0; v[1] = d0; v[2] = s1; v[3] = d1;
+    } else {
+      const uint32_t q0 = ntt_w_logical(lane, 0, 2), q1 = ntt_w_logical(lane, 2, 2);
+      Fr w0 = ntt_w_twiddle(A, q0, 2, cw_log, rest0), w1 = ntt_w_twiddle(A, q1, 2, cw_log, rest0);
+      ntt_w_butterfly(v[0], v[1], w0, neg_for(q0, 2));
+      ntt_w_butterfly(v[2], v[3], w1, neg_for(q1, 2));
+    }
+  }
+  // stages 3..T: swap lane bit 7-u with register bit 1, then pair (v[k], v[k+2])
+#pragma unroll 1
+  for (uint32_t u = 3; u <= T; u++) {
+    const uint32_t d = 7 - u, bit = (lane >> d) & 1u;
+    const bool trivial = (P + u == L);
+    const uint32_t q0 = ntt_w_logical(lane, 0, u), q1 = ntt_w_logical(lane, 1, u);
+    Fr w0, w1;
+    if (!trivial) { w0 = ntt_w_twiddle(A, q0, u, cw_log, rest0); w1 = ntt_w_twiddle(A, q1, u, cw_log, rest0); }
+#pragma unroll
+    for (uint32_t k = 0; k < 2; k++) {
+#pragma unroll
+      for (uint32_t i = 0; i < 8; i++) {
+        const uint32_t send = bit ? v[k].l[i] : v[k + 2].l[i];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1u << d);
+        if (bit) v[k].l[i] = recv; else v[k + 2].l[i] = recv;
+      }
+    }
+    if (trivial) {
+      Fr s0 = v[0] + v[2], d0 = v[0] - v[2], s1 = v[1] + v[3], d1 = v[1] - v[3];
+      v[0] = s0; v[2] = d0; v[1] = s1; v[3] = d1;
+    } else {
+      ntt_w_butterfly(v[0], v[2], w0, neg_for(q0, u));
+      ntt_w_butterfly(v[1], v[3], w1, neg_for(q1, u));
+    }
+  }
+  // store with the pass's digit bit-reversed
+  const uint32_t u_done = T >= 3 ? T : 2;
+#pragma unroll
+  for (uint32_t a = 0; a < 4; a++) {
+    const uint32_t q = ntt_w_logical(lane, a, u_done);
+    const uint32_t m = q >> cw_log;
+    const size_t rest = rest0 + (q & cw_mask);
+    const uint32_t r = T ? (__brev(m) >> (32 - T)) : 0;
+    const size_t U = rest >> P, Pb = rest & (((size_t)1 << P) - 1);
+    const size_t dst = (U << (T + P)) + ((size_t)r << P) + Pb;
+    Fr o = v[a];
+    if (A.post_mode == 1) o = ntt_w_scale(o, K.post[0]);
+    else if (A.post_mode == 2) o = ntt_w_scale(o, K.post[dst % 3]);
+    o.store(out + 2 * dst);
+  }
+}
+
 // tw[e] = omega^e for e < half_n; each thread produces kTwChunk consecutive powers
 constexpr int kTwChunk = 32;
 __global__ void k_gen_twiddles(uint4* tw, Fr omega, size_t half_n) {
@@ -252,12 +392,17 @@ int run_ntt(zk_ctx* ctx, const NttJob& J) {
   static const bool radix4 = getenv("ZK_NTT_RADIX4") && atoi(getenv("ZK_NTT_RADIX4")) == 1;
   ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass_t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  uint32_t npass = L == 0 ? 1 : (L + kMaxT - 1) / kMaxT;
+  // warp-resident passes (no shared memory, no barriers) from 2^10 points on; ZK_NTT_SMEM=1 keeps the shared-memory passes
+  static const bool force_smem = getenv("ZK_NTT_SMEM") && atoi(getenv("ZK_NTT_SMEM")) == 1;
+  const bool warp_pass = !force_smem && L >= 10;
+  const uint32_t max_t = warp_pass ? (uint32_t)kWarpPassMaxT : (uint32_t)kMaxT;
+  uint32_t npass = L == 0 ? 1 : (L + max_t - 1) / max_t;
   uint32_t base_t = L / npass, extra = L % npass;   // first `extra` passes take one more stage
   uint32_t min_t = base_t;
   uint32_t s0 = 0;
   const void* src = J.in;
   size_t src_stride = J.in_stride;
+  if (npass > 1 && !J.tmp) ZK_FAIL(ctx, ZK_ERR_STATE, "ntt: %u passes need a ping-pong buffer", npass);
   for (uint32_t p = 0; p < npass; p++) {
     uint32_t t = base_t + (p < extra ? 1 : 0);
     uint32_t logC = kTileLog - t;
@@ -274,11 +419,16 @@ int run_ntt(zk_ctx* ctx, const NttJob& J) {
     A.inverse = J.inverse;
     A.pre_mode = (p == 0) ? J.pre_mode : 0;
     A.post_mode = last ? J.post_mode : 0;
-    size_t tile = (size_t)1 << (t + logC);
-    dim3 grid((unsigned)(N >> (t + logC)), (unsigned)J.count);
-    size_t smem = tile * 32 + 64;
-    if (radix4) { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_t<1>, grid, kThreads, smem, A, J.K); }
-    else { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_t<0>, grid, kThreads, smem, A, J.K); }
+    if (warp_pass) {
+      dim3 grid((unsigned)(N >> 9), (unsigned)J.count);           // 4 warps x 128 points per CTA
+      ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_w, grid, kWarpPassThreads, 0, A, J.K);
+    } else {
+      size_t tile = (size_t)1 << (t + logC);
+      dim3 grid((unsigned)(N >> (t + logC)), (unsigned)J.count);
+      size_t smem = tile * 32 + 64;
+      if (radix4) { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_t<1>, grid, kThreads, smem, A, J.K); }
+      else { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_t<0>, grid, kThreads, smem, A, J.K); }
+    }
     src = dst; src_stride = N;
     s0 += t;
   }
@@ -415,6 +565,7 @@ int domain_ntt(zk_domain* d, const void* src, void* dst, size_t count, size_t in
   zk_ctx* ctx = d->ctx;
   size_t N = (size_t)1 << L;
   uint32_t npass = L == 0 ? 1 : (L + kMaxT - 1) / kMaxT;
+  if (L > (uint32_t)kWarpPassMaxT) npass = 2;        // warp-resident passes take at most 7 stages each
   NttJob J; memset(&J, 0, sizeof J);
   J.in = src; J.out = dst; J.count = count; J.in_stride = in_stride; J.n_in = n_in; J.L = L;
   J.tw = d->tw_ext; J.tw_shift = d->extended_k - L;
