@@ -406,6 +406,10 @@ int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t id
 void zk_group_destroy(zk_group* g);
 uint32_t zk_group_rank(const zk_group* g);
 uint32_t zk_group_world(const zk_group* g);
+/* 1 when the small exchanges of this group (commitment points, status words) go through peer-mapped windows: stores over
+ * NVLink issued from the producing kernel's epilogue plus a flag, instead of NCCL all-gathers (ZK_GROUP_NO_P2P=1 or a
+ * failed CUDA IPC mapping leave NCCL in charge) */
+int zk_group_p2p_enabled(const zk_group* g);
 /* Attach (or detach with NULL) a group: the key's proofs are then computed jointly.  The group must outlive its use. */
 int zk_pkey_set_group(zk_pkey* pk, zk_group* g);
 /* How `count` commitments over n bases are split: *mode 0 = rank commits columns [*lo, *hi) (every rank's share padded

@@ -64,6 +64,14 @@ extern "C" void ech_digits(const unsigned* canon, int c, int W, int* digits) {
   for (int w = 0; w < W; w++) digits[w] = signed_digit(canon, w, c, carry);
   digits[W] = carry;
 }
+// the streaming form the digit kernels use (registers only)
+extern "C" void ech_digits_stream(const unsigned* canon, int c, int W, int* digits) {
+  unsigned l[8];
+  memcpy(l, canon, 32);
+  int carry = 0;
+  for (int w = 0; w < W; w++) digits[w] = next_signed_digit(l, c, carry);
+  digits[W] = carry;
+}
 
 // ---- evaluate_h interpreter on the host -------------------------------------------------------
 #include "../../zk-dcap-verifier_b200/csrc/evalh_compile.hpp"

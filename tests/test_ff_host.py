@@ -118,6 +118,9 @@ def test_signed_digit_recoding(ffh, c):
         assert d[W] == 0, "carry out of the top window"
         assert all(-(1 << (c - 1)) < int(x) <= (1 << (c - 1)) for x in d[:W])
         assert sum(int(x) << (c * w) for w, x in enumerate(d[:W])) == v
+        d2 = np.zeros(W + 1, dtype=np.int32)                              # the streaming (register-only) form
+        ffh.ech_digits_stream(canon.ctypes.data_as(C.c_void_p), C.c_int(c), C.c_int(W), d2.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(d, d2)
 
 
 @pytest.mark.parametrize("kind", [0, 1])

@@ -18,6 +18,17 @@ struct zk_srs_set {
   int table_c = 0, table_w = 0;
 };
 
+// Peer-to-peer exchange of small results inside a group of GPUs (group.cu): every rank maps every peer's exchange window
+// (CUDA IPC over NVLink).  A producer kernel stores its results straight into the peers' windows and, once all of its CTAs
+// are done, raises a flag there; the consumer kernel on each peer spins on its own flags.  Passed BY VALUE to kernels.
+constexpr int kZkMaxGroup = 16;
+struct zk_p2p_push {
+  char* peer_data[kZkMaxGroup];        // peer q's window half for this exchange + my segment offset (nullptr for myself)
+  uint32_t* peer_flag[kZkMaxGroup];    // peer q's flag slot for ME
+  uint32_t world = 0, rank = 0, epoch = 0;
+  unsigned int* done = nullptr;        // local counter of finished producer CTAs
+};
+
 struct zk_timing_rec { const char* name; cudaEvent_t a, b; };
 struct zk_stat { uint64_t launches = 0; double ms = 0; };
 
@@ -57,6 +68,8 @@ struct zk_ctx {
   // device-side work counters (zk_ctx_counters): [0] bucket entries = non-zero signed digits sorted into buckets, i.e. the
   // group additions the accumulation performs, [1] MSMs
   unsigned long long* d_counters = nullptr;
+  // set by the prover around a sharded commitment: k_msm_final then also stores its XYZZ results into the peers' windows
+  const zk_p2p_push* p2p = nullptr;
 };
 
 #define ZK_FAIL(ctx, code, ...)                                  \

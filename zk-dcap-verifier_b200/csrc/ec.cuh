@@ -43,7 +43,10 @@ struct XYZZ {
     XYZZ p; p.x = Fq::zero(); p.y = Fq::zero(); p.zz = Fq::zero(); p.zzz = Fq::zero();
     return p;
   }
-  ZK_HD bool is_identity() const { return zz.is_zero(); }
+  // zz of the identity is the literal 0 (identity(), zeroed bucket memory, 0 * x in the formulas); zz of any other point is
+  // a product of non-zero field elements, whose lazy representative in [0, 2p) is never 0 -- so a raw limb test suffices
+  // (the full test needs a conditional subtraction of p first: ~40 more instructions in every mixed addition)
+  ZK_HD bool is_identity() const { return zz.is_zero_raw(); }
   ZK_HD static XYZZ from_affine(const Affine& a) {
     if (a.is_identity()) return identity();
     XYZZ p; p.x = a.x; p.y = a.y; p.zz = Fq::one(); p.zzz = Fq::one();
@@ -82,8 +85,9 @@ struct XYZZ {
     return r;
   }
   // P + (affine Q), madd-2008-s; all exceptional cases handled
+  // `q` comes from memory (canonical limbs) or from cneg of such a point (0 - 0 = 0), so its identity test is raw too
   ZK_HD XYZZ madd(const Affine& q) const {
-    if (q.is_identity()) return *this;
+    if (q.x.is_zero_raw() && q.y.is_zero_raw()) return *this;
     if (is_identity()) { XYZZ r; r.x = q.x; r.y = q.y; r.zz = Fq::one(); r.zzz = Fq::one(); return r; }
     Fq u2 = q.x * zz, s2 = q.y * zzz;
     Fq p = u2 - x, r_ = s2 - y;
@@ -157,6 +161,21 @@ ZK_HD int signed_digit(const uint32_t* limbs, int w, int c, int& carry) {
     if (li + 1 < 8) two |= (uint64_t)limbs[li + 1] << 32;
     v = (uint32_t)((two >> sh) & ((1u << c) - 1u));
   }
+  int d = (int)v + carry;
+  if (d > (1 << (c - 1))) { d -= (1 << c); carry = 1; } else carry = 0;
+  return d;
+}
+
+
+// The same recoding as a STREAM: windows are taken from the bottom while the value is shifted right by c bits, so every
+// limb access has a compile-time index and the scalar stays in registers (signed_digit's `limbs[bit >> 5]` with a
+// run-time window number made the digit kernels read the scalar back from local memory: 28 LDL per thread).
+// 1 <= c <= 31; `l` is consumed.
+ZK_HD int next_signed_digit(uint32_t* l, int c, int& carry) {
+  const uint32_t v = l[0] & ((1u << c) - 1u);
+#pragma unroll
+  for (int i = 0; i < 7; i++) l[i] = (l[i] >> c) | (l[i + 1] << (32 - c));
+  l[7] >>= c;
   int d = (int)v + carry;
   if (d > (1 << (c - 1))) { d -= (1 << c); carry = 1; } else carry = 0;
   return d;

@@ -10,16 +10,33 @@
 // never holds two NCCL instances); the library itself has no link-time dependency on it.
 #include <dlfcn.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
+
+// One peer-mapped exchange window per communicator (= per stream that issues exchanges): two halves used alternately
+// (a rank may be one exchange ahead of a peer, never two -- it cannot finish exchange e + 1 before every peer has pushed
+// e + 1, i.e. has consumed e), each half = world segments of kP2PSegment bytes, then one 128-byte flag line per source rank.
+constexpr size_t kP2PSegment = 64 * 1024;
+struct P2PWindow {
+  char* local = nullptr;
+  char* peer[kZkMaxGroup] = {};
+  unsigned int* done = nullptr;
+  uint32_t epoch = 0;
+  bool ok = false;
+  size_t half_bytes(uint32_t world) const { return world * kP2PSegment + world * 128; }
+};
 
 struct zk_group {
   zk_ctx* ctx = nullptr;
   uint32_t rank = 0, world = 1;
   void* comm = nullptr;      // collectives of the context's own stream
   void* comm2 = nullptr;     // collectives issued on another stream of the same device (the prover's transform stream)
+  P2PWindow win[2];          // [0] exchanges on the context's stream, [1] on the second stream
 };
 
 namespace {
@@ -63,7 +80,136 @@ Nccl* nccl() {
   return N.lib ? &N : nullptr;
 }
 
+// ---- peer-to-peer exchange kernels -------------------------------------------------------------------------------------------
+// spin until every peer's flag for this exchange shows `epoch` (bounded: ~4 s at 2 GHz, then *err = 1)
+__device__ __forceinline__ bool p2p_wait_flags(const char* local_flags, uint32_t world, uint32_t rank, uint32_t epoch) {
+  bool ok = true;
+  if (threadIdx.x < world && threadIdx.x != rank) {
+    const volatile uint32_t* f = (const volatile uint32_t*)(local_flags + 128 * threadIdx.x);
+    const long long t0 = clock64();
+    while (*f != epoch) {
+      if (clock64() - t0 > 8000000000ll) { ok = false; break; }
+    }
+  }
+  __threadfence_system();
+  return ok;
+}
+// consumer: wait, then copy the peers' segments from the local window into d_buf (segment q at d_buf + q * bytes)
+__global__ void __launch_bounds__(256) k_p2p_wait_gather(const char* half, const char* flags, uint32_t world, uint32_t rank, uint32_t epoch,
+                                                         char* d_buf, size_t bytes, int* err) {
+  if (!p2p_wait_flags(flags, world, rank, epoch)) *err = 1;
+  __syncthreads();
+  const size_t vec = bytes / 16;
+  for (uint32_t q = 0; q < world; q++) {
+    if (q == rank) continue;
+    const uint4* src = (const uint4*)(half + q * kP2PSegment);
+    uint4* dst = (uint4*)(d_buf + q * bytes);
+    for (size_t i = threadIdx.x; i < vec; i += blockDim.x) dst[i] = __ldcg(src + i);
+  }
+}
+// producer for data that is already in d_buf (generic small all-gather): push my segment, raise my flag everywhere
+__global__ void __launch_bounds__(256) k_p2p_push(zk_p2p_push pp, const char* my_segment, size_t bytes) {
+  const size_t vec = bytes / 16;
+  const uint4* src = (const uint4*)my_segment;
+  for (uint32_t q = 0; q < pp.world; q++) {
+    if (q == pp.rank) continue;
+    uint4* dst = (uint4*)pp.peer_data[q];
+    for (size_t i = threadIdx.x; i < vec; i += blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < pp.world && threadIdx.x != pp.rank) *(volatile uint32_t*)pp.peer_flag[threadIdx.x] = pp.epoch;
+}
+
+int p2p_setup(zk_group* g, Nccl* N, int which) {
+  zk_ctx* ctx = g->ctx;
+  P2PWindow& W = g->win[which];
+  const size_t total = 2 * W.half_bytes(g->world);
+  void* comm = which == 0 ? g->comm : g->comm2;
+  cudaIpcMemHandle_t* d_handles = nullptr;
+  std::vector<cudaIpcMemHandle_t> handles(g->world);
+  if (cudaMalloc(&W.local, total) != cudaSuccess) { cudaGetLastError(); return ZK_ERR_OOM; }
+  if (cudaMalloc(&W.done, 128) != cudaSuccess || cudaMalloc(&d_handles, g->world * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) { cudaGetLastError(); return ZK_ERR_OOM; }
+  cudaMemsetAsync(W.local, 0, total, ctx->stream);
+  cudaMemsetAsync(W.done, 0, 128, ctx->stream);
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, W.local) != cudaSuccess) { cudaGetLastError(); cudaFree(d_handles); return ZK_ERR_CUDA; }
+  cudaMemcpyAsync(d_handles + g->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream);
+  int r = N->allgather(d_handles + g->rank, d_handles, sizeof mine, /*ncclChar*/ 0, comm, ctx->stream);
+  if (r != 0 || cudaMemcpyAsync(handles.data(), d_handles, g->world * sizeof mine, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); cudaFree(d_handles); return ZK_ERR_CUDA; }
+  cudaFree(d_handles);
+  for (uint32_t q = 0; q < g->world; q++) {
+    if (q == g->rank) { W.peer[q] = W.local; continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, handles[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return ZK_ERR_CUDA; }
+    W.peer[q] = (char*)p;
+  }
+  // nobody may push before every window is zeroed and mapped: one more (tiny) collective as a barrier
+  int* d_tok = nullptr;
+  if (cudaMalloc(&d_tok, g->world * 4) != cudaSuccess) return ZK_ERR_OOM;
+  r = N->allgather(d_tok + g->rank, d_tok, 4, 0, comm, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_tok);
+  if (r != 0) return ZK_ERR_CUDA;
+  W.ok = true;
+  return ZK_OK;
+}
+void p2p_teardown(zk_group* g) {
+  for (auto& W : g->win) {
+    for (uint32_t q = 0; q < g->world; q++)
+      if (q != g->rank && W.peer[q]) cudaIpcCloseMemHandle(W.peer[q]);
+    if (W.local) cudaFree(W.local);
+    if (W.done) cudaFree(W.done);
+    W = P2PWindow();
+  }
+}
+
 }  // namespace
+
+// Descriptor of the next exchange on `on`'s stream for a producer kernel (k_msm_final's epilogue, k_p2p_push); false when the
+// peer windows are not available or a segment would not fit (the caller then uses the NCCL all-gather).
+bool zk_group_p2p_begin(zk_group* g, zk_ctx* on, size_t bytes_per_rank, zk_p2p_push* out) {
+  if (!g || g->world <= 1) return false;
+  P2PWindow& W = g->win[(on && on != g->ctx) ? 1 : 0];
+  if (!W.ok || bytes_per_rank > kP2PSegment || (bytes_per_rank & 15)) return false;
+  W.epoch++;
+  const size_t half = (W.epoch & 1) * W.half_bytes(g->world);
+  zk_p2p_push pp;
+  pp.world = g->world; pp.rank = g->rank; pp.epoch = W.epoch; pp.done = W.done;
+  for (uint32_t q = 0; q < g->world; q++) {
+    pp.peer_data[q] = W.peer[q] + half + g->rank * kP2PSegment;
+    pp.peer_flag[q] = (uint32_t*)(W.peer[q] + half + g->world * kP2PSegment + 128 * g->rank);
+  }
+  *out = pp;
+  return true;
+}
+// Completes the exchange begun by zk_group_p2p_begin: waits for every peer's flag and copies their segments into d_buf.
+int zk_group_p2p_finish(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank) {
+  zk_ctx* ctx = on ? on : g->ctx;
+  P2PWindow& W = g->win[ctx != g->ctx ? 1 : 0];
+  const size_t half = (W.epoch & 1) * W.half_bytes(g->world);
+  int* err = (int*)(W.done + 16);
+  ZK_LAUNCH(ctx, "group_p2p", k_p2p_wait_gather, 1, 256, 0, (const char*)(W.local + half), (const char*)(W.local + half + g->world * kP2PSegment),
+            g->world, g->rank, W.epoch, (char*)d_buf, bytes_per_rank, err);
+  return ZK_OK;
+}
+// Pushes a segment that is already complete in local memory (ranks without work in a sharded commitment, generic gathers).
+int zk_group_p2p_push(zk_group* g, zk_ctx* on, const zk_p2p_push& pp, const void* my_segment, size_t bytes) {
+  zk_ctx* ctx = on ? on : g->ctx;
+  ZK_LAUNCH(ctx, "group_p2p", k_p2p_push, 1, 256, 0, pp, (const char*)my_segment, bytes);
+  return ZK_OK;
+}
+// 1 when an exchange timed out since the last call (a peer never raised its flag); synchronises the stream.
+int zk_group_p2p_error(zk_group* g, zk_ctx* on) {
+  zk_ctx* ctx = on ? on : g->ctx;
+  P2PWindow& W = g->win[ctx != g->ctx ? 1 : 0];
+  if (!W.ok) return 0;
+  int e = 0;
+  cudaMemcpyAsync(&e, (int*)(W.done + 16), 4, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  return e;
+}
 
 extern "C" int zk_group_unique_id(uint8_t id[256]) {     // two NCCL ids: one communicator per stream
   Nccl* N = nccl();
@@ -97,13 +243,35 @@ extern "C" int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const
       ZK_FAIL(ctx, ZK_ERR_CUDA, "zk_group_create: ncclCommInitRank: %s", e.c_str());
     }
   }
+  // peer windows for the small exchanges (commitment points, status words); ZK_GROUP_NO_P2P=1 keeps NCCL all-gathers
+  if (world > 1 && !getenv("ZK_GROUP_NO_P2P")) {
+    for (int i = 0; i < 2; i++)
+      if (p2p_setup(g, N, i) != ZK_OK) { g->win[i].ok = false; break; }
+    // all ranks must agree (a rank that failed would deadlock the others): both windows or none, agreed through NCCL
+    int* d_ok = nullptr;
+    std::vector<int> oks(world, 0);
+    int mine = (g->win[0].ok && g->win[1].ok) ? 1 : 0;
+    if (cudaMalloc(&d_ok, world * 4) == cudaSuccess) {
+      cudaMemcpyAsync(d_ok + rank, &mine, 4, cudaMemcpyHostToDevice, ctx->stream);
+      N->allgather(d_ok + rank, d_ok, 4, 0, g->comm, ctx->stream);
+      cudaMemcpyAsync(oks.data(), d_ok, world * 4, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(d_ok);
+    }
+    bool all = true;
+    for (int v : oks) all = all && v == 1;
+    if (!all) { g->win[0].ok = g->win[1].ok = false; }
+  }
   *out = g;
   return ZK_OK;
 }
+extern "C" int zk_group_p2p_enabled(const zk_group* g) { return g && g->win[0].ok && g->win[1].ok ? 1 : 0; }
 
 extern "C" void zk_group_destroy(zk_group* g) {
   if (!g) return;
   Nccl* N = nccl();
+  cudaSetDevice(g->ctx->device); cudaDeviceSynchronize();
+  p2p_teardown(g);
   if (N && g->comm) {
     cudaSetDevice(g->ctx->device); cudaDeviceSynchronize();
     N->comm_destroy(g->comm);
@@ -121,6 +289,11 @@ int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_ra
   Nccl* N = nccl();
   if (!N) ZK_FAIL(ctx, ZK_ERR_STATE, "group: NCCL not loaded");
   void* comm = ctx == g->ctx ? g->comm : g->comm2;
+  zk_p2p_push pp;
+  if (zk_group_p2p_begin(g, ctx, bytes_per_rank, &pp)) {          // small: stores into the peers' windows + flags
+    ZK_TRY(zk_group_p2p_push(g, ctx, pp, (const char*)d_buf + (size_t)g->rank * bytes_per_rank, bytes_per_rank));
+    return zk_group_p2p_finish(g, ctx, d_buf, bytes_per_rank);
+  }
   zk_timing_begin(ctx, "group_allgather");
   int r = N->allgather((const char*)d_buf + (size_t)g->rank * bytes_per_rank, d_buf, bytes_per_rank, /*ncclChar*/ 0, comm, ctx->stream);
   zk_timing_end(ctx);

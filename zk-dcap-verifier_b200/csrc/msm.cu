@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint4* scalars, MsmPla
   uint32_t* cnt = counts + msm * P.nb;
   int carry = 0;
   for (uint32_t w = 0; w < P.W; w++) {
-    int d = signed_digit(s.l, (int)w, (int)P.c, carry);
+    int d = next_signed_digit(s.l, (int)P.c, carry);
     if (d == 0) continue;
     uint32_t neg = d < 0 ? 1u : 0u;
     uint32_t mag = (uint32_t)(d < 0 ? -d : d);
@@ -84,7 +84,7 @@ __device__ __forceinline__ void for_each_digit(const uint4* scalars, const MsmPl
   Fr s = Fr::load(scalars + 2 * (msm * P.sc_stride + P.base_off + i)).from_mont();
   int carry = 0;
   for (uint32_t w = 0; w < P.W; w++) {
-    int d = signed_digit(s.l, (int)w, (int)P.c, carry);
+    int d = next_signed_digit(s.l, (int)P.c, carry);
     if (d == 0) continue;
     uint32_t neg = d < 0 ? 1u : 0u;
     uint32_t mag = (uint32_t)(d < 0 ? -d : d);
@@ -587,7 +587,10 @@ __global__ void __launch_bounds__(128) k_msm_combine_levels(LevelPlan L, size_t 
 // of items doublings + items additions; one CTA per MSM, the items live in shared memory.
 constexpr uint32_t kFinalMaxItems = 512;
 // `items` values V_e per MSM with weight 2^(shift * e)
-__global__ void __launch_bounds__(256) k_msm_final(const uint4* sums, uint32_t items, uint32_t shift, uint4* out, int raw) {
+// In a group of GPUs (`pp.world` > 1, raw output) the epilogue is also the exchange: the 128-byte XYZZ result is stored into
+// every peer's window over NVLink, and the CTA that finishes last raises this rank's flag in every peer ("fuse the
+// exchange into the reduction kernel's epilogue"); no collective call, no staging copy.
+__global__ void __launch_bounds__(256) k_msm_final(const uint4* sums, uint32_t items, uint32_t shift, uint4* out, int raw, zk_p2p_push pp) {
   extern __shared__ uint4 fsm[];
   size_t msm = blockIdx.x;
   const uint4* s = sums + 8 * (msm * items);
@@ -605,6 +608,21 @@ __global__ void __launch_bounds__(256) k_msm_final(const uint4* sums, uint32_t i
   if (threadIdx.x == 0) {
     if (raw) XYZZ::load(fsm).store(out + 8 * msm);          // XYZZ record, normalised by the caller
     else store_g1_normalised(out + 6 * msm, XYZZ::load(fsm).to_affine());
+  }
+  if (raw && pp.world > 1) {
+    if (threadIdx.x < 8) {
+      const uint4 v = fsm[threadIdx.x];
+      for (uint32_t q = 0; q < pp.world; q++)
+        if (q != pp.rank) ((uint4*)pp.peer_data[q])[8 * msm + threadIdx.x] = v;
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(pp.done, 1u) == gridDim.x - 1) {
+      *pp.done = 0;
+      __threadfence_system();
+      for (uint32_t q = 0; q < pp.world; q++)
+        if (q != pp.rank) *(volatile uint32_t*)pp.peer_flag[q] = pp.epoch;
+    }
   }
 }
 
@@ -921,7 +939,7 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
     ZK_LAUNCH(ctx, "msm_final", k_msm_combine_levels, zk_div_up(rws, 128), 128, 0, L, rws, R);
     size_t fsmem = (size_t)P.G * 128;
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFinalMaxItems * 128)));
-    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)R, P.G, P.c, (uint4*)d_out, ctx->msm_raw ? 1 : 0);
+    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)R, P.G, P.c, (uint4*)d_out, ctx->msm_raw ? 1 : 0, (ctx->msm_raw && ctx->p2p) ? *ctx->p2p : zk_p2p_push());
     return ZK_OK;
   }
   // rows and columns (ZK_MSM_REDUCE=bits keeps the bit-sliced reduction over all buckets, which also serves G > 1)
@@ -956,7 +974,7 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
       ZK_TRY(tree(bits, P.count * items, kBitSegs, &I));
       if (used * 128 > red_bytes) ZK_FAIL(ctx, ZK_ERR_STATE, "msm: reduction arena overflow");
       ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFinalMaxItems * 128)));
-      ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, (size_t)items * 128, (const uint4*)I, items, 1u, (uint4*)d_out, ctx->msm_raw ? 1 : 0);
+      ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, (size_t)items * 128, (const uint4*)I, items, 1u, (uint4*)d_out, ctx->msm_raw ? 1 : 0, (ctx->msm_raw && ctx->p2p) ? *ctx->p2p : zk_p2p_push());
       return ZK_OK;
     }
   }
@@ -974,7 +992,7 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   {
     size_t fsmem = (size_t)P.G * P.c * 128;
     ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFinalMaxItems * 128)));
-    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)src, P.G * P.c, 1u, (uint4*)d_out, ctx->msm_raw ? 1 : 0);
+    ZK_LAUNCH(ctx, "msm_final", k_msm_final, (unsigned)P.count, 256, fsmem, (const uint4*)src, P.G * P.c, 1u, (uint4*)d_out, ctx->msm_raw ? 1 : 0, (ctx->msm_raw && ctx->p2p) ? *ctx->p2p : zk_p2p_push());
   }
   return ZK_OK;
 }

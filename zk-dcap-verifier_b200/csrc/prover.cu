@@ -33,6 +33,9 @@ int zk_evaluate_h_launch(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, con
                          const zk_fr* theta, zk_fr* d_out_ext, size_t row0, size_t row1);
 struct zk_group;
 int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank);
+bool zk_group_p2p_begin(zk_group* g, zk_ctx* on, size_t bytes_per_rank, zk_p2p_push* out);
+int zk_group_p2p_finish(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank);
+int zk_group_p2p_push(zk_group* g, zk_ctx* on, const zk_p2p_push& pp, const void* my_segment, size_t bytes);
 int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, const uint32_t* owners, size_t count, size_t height, size_t halo);
 extern "C" uint32_t zk_group_rank(const zk_group* g);
 extern "C" uint32_t zk_group_world(const zk_group* g);
@@ -251,22 +254,44 @@ int commit_enqueue(zk_pkey* K, const char* d_polys, size_t count, int which, siz
   int mode; size_t per, lo, hi;
   zk_group_shard_plan(rank, world, count, K->n, &mode, &per, &lo, &hi);
   PtRaw* xchg = (PtRaw*)K->d_xchg;
+  // The exchange of the points is fused into the MSM: k_msm_final stores each result straight into every peer's window
+  // and raises a flag when the rank's batch is complete (zk_p2p_push); the peers' wait kernel gathers them.  Without
+  // mapped windows (ZK_GROUP_NO_P2P, IPC failure) the NCCL all-gather does the same.
+  zk_p2p_push pp;
+  const size_t seg_bytes = (mode == 0 ? per : count) * sizeof(PtRaw);
+  const bool fused = zk_group_p2p_begin(K->group, ctx, seg_bytes, &pp);
+  struct PushGuard { zk_ctx* c; ~PushGuard() { c->p2p = nullptr; } } guard{ctx};
+  auto exchange = [&](bool launched_msm, PtRaw* mine) -> int {
+    ctx->p2p = nullptr;
+    if (!fused) return zk_group_allgather(K->group, ctx, xchg, seg_bytes);
+    if (!launched_msm) ZK_TRY(zk_group_p2p_push(K->group, ctx, pp, mine, seg_bytes));      // nothing to commit here: push the zeros
+    return zk_group_p2p_finish(K->group, ctx, xchg, seg_bytes);
+  };
   if (mode == 0) {
     // by column, ROUND-ROBIN (column p belongs to rank p mod world): neighbouring columns of a region tend to hold the same
     // kind of values (bits and bytes are cheap commitments, field elements expensive), contiguous ranges do not balance
     auto owned = [&](uint32_t r) { return count > r ? (count - r + world - 1) / world : (size_t)0; };
-    if (owned(rank))
+    PtRaw* mine = xchg + (size_t)rank * per;
+    if (fused && owned(rank) < per) ZK_CUDA(ctx, cudaMemsetAsync(mine, 0, per * sizeof(PtRaw), ctx->stream));
+    if (owned(rank)) {
+      if (fused) ctx->p2p = &pp;
       ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)(d_polys + (size_t)rank * K->n * 32), which, (size_t)world * K->n, 0, K->n, owned(rank),
-                                    (zk_g1*)(xchg + (size_t)rank * per)));
-    ZK_TRY(zk_group_allgather(K->group, ctx, xchg, per * sizeof(PtRaw)));
+                                    (zk_g1*)mine));
+    }
+    ZK_TRY(exchange(owned(rank) != 0, mine));
     for (uint32_t r = 0; r < world; r++)
       if (owned(r))
         ZK_CUDA(ctx, cudaMemcpy2DAsync(out + r, (size_t)world * sizeof(PtRaw), xchg + (size_t)r * per, sizeof(PtRaw), sizeof(PtRaw), owned(r),
                                        cudaMemcpyDeviceToDevice, ctx->stream));
   } else {
-    if (hi > lo) ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, lo, hi - lo, count, (zk_g1*)(xchg + (size_t)rank * count)));
-    else ZK_CUDA(ctx, cudaMemsetAsync(xchg + (size_t)rank * count, 0, count * sizeof(PtRaw), ctx->stream));   // zz = 0: identity
-    ZK_TRY(zk_group_allgather(K->group, ctx, xchg, count * sizeof(PtRaw)));
+    PtRaw* mine = xchg + (size_t)rank * count;
+    if (hi > lo) {
+      if (fused) ctx->p2p = &pp;
+      ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, lo, hi - lo, count, (zk_g1*)mine));
+    } else {
+      ZK_CUDA(ctx, cudaMemsetAsync(mine, 0, count * sizeof(PtRaw), ctx->stream));   // zz = 0: identity
+    }
+    ZK_TRY(exchange(hi > lo, mine));
     ZK_TRY(zk_g1_sum_strided_dev(ctx, (const zk_g1*)xchg, world, count, (zk_g1*)out));
   }
   return ZK_OK;
@@ -684,8 +709,10 @@ extern "C" int zk_keygen(zk_ctx* ctx, const zk_circuit_desc* cd, const zk_fr* co
   KG(dev_alloc(K, &K->d_lookup_polys, (size_t)D.n_lookups * 3 * nb));
   KG(dev_alloc(K, &K->d_perm_z_polys, K->n_sets * nb));
   KG(dev_alloc(K, &K->d_instance, D.n_instance * nb)); KG(dev_alloc(K, &K->d_instance_polys, D.n_instance * nb));
-  KG(dev_alloc(K, &K->d_lookup, (size_t)D.n_lookups * 5 * nb));
-  KG(dev_alloc(K, &K->d_perm_z, K->n_sets * nb));
+  // the permutation products sit right behind plane 4 (Z) of the lookup area, so that [lookup Z | permutation z] is ONE
+  // contiguous batch for the commitment (no challenge separates the two: both follow beta / gamma)
+  KG(dev_alloc(K, &K->d_lookup, ((size_t)D.n_lookups * 5 + K->n_sets) * nb));
+  K->d_perm_z = K->d_lookup + (size_t)D.n_lookups * 5 * nb;
   KG(dev_alloc(K, &K->d_random, nb)); KG(dev_alloc(K, &K->d_hext, K->ext_n * 32));
   KG(dev_alloc(K, &K->d_hpieces, (size_t)(D.degree - 1) * nb));
   KG(dev_alloc(K, &K->d_hpoly, nb)); KG(dev_alloc(K, &K->d_hx, nb)); KG(dev_alloc(K, &K->d_lx, nb));
@@ -987,6 +1014,9 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     return c.column_type == ZK_COL_ADVICE ? K->d_advice + c.index * nb : c.column_type == ZK_COL_FIXED ? K->d_fixed_values + c.index * nb
                                                                                                       : K->d_instance + c.index * nb;
   };
+  // single GPU: the permutation and lookup products are committed together (17 columns for the QE3 shape) -- one call's
+  // fixed latency less; a group keeps its two differently sharded commitments
+  const bool merged_products = K->n_sets && L && !(K->group && zk_group_world(K->group) > 1) && !getenv("ZK_PROVER_SPLIT_PRODUCTS");
   if (K->n_sets) {
     // every column set at once: z_s = seed_s * (exclusive prefix products of num/den), seed_{s+1} = z_s[usable]
     const uint32_t NS = K->n_sets;
@@ -1022,9 +1052,11 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     ZK_TRY(side(2, [&](zk_domain* d, zk_ctx* on) -> int {
       return transform_columns(K, d, on, K->d_perm_z, K->d_perm_z_polys, NS, [&](size_t i) { return slot_z((uint32_t)i); });
     }));
-    std::vector<HostPoint> pts;
-    ZK_TRY(commit(K, K->d_perm_z, NS, ZK_BASES_G_LAGRANGE, &pts));
-    ZK_TRY(write_points(pts));
+    if (!merged_products) {
+      std::vector<HostPoint> pts;
+      ZK_TRY(commit(K, K->d_perm_z, NS, ZK_BASES_G_LAGRANGE, &pts));
+      ZK_TRY(write_points(pts));
+    }
   }
 
   // ---- lookups: commit_product (own lookups only in a group) -------------------------------------------------------------------
@@ -1046,11 +1078,20 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       for (uint32_t l = 0; l < L; l++) jobs.push_back({lk(l, 4), lkp(l, 2), slot_lk(l, 0), lookup_owner(l)});
       return transform_jobs(K, d, on, jobs);
     }));
-    std::vector<CommitJob> cj;
-    for (uint32_t l = 0; l < L; l++) cj.push_back({lk(l, 4), lookup_owner(l)});
-    std::vector<HostPoint> pts;
-    ZK_TRY(commit_jobs(K, cj, ZK_BASES_G_LAGRANGE, &pts));
-    ZK_TRY(write_points(pts));
+    if (merged_products) {
+      // one batch of L + n_sets columns; the transcript takes the permutation points first
+      std::vector<HostPoint> pts;
+      ZK_TRY(commit(K, lk(0, 4), L + K->n_sets, ZK_BASES_G_LAGRANGE, &pts));
+      std::vector<HostPoint> perm(pts.begin() + L, pts.end()), look(pts.begin(), pts.begin() + L);
+      ZK_TRY(write_points(perm));
+      ZK_TRY(write_points(look));
+    } else {
+      std::vector<CommitJob> cj;
+      for (uint32_t l = 0; l < L; l++) cj.push_back({lk(l, 4), lookup_owner(l)});
+      std::vector<HostPoint> pts;
+      ZK_TRY(commit_jobs(K, cj, ZK_BASES_G_LAGRANGE, &pts));
+      ZK_TRY(write_points(pts));
+    }
   }
 
   // ---- vanishing.commit: random polynomial ------------------------------------------------------------------------------------
