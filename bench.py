@@ -111,6 +111,9 @@ def parse():
     ap.add_argument("--streams", type=int, default=3, help="1 = one stream, 3 = commitments on two streams + NTT/h(X) on a third")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-max", type=int, default=24)
+    ap.add_argument("--sweep-min", type=int, default=16)
+    ap.add_argument("--sweep-oracle-max", type=int, default=22, help="largest k whose MSM is checked against the oracle's best_multiexp")
+    ap.add_argument("--sweep-coset-max", type=int, default=24)
     ap.add_argument("--sweep-classes", action="store_true",
                     help="sweep mode: also time the resident MSM on 88-bit scalars and on 90 %% zero / small scalars (SURVEY 8d config 3)")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-proof / one-MSM-over-all-GPUs measurements")
@@ -513,8 +516,13 @@ class ProofWorkload:
     def _program_stats(self):
         m, c = C.c_uint64(), C.c_uint64()
         lib = self.ctx.lib
-        self.ctx.check(lib.zk_pk_program_stats(C.c_void_p(lib.zk_pkey_pk(self.key.h)), C.byref(m), C.byref(c)))
-        return {"muls_per_row": m.value, "columns_read": c.value}
+        pk = C.c_void_p(lib.zk_pkey_pk(self.key.h))
+        self.ctx.check(lib.zk_pk_program_stats(pk, C.byref(m), C.byref(c)))
+        secs = C.c_double()
+        log = lib.zk_pk_evaluator_log(pk, C.byref(secs))
+        return {"muls_per_row": m.value, "columns_read": c.value,
+                "evaluator": "generated (NVRTC, sm_100a)" if lib.zk_pk_evaluator_kind(pk) else "interpreter",
+                "evaluator_note": (log or b"").decode()[:200], "nvrtc_compile_s": secs.value}
 
     def step(self):
         A = self.counts["advice"]
@@ -1007,10 +1015,8 @@ def main():
         ach = bytes_step / launches_per_step / (per_launch_ms * 1e-3) / 1e9
         prof = ncu.get(dom_name) or {}
         traffic = None
-        if prof.get("dram_bytes_per_bucket_addition") and dom_name == "msm_accumulate" and bucket_adds_step:
-            traffic = prof["dram_bytes_per_bucket_addition"] * bucket_adds_step / launches_per_step
-        elif prof.get("dram_bytes_per_launch") and prof.get("k") == args.k:
-            traffic = prof["dram_bytes_per_launch"]
+        if prof.get("dram_bytes_per_launch") and prof.get("k") == args.k:
+            traffic = prof["dram_bytes_per_launch"]      # mean over the launches of this kernel in ONE captured proof
         roof = {"kernel": dom_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic,
                 "traffic_source": (prof.get("source") if traffic else None), "peak_source": peak_src,
@@ -1046,6 +1052,8 @@ def main():
         int_pipe["msm_accumulate"] = acc
         if roof and roof["kernel"] == "msm_accumulate":
             roof["int_pipe"] = acc
+            if roof.get("traffic"):
+                roof["dram_bytes_per_bucket_addition_from_profile"] = roof["traffic"] * fam["msm_accumulate"]["launches"] / args.steps / bucket_adds_step
 
     import hashlib
     cpu = None
@@ -1082,6 +1090,7 @@ def main():
             "kernels": fam, "cpu_baseline": cpu, "batch": batch, "proof_verified": verified,
             "sharded_proof": sharded_proof, "sharded_msm": sharded_msm}
     if full:
+        line["evaluate_h"] = wl.pk_stats
         line["keygen_s"] = wl.keygen_s
         line["proof_sha256"] = hashlib.sha256(proof_plain).hexdigest()
         line["proof_bytes"] = len(proof_plain)
@@ -1236,34 +1245,64 @@ def measure_dropin(args, zk, shapes, torch, local_rank, wl_proof):
 
 
 def sweep(args, zk, torch, dev, local_rank):
-    """MSM Gpts/s and NTT GB/s sweeps (BASELINE configs[2], [3]); one JSON line per size."""
+    """MSM Gpts/s and NTT / coset-NTT GB/s sweeps (BASELINE configs[2], [3]); one JSON line per size, EVERY timed result
+    checked (the checker is the CPU oracle -- never inside a timed region):
+      MSM   k <= --sweep-oracle-max: bit-exact against the oracle's best_multiexp on the downloaded bases and scalars;
+            above: the bases are r_i * G with known r_i, so sum s_i * (r_i * G) must equal (sum s_i * r_i) * G -- the dot
+            product and the single scalar multiplication are done by the oracle (exact, size independent)
+      NTT   k <= 22: bit-exact against the oracle's best_fft; above: spot evaluations f[i] = poly(omega^i) by the oracle
+      coset k <= 20: bit-exact against the oracle's coeff_to_extended; above: spot evaluations at zeta * omega_ext^i"""
     h2 = __import__("importlib").import_module("zk-dcap-verifier_b200.halo2")
+    from oracle import oracle as orc
+    from oracle import pymodel as pm
     ctx = zk.Context(local_rank, work_stream(torch, dev))
     gen = torch.Generator(device=dev); gen.manual_seed(0x5CA1A4)
     G = np.concatenate([zk.fq_to_limbs(1), zk.fq_to_limbs(2)])
     R_MOD = h2.R_MOD
     root = pow(7, (R_MOD - 1) >> 28, R_MOD)
-    for k in range(16, args.sweep_max + 1):
+    one = zk.fr_to_limbs(1)
+    host = lambda t: t.cpu().numpy().view(np.uint64)
+    aff = lambda g1: orc.g1_to_affine(np.asarray(g1, dtype=np.uint64).reshape(-1, 12))
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def msm_expected(sc_h, pts_h, r_h, k):
+        if k <= args.sweep_oracle_max:
+            return aff(orc.best_multiexp(sc_h, pts_h)), "exact: oracle best_multiexp"
+        dot = orc.eval_polynomial(orc.field_op("fr", "mul", sc_h, r_h), one)       # sum s_i * r_i  (Horner at 1)
+        return aff(orc.g1_mul(G, dot)), "exact: sum s_i*(r_i*G) == (sum s_i*r_i)*G, dot product and scalar multiplication by the oracle"
+
+    for k in range(args.sweep_min, args.sweep_max + 1):
         n = 1 << k
         sc = rand_fr(torch, n, dev, gen)
+        rs = rand_fr(torch, n, dev, gen)                   # discrete logs of the bases
         pts = torch.empty((n, 8), dtype=torch.int64, device=dev)
-        h2.fixed_base_mul_dev(ctx, G, sc.data_ptr(), n, pts.data_ptr())
+        h2.fixed_base_mul_dev(ctx, G, rs.data_ptr(), n, pts.data_ptr())
         h2.srs_upload_dev(ctx, k, pts.data_ptr(), pts.data_ptr(), precompute=True)
         params = h2.ResidentParams(ctx, k)
+        cw = (C.c_uint32(), C.c_uint32())
+        ctx.check(ctx.lib.zk_srs_window(ctx.h, 2, C.byref(cw[0]), C.byref(cw[1])))
         out = torch.empty((1, 12), dtype=torch.int64, device=dev)
-        res = {"k": k}
+        res = {"k": k, "window_bits": cw[0].value, "windows": cw[1].value}
+        sc_h, r_h = host(sc).reshape(n, 4), host(rs).reshape(n, 4)
+        pts_h = host(pts).reshape(n, 8) if k <= args.sweep_oracle_max else None
+        want, how = msm_expected(sc_h, pts_h, r_h, k)
+        ok = True
         for name, fn in (("msm_resident", lambda: h2.commit_dev(params, sc.data_ptr(), 1, out.data_ptr(), lagrange=True)),
                          ("msm_plain", lambda: h2.msm_dev(ctx, sc.data_ptr(), pts.data_ptr(), n, out.data_ptr()))):
-            for _ in range(3):
-                fn()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); e0.record()
-            reps = 5
-            for _ in range(reps):
-                fn()
-            e1.record(); torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / reps
+            ms = timed(fn)
             res[name + "_ms"] = ms; res[name + "_Gpts_s"] = n / (ms * 1e-3) / 1e9
+            good = bool(np.array_equal(aff(host(out)), want))
+            res[name + "_parity"] = how if good else "MISMATCH"
+            ok = ok and good
         if args.sweep_classes and k <= 24:
             # SURVEY 8d config 3 (ii), (iii): canonical values built on the host, converted to Montgomery form by the library
             rng = np.random.default_rng(0x5CA1A4 + k)
@@ -1279,32 +1318,56 @@ def sweep(args, zk, torch, dev, local_rank):
                     raw[big] = rand_fr_host(rng, int(big.sum()))
                 mont = ctx.field_op("fr", "to_mont", np.ascontiguousarray(raw))
                 sc_c = torch.from_numpy(mont.view(np.int64)).to(dev)
-                fn = lambda: h2.commit_dev(params, sc_c.data_ptr(), 1, out.data_ptr(), lagrange=True)
-                for _ in range(3):
-                    fn()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize(); e0.record()
-                for _ in range(5):
-                    fn()
-                e1.record(); torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / 5
+                ms = timed(lambda: h2.commit_dev(params, sc_c.data_ptr(), 1, out.data_ptr(), lagrange=True))
                 res["msm_resident_%s_ms" % cname] = ms
                 res["msm_resident_%s_Gpts_s" % cname] = n / (ms * 1e-3) / 1e9
+                want_c, how_c = msm_expected(mont, pts_h, r_h, k)
+                good = bool(np.array_equal(aff(host(out)), want_c))
+                res["msm_resident_%s_parity" % cname] = how_c if good else "MISMATCH"
+                ok = ok and good
                 del sc_c
-        omega = zk.fr_to_limbs(pow(root, 1 << (28 - k), R_MOD))
+        del pts, rs, pts_h, r_h
+        # ---- best_fft ------------------------------------------------------------------------------------------------
+        w = pow(root, 1 << (28 - k), R_MOD)
+        omega = zk.fr_to_limbs(w)
         a = rand_fr(torch, n, dev, gen)
-        for _ in range(3):
-            h2.ntt_dev(ctx, a.data_ptr(), omega, k)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record()
-        for _ in range(5):
-            h2.ntt_dev(ctx, a.data_ptr(), omega, k)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
+        a_h = host(a).reshape(n, 4).copy()
+        work = a.clone()
+        ms = timed(lambda: h2.ntt_dev(ctx, work.data_ptr(), omega, k))
         res["ntt_ms"] = ms; res["ntt_GB_s"] = 64 * n / (ms * 1e-3) / 1e9
         res["ntt_Gmul_s"] = (n // 2) * k / (ms * 1e-3) / 1e9
+        work.copy_(a)
+        h2.ntt_dev(ctx, work.data_ptr(), omega, k)
+        f = host(work).reshape(n, 4)
+        if k <= 22:
+            good = bool(np.array_equal(f, orc.best_fft(a_h, omega, k))); how = "exact: oracle best_fft"
+        else:
+            good = all(np.array_equal(orc.eval_polynomial(a_h, zk.fr_to_limbs(pow(w, i, R_MOD))), f[i]) for i in (0, 1, n // 2 + 7, n - 1))
+            how = "spot: 4 outputs equal the oracle's evaluation of the input polynomial at omega^i"
+        res["ntt_parity"] = how if good else "MISMATCH"
+        ok = ok and good
+        del work
+        # ---- coeff_to_extended (coset NTT k -> k + 2, the transform evaluate_h's inputs take) ------------------------
+        if k + 2 <= 28 and k <= args.sweep_coset_max:
+            dom = zk.EvaluationDomain(5, k, ctx)
+            ext = torch.empty((4 * n, 4), dtype=torch.int64, device=dev)
+            ms = timed(lambda: h2.coeff_to_extended_dev(dom, a.data_ptr(), ext.data_ptr(), 1))
+            res["coset_ntt_ms"] = ms; res["coset_ntt_GB_s"] = (32 * n + 32 * 4 * n) / (ms * 1e-3) / 1e9
+            e_h = host(ext).reshape(4 * n, 4)
+            if k <= 20:
+                good = bool(np.array_equal(e_h, orc.Domain(5, k).coeff_to_extended(a_h))); how = "exact: oracle coeff_to_extended"
+            else:
+                we = pow(root, 1 << (28 - (k + 2)), R_MOD)
+                good = all(np.array_equal(orc.eval_polynomial(a_h, zk.fr_to_limbs(pm.ZETA * pow(we, i, R_MOD) % R_MOD)), e_h[i])
+                           for i in (0, 1, 2 * n + 5, 4 * n - 1))
+                how = "spot: 4 outputs equal the oracle's evaluation at zeta * omega_ext^i"
+            res["coset_ntt_parity"] = how if good else "MISMATCH"
+            ok = ok and good
+            del ext, dom
+        res["parity"] = "exact" if ok else "MISMATCH"
         emit(res)
-        del sc, pts, a
+        del sc, a
+        torch.cuda.empty_cache()
     return 0
 
 

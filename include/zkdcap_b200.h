@@ -285,6 +285,17 @@ zk_domain* zk_pk_domain(zk_pk* pk);
  * the number of distinct extended columns it reads (roofline bookkeeping). */
 int zk_pk_program_stats(const zk_pk* pk, uint64_t* muls_per_row, uint64_t* columns_read);
 
+/* evaluate_h is COMPILED from the circuit's expression graphs: zk_pk_upload (and zk_keygen through it) emits straight-line
+ * CUDA C++ for the optimised program and compiles it with NVRTC for sm_100a; the word-stream interpreter remains as the
+ * checked reference (ZK_EVALH=interp selects it; it also takes over when NVRTC is unavailable).
+ *   zk_evalh_generate_source  the generated text (host_flavour != 0: the same statements as a plain C++ function, for CPU
+ *                             tests); buf may be NULL to query the length.  Host only.
+ *   zk_pk_evaluator_kind      1 = generated kernel in use, 0 = interpreter
+ *   zk_pk_evaluator_log       why not ("" when it is); *compile_seconds = NVRTC time at key generation */
+int zk_evalh_generate_source(const zk_evaluator_desc* desc, int host_flavour, char* buf, size_t cap, size_t* len);
+int zk_pk_evaluator_kind(const zk_pk* pk);
+const char* zk_pk_evaluator_log(const zk_pk* pk, double* compile_seconds);
+
 /* Evaluator::evaluate_h for one circuit instance.  Polynomials are in
  * coefficient form (n each), host pointers:
  *   advice_polys[n_advice], instance_polys[n_instance], challenges[n_challenges],

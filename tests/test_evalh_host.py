@@ -228,3 +228,77 @@ def test_graph_evaluator_dedup_rules():
     assert g.calculations[-1][0][0] == "Sub"
     assert g.add_expression(-E.Constant(5)) == (_abi.VS_CONSTANT, g.constants.index(pm.R_MOD - 5), 0)
     assert g.constants[:3] == [0, 1, 2] and g.rotations == [0, 1]
+
+
+# ---- evaluate_h as GENERATED code (csrc/evalh_codegen.hpp) ----------------------------------------------------------------------
+def generated_source(desc, host):
+    lib = zk._abi.load()
+    ln = C.c_size_t()
+    assert lib.zk_evalh_generate_source(C.byref(desc), 1 if host else 0, None, 0, C.byref(ln)) == 0
+    buf = C.create_string_buffer(ln.value + 1)
+    assert lib.zk_evalh_generate_source(C.byref(desc), 1 if host else 0, buf, ln.value + 1, C.byref(ln)) == 0
+    return buf.value.decode()
+
+
+def host_generated_h(cs, k, case, desc, tmp_path):
+    """compile the host flavour of the generated text with g++ and run every extended row"""
+    import subprocess
+    src = generated_source(desc, host=True)
+    cpath, so = tmp_path / "evalh_gen.cpp", tmp_path / "evalh_gen.so"
+    cpath.write_text(src)
+    inc = os.path.join(os.path.dirname(HERE), "zk-dcap-verifier_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-I", inc, "-o", str(so), str(cpath)])
+    gen = C.CDLL(str(so))
+    dom = case["dom"]
+    ext = dom.coeff_to_extended
+    cols = list(case["fixed_cosets"]) + [ext(p) for p in case["advice"]] + [ext(p) for p in case["instance"]]
+    cols += list(case["sigma_cosets"]) + [ext(p) for p in case["z_polys"]]
+    cols += [ext(p) for t in case["lookup_polys"] for p in t]
+    cols += [case["l0"], case["l_last"], case["l_active"]]
+    cols = [np.ascontiguousarray(c) for c in cols]
+    tab = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    ch = pm.to_mont_limbs(case["challenges"], pm.R_MOD) if case["challenges"] else np.zeros((1, 4), np.uint64)
+    beta = case["beta"]
+    sc = pm.to_mont_limbs([beta, case["gamma"], case["theta"], case["y"], beta * pm.ZETA % pm.R_MOD, pm.DELTA, 1], pm.R_MOD)
+    out = np.zeros((dom.ext_n, 4), dtype=np.uint64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    gen.zk_evalh_gen_host(tab, p(ch), p(np.ascontiguousarray(sc)), p(np.ascontiguousarray(dom.extended_omega)), p(out),
+                          C.c_size_t(0), C.c_size_t(dom.ext_n))
+    return out, src
+
+
+@pytest.mark.parametrize("shape,k", [("toy_shape", 3), ("qe3_shape", 4)])
+def test_generated_evaluator_equals_oracle_on_host(orc, tmp_path, shape, k):
+    """the text zk_pk_upload hands to NVRTC, compiled for the CPU instead: every row equals the oracle's evaluate_h"""
+    cs = getattr(shapes, shape)()
+    case = make_case(cs, k, 21, orc)
+    want, desc, keep = oracle_h(orc, cs, k, case)
+    got, src = host_generated_h(cs, k, case, desc, tmp_path)
+    assert np.array_equal(got, want)
+    assert "ev_fma" in src and "zk_evalh_gen_host" in src
+
+
+def test_generated_evaluator_compiles_for_sm_100a():
+    """NVRTC (libnvrtc.so.12 of the toolkit; no GPU needed) accepts the device flavour for sm_100a"""
+    try:
+        nv = C.CDLL("libnvrtc.so.12")
+    except OSError:
+        pytest.skip("libnvrtc.so.12 not loadable")
+    cs = shapes.qe3_shape()
+    desc, keep = zk.Evaluator.new(cs).describe(cs, 10)
+    src = generated_source(desc, host=False).encode()
+    prog = C.c_void_p()
+    assert nv.nvrtcCreateProgram(C.byref(prog), src, b"zk_evalh_gen.cu", 0, None, None) == 0
+    opts = (C.c_char_p * 3)(b"--gpu-architecture=sm_100a", b"-std=c++17", b"-lineinfo")
+    rc = nv.nvrtcCompileProgram(prog, 3, opts)
+    if rc != 0:
+        ls = C.c_size_t()
+        nv.nvrtcGetProgramLogSize(prog, C.byref(ls))
+        log = C.create_string_buffer(ls.value + 1)
+        nv.nvrtcGetProgramLog(prog, log)
+        raise AssertionError(log.value.decode()[-3000:])
+    cs_ = C.c_size_t()
+    assert nv.nvrtcGetCUBINSize(prog, C.byref(cs_)) == 0 and cs_.value > 10000
+    cubin = C.create_string_buffer(cs_.value)
+    assert nv.nvrtcGetCUBIN(prog, cubin) == 0
+    assert b"zk_evalh_gen" in cubin.raw

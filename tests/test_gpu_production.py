@@ -207,3 +207,27 @@ def test_srs_file_to_verified_proof(ctx, fmt):
         zk.verify_proof(case["circ"], fc, pcm, g1, params.g2, params.s_g2, case["instances_limbs"], proof) if fmt != "raw_bytes" else \
             zk.verify_proof(case["circ"], fc, pcm, g1, params.g2[:64], params.s_g2[:64], case["instances_limbs"], proof)
     assert params.write(fmt=fmt) == data
+
+
+def test_generated_evaluator_is_in_use_and_matches_the_interpreter(ctx, orc):
+    """evaluate_h runs the circuit's own NVRTC-compiled kernel (csrc/evalh_codegen.hpp); the interpreter (ZK_EVALH=interp)
+    and the CPU oracle give the same rows"""
+    import ctypes as C
+    from importlib import import_module
+    from tests.test_evalh_host import make_case, oracle_h, L
+    shapes = import_module("zk-dcap-verifier_b200.shapes")
+    cs, k = shapes.qe3_shape(), 8
+    case = make_case(cs, k, 33, orc)
+    want, desc, keep = oracle_h(orc, cs, k, case)
+    ch = pm.to_mont_limbs(case["challenges"], pm.R_MOD) if case["challenges"] else []
+    got = {}
+    for mode in ("generated", "interp"):
+        with env(ZK_EVALH="interp" if mode == "interp" else "auto"):
+            pk = zk.ProvingKey(cs, k, case["fixed_cosets"], case["sigma_cosets"], case["l0"], case["l_last"], case["l_active"], ctx=ctx)
+        kind = ctx.lib.zk_pk_evaluator_kind(pk.h)
+        secs = C.c_double()
+        note = ctx.lib.zk_pk_evaluator_log(pk.h, C.byref(secs))
+        assert kind == (1 if mode == "generated" else 0), note
+        got[mode] = pk.evaluate_h(case["advice"], case["instance"], ch, L(case["y"]), L(case["beta"]), L(case["gamma"]),
+                                  L(case["theta"]), case["lookup_polys"], case["z_polys"])
+        assert np.array_equal(got[mode], want), mode

@@ -89,7 +89,7 @@ SYMBOLS = [
     "zk_divide_by_vanishing_poly",
     "zk_lagrange_to_coeff_dev", "zk_coeff_to_lagrange_dev", "zk_coeff_to_extended_dev", "zk_extended_to_coeff_dev",
     "zk_divide_by_vanishing_poly_dev",
-    "zk_pk_upload", "zk_pk_destroy", "zk_pk_domain", "zk_pk_program_stats",
+    "zk_pk_upload", "zk_pk_destroy", "zk_pk_domain", "zk_pk_program_stats", "zk_evalh_generate_source", "zk_pk_evaluator_kind", "zk_pk_evaluator_log",
     "zk_evaluate_h", "zk_evaluate_h_dev",
     "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_pkey_aux_ctx", "zk_pkey_set_transcript", "zk_proof_randoms", "zk_proof_max_bytes",
     "zk_create_proof", "zk_verify_proof", "zk_g2_decode", "zk_g2_encode",
@@ -165,6 +165,9 @@ def load():
         "zk_pk_destroy": (None, [vp]),
         "zk_pk_domain": (vp, [vp]),
         "zk_pk_program_stats": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "zk_evalh_generate_source": (i32, [C.POINTER(zk_evaluator_desc), i32, vp, sz, C.POINTER(sz)]),
+        "zk_pk_evaluator_kind": (i32, [vp]),
+        "zk_pk_evaluator_log": (C.c_char_p, [vp, C.POINTER(C.c_double)]),
         "zk_evaluate_h": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "zk_evaluate_h_dev": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "zk_keygen": (i32, [vp, C.POINTER(zk_circuit_desc), vp, vp, C.POINTER(vp)]),

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libzkdcap_b200.so")
 SOURCES = ["api.cu", "ntt.cu", "msm.cu", "evalh.cu", "prover.cu", "group.cu", "params.cu", "verifier.cu"]
-HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", "evalh.cuh", "evalh_compile.hpp", "prover_kernels.cuh", "transcript.hpp", os.path.join("..", "..", "include", "zkdcap_b200.h")]
+HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", "evalh.cuh", "evalh_compile.hpp", "evalh_codegen.hpp", "prover_kernels.cuh", "transcript.hpp", os.path.join("..", "..", "include", "zkdcap_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("ZK_NVCC_EXTRA", "").split()
@@ -21,8 +21,21 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def embed_ff():
+    """csrc/ff.cuh as a C++ raw string literal (build/ff_embed.inc): the prelude of the evaluate_h kernels that evalh.cu
+    generates and compiles with NVRTC at key generation"""
+    src = open(os.path.join(CSRC, "ff.cuh")).read().replace("#include <stdint.h>", "")
+    out = os.path.join(HERE, "build", "ff_embed.inc")
+    text = 'R"ZKFF(' + src + ')ZKFF"\n'
+    if not os.path.exists(out) or open(out).read() != text:
+        with open(out, "w") as f:
+            f.write(text)
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    embed_ff()
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs, jobs = [], []
     for s in SOURCES:

@@ -4,10 +4,17 @@
 // @ c254c75f), called from create_proof (circuits/src/sgx_dcap_verifier.rs:814).
 #include <stdlib.h>
 
+#include <dlfcn.h>
+
 #include "common.cuh"
-#include "evalh_compile.hpp"
+#include "evalh_codegen.hpp"
 
 using namespace zk;
+
+// csrc/ff.cuh as text (written by build.py): the prelude of the generated evaluate_h kernels
+static const char kFfSource[] =
+#include "../build/ff_embed.inc"
+    ;
 
 struct zk_pk {
   zk_ctx* ctx = nullptr;
@@ -22,6 +29,12 @@ struct zk_pk {
   const void** d_cols = nullptr;  // device copy of the column pointer table
   void* d_challenges = nullptr;
   size_t n_resident = 0, n_witness = 0;
+  // the circuit's own evaluate_h kernel: generated source (evalh_codegen.hpp) compiled with NVRTC at key generation
+  cudaLibrary_t gen_lib = nullptr;
+  cudaKernel_t gen_kernel = nullptr;
+  void* d_gen_sc = nullptr;       // beta, gamma, theta, y, delta_start, delta, one
+  std::string gen_log;            // why the generated kernel is not in use (empty when it is)
+  double gen_compile_s = 0;
 };
 
 namespace {
@@ -54,6 +67,63 @@ __global__ void k_l_active(const uint4* l_last, uint4* l_blind_inout, size_t n) 
   (Fr::one() - (Fr::load(l_last + 2 * i) + Fr::load(l_blind_inout + 2 * i))).store(l_blind_inout + 2 * i);
 }
 
+// ---- NVRTC, bound at run time (libnvrtc.so.12 ships with the CUDA toolkit of this image) --------------------------------
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Nvrtc {
+  void* lib = nullptr;
+  int (*create)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*compile)(nvrtcProgram, int, const char* const*) = nullptr;
+  int (*cubin_size)(nvrtcProgram, size_t*) = nullptr;
+  int (*cubin)(nvrtcProgram, char*) = nullptr;
+  int (*log_size)(nvrtcProgram, size_t*) = nullptr;
+  int (*log)(nvrtcProgram, char*) = nullptr;
+  int (*destroy)(nvrtcProgram*) = nullptr;
+};
+Nvrtc* nvrtc() {
+  static Nvrtc N;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+      N.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (N.lib) break;
+    }
+    if (N.lib) {
+      N.create = (decltype(N.create))dlsym(N.lib, "nvrtcCreateProgram");
+      N.compile = (decltype(N.compile))dlsym(N.lib, "nvrtcCompileProgram");
+      N.cubin_size = (decltype(N.cubin_size))dlsym(N.lib, "nvrtcGetCUBINSize");
+      N.cubin = (decltype(N.cubin))dlsym(N.lib, "nvrtcGetCUBIN");
+      N.log_size = (decltype(N.log_size))dlsym(N.lib, "nvrtcGetProgramLogSize");
+      N.log = (decltype(N.log))dlsym(N.lib, "nvrtcGetProgramLog");
+      N.destroy = (decltype(N.destroy))dlsym(N.lib, "nvrtcDestroyProgram");
+      if (!N.create || !N.compile || !N.cubin_size || !N.cubin || !N.destroy) N.lib = nullptr;
+    }
+  }
+  return N.lib ? &N : nullptr;
+}
+// source -> sm_100a cubin; empty vector + `log` on failure
+std::vector<char> nvrtc_compile(const std::string& src, std::string& log) {
+  std::vector<char> out;
+  Nvrtc* N = nvrtc();
+  if (!N) { log = "libnvrtc.so.12 not found"; return out; }
+  nvrtcProgram prog = nullptr;
+  if (N->create(&prog, src.c_str(), "zk_evalh_gen.cu", 0, nullptr, nullptr) != 0) { log = "nvrtcCreateProgram failed"; return out; }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+  int rc = N->compile(prog, 3, opts);          // -default-device is not needed: every function is annotated
+  if (rc != 0) {
+    size_t ls = 0;
+    if (N->log_size && N->log && N->log_size(prog, &ls) == 0 && ls > 1) { log.resize(ls); N->log(prog, &log[0]); }
+    else log = "nvrtcCompileProgram failed";
+    N->destroy(&prog);
+    return out;
+  }
+  size_t cs = 0;
+  if (N->cubin_size(prog, &cs) == 0 && cs) { out.resize(cs); if (N->cubin(prog, out.data()) != 0) out.clear(); }
+  if (out.empty()) log = "nvrtcGetCUBIN failed";
+  N->destroy(&prog);
+  return out;
+}
+
 Fr fr_canon(const uint32_t c[8]) { Fr v; memcpy(v.l, c, 32); return v.to_mont(); }
 Fr fr_host(const zk_fr* p) { Fr v; memcpy(v.l, p, 32); return v; }
 
@@ -70,10 +140,59 @@ extern "C" void zk_pk_destroy(zk_pk* pk) {
   cudaStreamSynchronize(pk->ctx->stream);
   cudaFree(pk->d_code); cudaFree(pk->d_consts); cudaFree(pk->d_resident); cudaFree(pk->d_witness);
   cudaFree(pk->d_stage); cudaFree((void*)pk->d_cols); cudaFree(pk->d_challenges);
+  if (pk->d_gen_sc) cudaFree(pk->d_gen_sc);
+  if (pk->gen_lib) cudaLibraryUnload(pk->gen_lib);
   if (pk->dom) zk_domain_destroy(pk->dom);
   delete pk;
 }
 extern "C" zk_domain* zk_pk_domain(zk_pk* pk) { return pk ? pk->dom : nullptr; }
+
+// The CUDA C++ text of a circuit's evaluate_h (what zk_pk_upload compiles with NVRTC); `host_flavour` != 0 gives the same
+// statements as a plain C++ function over a column pointer table (CPU tests).  Host only, no device needed.
+extern "C" int zk_evalh_generate_source(const zk_evaluator_desc* desc, int host_flavour, char* buf, size_t cap, size_t* len) {
+  if (!desc || !len) return ZK_ERR_ARG;
+  CompiledEval C;
+  if (!compile_program(*desc, C, true)) return ZK_ERR_ARG;
+  const std::string src = generate_evalh_source(C, *desc, host_flavour != 0, host_flavour ? std::string() : std::string(kFfSource));
+  *len = src.size();
+  if (buf) {
+    if (cap < src.size() + 1) return ZK_ERR_ARG;
+    memcpy(buf, src.c_str(), src.size() + 1);
+  }
+  return ZK_OK;
+}
+// 1 = the generated (NVRTC-compiled) kernel evaluates h(X) for this key, 0 = the interpreter
+extern "C" int zk_pk_evaluator_kind(const zk_pk* pk) { return pk && pk->gen_kernel ? 1 : 0; }
+// Why the generated kernel is not in use ("" when it is), and how long NVRTC took
+extern "C" const char* zk_pk_evaluator_log(const zk_pk* pk, double* compile_seconds) {
+  if (compile_seconds) *compile_seconds = pk ? pk->gen_compile_s : 0;
+  return pk ? pk->gen_log.c_str() : "null key";
+}
+
+namespace {
+// evaluate_h as generated code: emit, compile for sm_100a, load.  Any failure leaves the interpreter in charge.
+void build_generated_kernel(zk_pk* pk, const zk_evaluator_desc& desc) {
+  if (const char* v = getenv("ZK_EVALH")) if (!strcmp(v, "interp")) { pk->gen_log = "disabled by ZK_EVALH=interp"; return; }
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  const std::string src = generate_evalh_source(pk->C, desc, false, std::string(kFfSource));
+  std::string log;
+  std::vector<char> cubin = nvrtc_compile(src, log);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  pk->gen_compile_s = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+  if (cubin.empty()) { pk->gen_log = "NVRTC: " + log; return; }
+  if (cudaLibraryLoadData(&pk->gen_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+    pk->gen_log = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(cudaGetLastError()); pk->gen_lib = nullptr; return;
+  }
+  if (cudaLibraryGetKernel(&pk->gen_kernel, pk->gen_lib, "zk_evalh_gen") != cudaSuccess) {
+    pk->gen_log = std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(cudaGetLastError());
+    cudaLibraryUnload(pk->gen_lib); pk->gen_lib = nullptr; pk->gen_kernel = nullptr; return;
+  }
+  if (cudaMalloc(&pk->d_gen_sc, 7 * 32) != cudaSuccess) {
+    cudaGetLastError(); cudaLibraryUnload(pk->gen_lib); pk->gen_lib = nullptr; pk->gen_kernel = nullptr; pk->gen_log = "scalar buffer"; return;
+  }
+}
+}  // namespace
 extern "C" int zk_pk_program_stats(const zk_pk* pk, uint64_t* muls_per_row, uint64_t* columns_read) {
   if (!pk) return ZK_ERR_ARG;
   if (muls_per_row) *muls_per_row = pk->C.muls_per_row;
@@ -154,6 +273,7 @@ extern "C" int zk_pk_upload(zk_ctx* ctx, const zk_evaluator_desc* desc, const zk
   }
   PK_CUDA(cudaStreamSynchronize(ctx->stream));
 #undef PK_CUDA
+  build_generated_kernel(pk, *desc);
   *out = pk;
   return ZK_OK;
 }
@@ -196,6 +316,21 @@ int launch_evalh(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr
   if (row1 > E) row1 = E;
   if (row0 >= row1) return ZK_OK;
   unsigned grid = zk_div_up(row1 - row0, 128);
+  if (pk->gen_kernel) {
+    // the circuit's own compiled kernel: the seven scalars travel in a small buffer (staged copy of a stack array)
+    Fr scv[7] = {S.beta, S.gamma, S.theta, S.y, S.delta_start, S.delta, S.one};
+    ZK_CUDA(ctx, cudaMemcpyAsync(pk->d_gen_sc, scv, sizeof scv, cudaMemcpyHostToDevice, ctx->stream));
+    const uint4* a_res = (const uint4*)pk->d_resident; const uint4* a_wit = (const uint4*)pk->d_witness;
+    const uint4* a_ch = (const uint4*)pk->d_challenges; const uint4* a_sc = (const uint4*)pk->d_gen_sc;
+    uint4* a_out = (uint4*)d_out_ext;
+    unsigned long long a_r0 = row0, a_r1 = row1;
+    void* args[] = {&a_res, &a_wit, &a_ch, &a_sc, &tw, &a_out, &a_r0, &a_r1};
+    zk_timing_begin(ctx, "evaluate_h");
+    cudaError_t le = cudaLaunchKernel((const void*)pk->gen_kernel, dim3(grid), dim3(128), args, 0, ctx->stream);
+    zk_timing_end(ctx);
+    if (le != cudaSuccess) ZK_FAIL(ctx, ZK_ERR_CUDA, "launch generated evaluate_h: %s", cudaGetErrorString(le));
+    return ZK_OK;
+  }
   uint32_t ni = pk->C.max_intermediates;
   // measured on B200: the select-based register file (NI = 4) is slower than 16 L1-resident slots (21.5 vs 19.2 ms)
   uint32_t ni_min = 16;

@@ -229,8 +229,12 @@ constexpr int kWarpPassMaxT = 7;
 // coset / 1/N scaling on the first load and the last store: called, not inlined (8 more copies of the multiplier would
 // triple the kernel's code size for a path only the first and last pass take)
 __device__ __noinline__ Fr ntt_w_scale(Fr a, Fr b) { return a * b; }
-constexpr int kWarpPassThreads = 128;     // 4 independent warps per CTA, 5 CTAs per SM at <= 102 registers
-__global__ void __launch_bounds__(kWarpPassThreads, 5) k_ntt_pass_w(PassArgs A, PassConsts K) {
+constexpr int kWarpPassThreads = 128;     // 4 independent warps per CTA
+// MINB = resident CTAs per SM the register allocation is held to (5: <= 102 registers, 4: <= 128, 3: <= 168): more
+// registers let ptxas interleave the two independent multiplications of a lane (instruction-level parallelism on the
+// IMAD carry chains) at the price of fewer resident warps; ZK_NTT_W_CTAS selects, measured default below
+template <int MINB>
+__global__ void __launch_bounds__(kWarpPassThreads, MINB) k_ntt_pass_w(PassArgs A, PassConsts K) {
   const uint32_t lane = threadIdx.x & 31u, T = A.t, L = A.L, P = A.s0;
   const uint32_t cw_log = 7 - T, cw_mask = (1u << cw_log) - 1u;
   const size_t warp = (size_t)blockIdx.x * (kWarpPassThreads / 32) + (threadIdx.x >> 5);
@@ -392,9 +396,12 @@ int run_ntt(zk_ctx* ctx, const NttJob& J) {
   static const bool radix4 = getenv("ZK_NTT_RADIX4") && atoi(getenv("ZK_NTT_RADIX4")) == 1;
   ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass_t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  // warp-resident passes (no shared memory, no barriers) from 2^10 points on; ZK_NTT_SMEM=1 keeps the shared-memory passes
-  static const bool force_smem = getenv("ZK_NTT_SMEM") && atoi(getenv("ZK_NTT_SMEM")) == 1;
-  const bool warp_pass = !force_smem && L >= 10;
+  // ZK_NTT_WARP=1: warp-resident passes (register butterflies + shuffles, no shared memory, no barriers) from 2^10 points on.
+  // Measured on B200 inside the complete k = 19 proof: 35.9 ms of NTT per proof against 35.4 ms for the shared-memory passes
+  // (ncu, one 2^21 pass: fmaheavy 77.5 % vs 73.8 % active, the same 168 us -- the extra activity is the index arithmetic of
+  // the exchanges), so the shared-memory passes stay the default (profiles/r2_ncu_ntt_pass_{w,t}.txt).
+  static const bool want_warp = getenv("ZK_NTT_WARP") && atoi(getenv("ZK_NTT_WARP")) == 1;
+  const bool warp_pass = want_warp && L >= 10;
   const uint32_t max_t = warp_pass ? (uint32_t)kWarpPassMaxT : (uint32_t)kMaxT;
   uint32_t npass = L == 0 ? 1 : (L + max_t - 1) / max_t;
   uint32_t base_t = L / npass, extra = L % npass;   // first `extra` passes take one more stage
@@ -421,7 +428,10 @@ int run_ntt(zk_ctx* ctx, const NttJob& J) {
     A.post_mode = last ? J.post_mode : 0;
     if (warp_pass) {
       dim3 grid((unsigned)(N >> 9), (unsigned)J.count);           // 4 warps x 128 points per CTA
-      ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_w, grid, kWarpPassThreads, 0, A, J.K);
+      static const int minb = getenv("ZK_NTT_W_CTAS") ? atoi(getenv("ZK_NTT_W_CTAS")) : 4;
+      if (minb >= 5) { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_w<5>, grid, kWarpPassThreads, 0, A, J.K); }
+      else if (minb == 4) { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_w<4>, grid, kWarpPassThreads, 0, A, J.K); }
+      else { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_w<3>, grid, kWarpPassThreads, 0, A, J.K); }
     } else {
       size_t tile = (size_t)1 << (t + logC);
       dim3 grid((unsigned)(N >> (t + logC)), (unsigned)J.count);
