@@ -1170,14 +1170,15 @@ def measure_sharded_msm(args, zk, torch, dist, dev, rank, local_rank, world, bar
     h2.fixed_base_mul_dev(ctx, G, bs.data_ptr(), per, pts.data_ptr())
     h2.srs_upload_dev(ctx, ks, pts.data_ptr(), pts.data_ptr(), precompute=True)
     params = h2.ResidentParams(ctx, ks)
-    part = torch.empty((1, 12), dtype=torch.int64, device=dev)
-    gathered = torch.empty((world, 12), dtype=torch.int64, device=dev)
     out = torch.empty((1, 12), dtype=torch.int64, device=dev)
+    uid = [zk.Group.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    group = zk.Group(ctx, rank, world, uid[0])
 
     def step():
-        h2.commit_dev(params, sc.data_ptr(), 1, part.data_ptr(), lagrange=True)
-        dist.all_gather_into_tensor(gathered, part)
-        ctx.check(ctx.lib.zk_g1_sum_dev(ctx.h, C.c_void_p(gathered.data_ptr()), world, C.c_void_p(out.data_ptr())))
+        # zk_msm_sharded_dev: local Pippenger on the resident slice; its last kernel stores the partial point into every
+        # peer's window and raises a flag, the wait kernel gathers, one more kernel sums and normalises
+        group.msm_sharded_dev(sc.data_ptr(), per, out.data_ptr(), lagrange=True)
     for _ in range(3):
         step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1191,7 +1192,8 @@ def measure_sharded_msm(args, zk, torch, dist, dev, rank, local_rank, world, bar
     ms = float(t.item()) / reps
     res = {"k": k, "ms": ms, "Gpts_s": n / (ms * 1e-3) / 1e9, "n_gpus": world, "scaling": "strong",
            "bases": "resident per rank: slice of 2^%d bases with its own window table" % ks,
-           "exchange": "all-gather of one 96-byte point per rank (NCCL) + zk_g1_sum"}
+           "exchange": ("peer-to-peer: the MSM's last kernel stores its 128-byte partial point into every peer's window over NVLink and raises a "
+                        "flag; no collective call") if group.p2p else "NCCL all-gather of one 128-byte point per rank"}
     # single-GPU reference of the SAME MSM on rank 0: the slices one after the other on its own context
     if rank == 0:
         parts = torch.empty((world, 12), dtype=torch.int64, device=dev)
@@ -1211,10 +1213,12 @@ def measure_sharded_msm(args, zk, torch, dist, dev, rank, local_rank, world, bar
         single = torch.empty((1, 12), dtype=torch.int64, device=dev)
         ctx.check(ctx.lib.zk_g1_sum_dev(ctx.h, C.c_void_p(parts.data_ptr()), world, C.c_void_p(single.data_ptr())))
         torch.cuda.synchronize()
+        # `single` comes from zk_g1_sum over Jacobian records, `out` from the XYZZ sum: both normalised (z = 1)
         res["matches_single_gpu"] = bool(torch.equal(single, out))
         res["single_gpu_ms_slice_by_slice"] = t1
         res["result_point"] = [int(x) & 0xFFFFFFFFFFFFFFFF for x in out.cpu().view(-1).tolist()]
     barrier()
+    group.close()
     return res
 
 

@@ -423,6 +423,12 @@ uint32_t zk_group_world(const zk_group* g);
 int zk_group_p2p_enabled(const zk_group* g);
 /* Attach (or detach with NULL) a group: the key's proofs are then computed jointly.  The group must outlive its use. */
 int zk_pkey_set_group(zk_pkey* pk, zk_group* g);
+/* ONE MSM over the group's GPUs, sharded by contiguous base range (`zk_msm_sharded` of 8b): every rank has
+ * uploaded ITS slice of the bases as the context's resident SRS (zk_srs_upload*, window table per slice) and passes its slice
+ * of the scalars (device memory).  The partial points are exchanged by the MSM's own last kernel (stores into the peers'
+ * windows over NVLink + a flag; NCCL all-gather when the windows are unavailable) and summed on every rank:
+ * d_out = one normalised G1 (device), identical everywhere. */
+int zk_msm_sharded_dev(zk_group* g, const zk_fr* d_scalars, int which, size_t n_local, zk_g1* d_out);
 /* How `count` commitments over n bases are split: *mode 0 = rank commits columns [*lo, *hi) (every rank's share padded
  * to *per columns), *mode 1 = every rank commits all of them over the bases [*lo, *hi).  Pure host function. */
 void zk_group_shard_plan(uint32_t rank, uint32_t world, size_t count, size_t n, int* mode, size_t* per, size_t* lo, size_t* hi);

@@ -40,6 +40,23 @@ def main():
         opk = op.keygen(orc, p, case["circ"], case["fixed"], case["mapping"], case["circ"].transcript_repr)
         want = op.create_proof(orc, p, opk, case["circ"], case["advice"], case["instances_int"], case["randoms"])
         ok = ok and plain == want
+    # ONE MSM sharded by base range (zk_msm_sharded_dev): every rank holds its slice of the bases as its resident SRS
+    import numpy as np
+    km = 12
+    n = 1 << km
+    per = n // world
+    bases, scal = orc.gen_points(0x5A0 + km, n), orc.gen_scalars(0x5A1 + km, n)
+    ks = km - (world.bit_length() - 1)
+    sl = slice(rank * per, (rank + 1) * per)
+    zk.ParamsKZG(ks, bases[sl], bases[sl], ctx, precompute=True)
+    d_s = torch.from_numpy(np.ascontiguousarray(scal[sl]).view(np.int64)).cuda()
+    d_o = torch.zeros((1, 12), dtype=torch.int64, device="cuda")
+    for _ in range(3):                                      # repeated: the exchange windows alternate
+        grp.msm_sharded_dev(d_s.data_ptr(), per, d_o.data_ptr())
+    torch.cuda.synchronize()
+    got = d_o.cpu().numpy().view(np.uint64).reshape(12)
+    msm_ok = bool(np.array_equal(orc.g1_to_affine(got), orc.g1_to_affine(orc.best_multiexp(scal, bases))))
+    ok = ok and msm_ok
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -27,7 +27,7 @@ extern "C" int zk_ctx_create(int device, void* cuda_stream, zk_ctx** out) {
 }
 
 static void free_scratch(zk_scratch& s) { if (s.p) cudaFree(s.p); s.p = nullptr; s.cap = 0; }
-static void free_srs(zk_srs_set& s) { if (s.bases) cudaFree(s.bases); if (s.table) cudaFree(s.table); s = zk_srs_set(); }
+static void free_srs(zk_srs_set& s) { if (!s.alias) { if (s.bases) cudaFree(s.bases); if (s.table) cudaFree(s.table); } s = zk_srs_set(); }
 
 extern "C" void zk_ctx_destroy(zk_ctx* ctx) {
   if (!ctx) return;

@@ -16,6 +16,7 @@ struct zk_srs_set {
   void* bases = nullptr;       // n affine points (64 B each)
   void* table = nullptr;       // optional window table: W x n affine points, table[w][i] = 2^(c*w) * bases[i]
   int table_c = 0, table_w = 0;
+  bool alias = false;          // same memory as the other base set (g == g_lagrange was uploaded): never freed on its own
 };
 
 // Peer-to-peer exchange of small results inside a group of GPUs (group.cu): every rank maps every peer's exchange window

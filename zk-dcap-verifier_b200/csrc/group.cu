@@ -37,6 +37,7 @@ struct zk_group {
   void* comm = nullptr;      // collectives of the context's own stream
   void* comm2 = nullptr;     // collectives issued on another stream of the same device (the prover's transform stream)
   P2PWindow win[2];          // [0] exchanges on the context's stream, [1] on the second stream
+  char* msm_xchg = nullptr;  // world XYZZ records: the partial points of zk_msm_sharded_dev
 };
 
 namespace {
@@ -267,10 +268,45 @@ extern "C" int zk_group_create(zk_ctx* ctx, uint32_t rank, uint32_t world, const
 }
 extern "C" int zk_group_p2p_enabled(const zk_group* g) { return g && g->win[0].ok && g->win[1].ok ? 1 : 0; }
 
+int zk_xyzz_sum_normalised_dev(zk_ctx* ctx, const void* d_xyzz, size_t parts, zk_g1* d_out);      // msm.cu
+int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank);
+
+// ONE multi-scalar multiplication over the GPUs of a group, sharded by contiguous base range: every rank
+// keeps ITS slice of the bases resident (zk_srs_upload of the slice, with its own window table) and passes its slice of the
+// scalars; the partial point of each rank is produced by the usual Pippenger pipeline, whose last kernel stores it straight
+// into every peer's exchange window and raises a flag (no collective call); every rank then sums the `world` partial points
+// and normalises.  d_out: one normalised G1 (device), identical on every rank.
+extern "C" int zk_msm_sharded_dev(zk_group* g, const zk_fr* d_scalars, int which, size_t n_local, zk_g1* d_out) {
+  if (!g) return ZK_ERR_ARG;
+  zk_ctx* ctx = g->ctx;
+  if (!d_out || (n_local && !d_scalars)) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_msm_sharded_dev: bad argument");
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!g->msm_xchg) ZK_CUDA(ctx, cudaMalloc(&g->msm_xchg, (size_t)kZkMaxGroup * 128));
+  char* mine = g->msm_xchg + (size_t)g->rank * 128;
+  zk_p2p_push pp;
+  const bool fused = g->world > 1 && zk_group_p2p_begin(g, ctx, 128, &pp);
+  const bool old_raw = ctx->msm_raw;
+  ctx->msm_raw = true;
+  if (fused && n_local) ctx->p2p = &pp;
+  int r = zk_msm_batch_dev(ctx, d_scalars, which, n_local, 1, (zk_g1*)mine);
+  ctx->p2p = nullptr; ctx->msm_raw = old_raw;
+  if (r != ZK_OK) return r;
+  if (g->world > 1) {
+    if (fused) {
+      if (!n_local) ZK_TRY(zk_group_p2p_push(g, ctx, pp, mine, 128));       // the empty sum was written locally only
+      ZK_TRY(zk_group_p2p_finish(g, ctx, g->msm_xchg, 128));
+    } else {
+      ZK_TRY(zk_group_allgather(g, ctx, g->msm_xchg, 128));
+    }
+  }
+  return zk_xyzz_sum_normalised_dev(ctx, g->msm_xchg, g->world, d_out);
+}
+
 extern "C" void zk_group_destroy(zk_group* g) {
   if (!g) return;
   Nccl* N = nccl();
   cudaSetDevice(g->ctx->device); cudaDeviceSynchronize();
+  if (g->msm_xchg) cudaFree(g->msm_xchg);
   p2p_teardown(g);
   if (N && g->comm) {
     cudaSetDevice(g->ctx->device); cudaDeviceSynchronize();

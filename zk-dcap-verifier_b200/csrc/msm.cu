@@ -1019,7 +1019,9 @@ static int srs_install(zk_ctx* ctx, uint32_t k, const zk_g1_affine* g, const zk_
   zk_srs_set fresh[2];
   const zk_g1_affine* src[2] = {g, g_lagrange};
   int rc = ZK_OK;
-  for (int i = 0; i < 2 && rc == ZK_OK; i++) {
+  // the same array for both sets (single-MSM sweeps, sharded slices): one copy and one window table serve both
+  const int nsets = (g == g_lagrange) ? 1 : 2;
+  for (int i = 0; i < nsets && rc == ZK_OK; i++) {
     if (cudaMalloc(&fresh[i].bases, n * 64) != cudaSuccess) {
       cudaGetLastError();
       ctx->err = "zk_srs_upload: cannot allocate the base set"; rc = ZK_ERR_OOM; break;
@@ -1037,9 +1039,10 @@ static int srs_install(zk_ctx* ctx, uint32_t k, const zk_g1_affine* g, const zk_
     for (auto& f : fresh) { if (f.bases) cudaFree(f.bases); if (f.table) cudaFree(f.table); }
     return rc;
   }
+  if (nsets == 1) { fresh[1] = fresh[0]; fresh[1].alias = true; }
   zk_srs_set* sets[2] = {&ctx->srs_g, &ctx->srs_lagrange};
   for (int i = 0; i < 2; i++) {
-    if (!ctx->srs_borrowed) { if (sets[i]->bases) cudaFree(sets[i]->bases); if (sets[i]->table) cudaFree(sets[i]->table); }
+    if (!ctx->srs_borrowed && !sets[i]->alias) { if (sets[i]->bases) cudaFree(sets[i]->bases); if (sets[i]->table) cudaFree(sets[i]->table); }
     *sets[i] = fresh[i];
   }
   ctx->srs_k = k; ctx->srs_n = n; ctx->srs_borrowed = false;
@@ -1153,6 +1156,18 @@ int zk_msm_range_batch_dev(zk_ctx* ctx, const zk_fr* d_scalars, int which, size_
 }
 int zk_g1_sum_strided_dev(zk_ctx* ctx, const zk_g1* d_points, size_t parts, size_t count, zk_g1* d_out) {
   ZK_LAUNCH(ctx, "g1_sum", k_g1_sum_strided, zk_div_up(count, 32), 32, 0, (const uint4*)d_points, parts, count, (uint4*)d_out, ctx->msm_raw ? 1 : 0);
+  return ZK_OK;
+}
+
+// sum of `parts` XYZZ records (the partial results of a base-range-sharded MSM) -> one normalised G1
+__global__ void k_xyzz_sum_normalise(const uint4* pts, size_t parts, uint4* out) {
+  if (blockIdx.x || threadIdx.x) return;
+  XYZZ acc = XYZZ::identity();
+  for (size_t r = 0; r < parts; r++) acc = acc.add(XYZZ::load(pts + 8 * r));
+  store_g1_normalised(out, acc.to_affine());
+}
+int zk_xyzz_sum_normalised_dev(zk_ctx* ctx, const void* d_xyzz, size_t parts, zk_g1* d_out) {
+  ZK_LAUNCH(ctx, "g1_sum", k_xyzz_sum_normalise, 1, 32, 0, (const uint4*)d_xyzz, parts, (uint4*)d_out);
   return ZK_OK;
 }
 

@@ -729,6 +729,17 @@ class Group:
             self.ctx.lib.zk_group_destroy(self.h)
             self.h = None
 
+    @property
+    def p2p(self):
+        """True when the small exchanges go through peer-mapped windows (stores over NVLink + flags) instead of NCCL"""
+        return bool(self.ctx.lib.zk_group_p2p_enabled(self.h))
+
+    def msm_sharded_dev(self, d_scalars, n_local, d_out, lagrange=True):
+        """ONE MSM sharded by base range: this rank's slice of the scalars (device) against its resident slice of the
+        bases; d_out (device) receives the normalised G1 of the whole sum on every rank"""
+        which = _abi.BASES_G_LAGRANGE if lagrange else _abi.BASES_G
+        self.ctx.check(self.ctx.lib.zk_msm_sharded_dev(self.h, _vp(d_scalars), which, n_local, _vp(d_out)))
+
     @staticmethod
     def shard_plan(rank, world, count, n):
         """(mode, per, lo, hi): mode 0 = columns [lo, hi) per rank, mode 1 = base range [lo, hi) per rank"""
