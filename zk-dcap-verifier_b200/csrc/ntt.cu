@@ -379,6 +379,7 @@ struct NttJob {
   void* out;            // device, may alias `in` only when the transform is a single pass... never aliased here
   void* tmp;            // device scratch of count * N elements (ping-pong partner of out)
   size_t count, in_stride, n_in;
+  size_t out_stride;    // elements between consecutive polynomials in `out` (0 = 2^L: densely packed)
   uint32_t L;
   const void* tw; uint32_t tw_shift;
   int inverse, pre_mode, post_mode;
@@ -420,7 +421,7 @@ int run_ntt(zk_ctx* ctx, const NttJob& J) {
     void* dst = ((npass - 1 - p) % 2 == 0) ? J.out : J.tmp;
     PassArgs A;
     A.in = (const uint4*)src; A.out = (uint4*)dst; A.tw = (const uint4*)J.tw;
-    A.in_stride = src_stride; A.out_stride = N;
+    A.in_stride = src_stride; A.out_stride = (dst == J.out && J.out_stride) ? J.out_stride : N;
     A.n_in = (p == 0) ? J.n_in : N;
     A.L = L; A.s0 = s0; A.t = t; A.logC = logC; A.tw_shift = J.tw_shift;
     A.inverse = J.inverse;
@@ -439,7 +440,7 @@ int run_ntt(zk_ctx* ctx, const NttJob& J) {
       if (radix4) { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_t<1>, grid, kThreads, smem, A, J.K); }
       else { ZK_LAUNCH(ctx, "ntt_pass", k_ntt_pass_t<0>, grid, kThreads, smem, A, J.K); }
     }
-    src = dst; src_stride = N;
+    src = dst; src_stride = A.out_stride;
     s0 += t;
   }
   return ZK_OK;
@@ -571,7 +572,7 @@ extern "C" int zk_domain_constants(const zk_domain* d, zk_fr out[8]) {
 namespace {
 // transform `count` polynomials: src (stride in_stride, n_in valid) -> dst (stride 2^L)
 int domain_ntt(zk_domain* d, const void* src, void* dst, size_t count, size_t in_stride, size_t n_in,
-               uint32_t L, int inverse, int pre_mode, int post_mode, const PassConsts& K) {
+               uint32_t L, int inverse, int pre_mode, int post_mode, const PassConsts& K, size_t out_stride = 0) {
   zk_ctx* ctx = d->ctx;
   size_t N = (size_t)1 << L;
   uint32_t npass = L == 0 ? 1 : (L + kMaxT - 1) / kMaxT;
@@ -580,6 +581,7 @@ int domain_ntt(zk_domain* d, const void* src, void* dst, size_t count, size_t in
   J.in = src; J.out = dst; J.count = count; J.in_stride = in_stride; J.n_in = n_in; J.L = L;
   J.tw = d->tw_ext; J.tw_shift = d->extended_k - L;
   J.inverse = inverse; J.pre_mode = pre_mode; J.post_mode = post_mode; J.K = K;
+  J.out_stride = out_stride;
   if (npass > 1) {
     ZK_TRY(zk_scratch_reserve(ctx, d->work_b, count * N * 32));
     J.tmp = d->work_b.p;
@@ -631,6 +633,18 @@ extern "C" int zk_coeff_to_extended_dev(zk_domain* d, const zk_fr* d_a, zk_fr* d
   PassConsts K; memset(&K, 0, sizeof K);
   K.pre[0] = Fr::one(); K.pre[1] = d->g_coset; K.pre[2] = d->g_coset_inv;    // zeta^(i mod 3)
   return domain_ntt(d, d_a, d_out_ext, count, d->n, d->n, d->extended_k, 0, 1, 0, K);
+}
+// coeff_to_extended of `count` polynomials whose cosets go to slots `out_stride` elements apart (a multiple of the
+// extended size; e.g. the A' columns of all lookup arguments into every third evaluate_h slot): ONE batch of launches
+int zk_coeff_to_extended_strided(zk_domain* d, const zk_fr* d_a, zk_fr* d_out_ext, size_t count, size_t out_stride) {
+  if (!d || !d_a || !d_out_ext) return ZK_ERR_ARG;
+  zk_ctx* ctx = d->ctx;
+  ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!count) return ZK_OK;
+  if (out_stride < d->ext_n) ZK_FAIL(ctx, ZK_ERR_ARG, "coeff_to_extended: output stride below the extended size");
+  PassConsts K; memset(&K, 0, sizeof K);
+  K.pre[0] = Fr::one(); K.pre[1] = d->g_coset; K.pre[2] = d->g_coset_inv;
+  return domain_ntt(d, d_a, d_out_ext, count, d->n, d->n, d->extended_k, 0, 1, 0, K, out_stride);
 }
 extern "C" int zk_extended_to_coeff_dev(zk_domain* d, zk_fr* d_a_ext, zk_fr* d_out) {
   if (!d || !d_a_ext || !d_out) return ZK_ERR_ARG;
