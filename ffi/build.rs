@@ -4,7 +4,7 @@ use std::process::Command;
 fn main() {
     let root = std::path::Path::new(env!("CARGO_MANIFEST_DIR")).parent().unwrap().to_path_buf();
     let pkg = root.join("zk-dcap-verifier_b200");
-    let status = Command::new("python").arg(pkg.join("build.py")).status().expect("python + nvcc are required");
+    let status = Command::new("python3").arg(pkg.join("build.py")).status().expect("python + nvcc are required");
     assert!(status.success(), "nvcc build of libzkdcap_b200.so failed");
     println!("cargo:rustc-link-search=native={}", pkg.display());
     println!("cargo:rustc-link-lib=dylib=zkdcap_b200");

@@ -99,6 +99,17 @@ extern "C" {
     pub fn zk_group_create(ctx: *mut zk_ctx, rank: u32, world: u32, id: *const u8, out: *mut *mut zk_group) -> c_int;
     pub fn zk_group_destroy(g: *mut zk_group);
     pub fn zk_pkey_set_group(pk: *mut zk_pkey, g: *mut zk_group) -> c_int;
+    pub fn zk_group_p2p_enabled(g: *const zk_group) -> c_int;
+    /// ONE MSM sharded by base range: this rank's slice of the scalars against its resident slice of the bases (device memory)
+    pub fn zk_msm_sharded_dev(g: *mut zk_group, d_scalars: *const zk_fr, which: c_int, n_local: usize, d_out: *mut zk_g1) -> c_int;
+    pub fn zk_ctx_share_srs(dst: *mut zk_ctx, src: *const zk_ctx) -> c_int;
+    pub fn zk_srs_window(ctx: *mut zk_ctx, which: c_int, c_out: *mut u32, w_out: *mut u32) -> c_int;
+    // evaluate_h compiled from the expression graph (NVRTC at zk_pk_upload / zk_keygen)
+    pub fn zk_pk_evaluator_kind(pk: *const zk_pk) -> c_int;          // 1 = generated kernel, 0 = interpreter
+    pub fn zk_evalh_generate_source(desc: *const zk_evaluator_desc, host_flavour: c_int, buf: *mut c_char, cap: usize, len: *mut usize) -> c_int;
+    // ParamsKZG.g2 / s_g2: file encoding <-> the 128 uncompressed bytes zk_verify_proof takes
+    pub fn zk_g2_decode(format: c_int, input: *const u8, out_uncompressed: *mut u8) -> c_int;
+    pub fn zk_g2_encode(format: c_int, in_uncompressed: *const u8, out: *mut u8) -> c_int;
     // verify_proof (host code with its own BN254 pairing)
     pub fn zk_verify_proof(circuit: *const zk_circuit_desc, vp: *const zk_verifier_params, instance_values: *const *const zk_fr,
                            instance_lens: *const u32, proof: *const u8, proof_len: usize, accepted: *mut c_int) -> c_int;

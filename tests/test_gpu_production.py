@@ -104,16 +104,17 @@ def test_resident_msm_production_window(ctx, orc, k):
     del params
 
 
-@pytest.mark.parametrize("k", [13, 14, 15, 16])
-def test_window16_forced_on_small_inputs(ctx, orc, k):
+@pytest.mark.parametrize("k,c", [(13, 16), (14, 16), (15, 16), (16, 16), (14, 20), (16, 20)])
+def test_window16_forced_on_small_inputs(ctx, orc, k, c):
     """ZK_MSM_C=16 makes k = 13..16 take the code path of the bench sizes: 2^15 counters in shared memory, nR = 128,
-    nC = 256, W = 16 table rows."""
+    nC = 256, W = 16 table rows.  ZK_MSM_C=20 is the configuration of single commitments from 2^23 points on: 2^19 buckets,
+    W = 13, digits through the global-atomic kernels, 512 x 1024 row / column reduction."""
     n = 1 << k
     g = orc.gen_points(0xC16 + k, n)
     g[5] = g[4]
-    with env(ZK_MSM_C=16):
+    with env(ZK_MSM_C=c):
         params = zk.ParamsKZG(k, g, g, ctx, precompute=True)
-    assert window_bits(ctx) == (16, 16)
+    assert window_bits(ctx) == (c, 254 // c + 1)
     cls = scalar_classes(orc, n, 0xC16 + k)
     cls["ones"] = pm.to_mont_limbs([1] * n, pm.R_MOD)
     cls["top"] = pm.to_mont_limbs([pm.R_MOD - 1 - i for i in range(n)], pm.R_MOD)

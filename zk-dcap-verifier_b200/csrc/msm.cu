@@ -709,6 +709,10 @@ bool use_chunk_reduce() {
 
 uint32_t table_window_bits(uint32_t k) {
   if (const char* v = getenv("ZK_MSM_C")) { int c = atoi(v); if (c >= 2 && c <= 22) return (uint32_t)c; }
+  // single commitments of 2^23 points and more: c = 20 (W = 13 windows instead of 16: 19 % fewer bucket additions; 2^19 buckets,
+  // digits through the global-atomic path).  Measured, resident MSM, ms at c = 16 / 20 / 22 (profiles/r2_msm_window_probe.txt):
+  // 2^22: 12.6 / 12.6 / 17.6, 2^23: 24.7 / 22.3 / 27.5, 2^24: 49.3 / 42.6 / 47.4, 2^25: 104.9 / 83.0 / 86.9, 2^26: 211 / 164 / 166
+  if (k >= 23) return 20;
   int c = (int)k - 3;
   if (c < 4) c = 4;
   if (c > 16) c = 16;

@@ -181,8 +181,8 @@ int lincomb(zk_pkey* K, const std::vector<const void*>& polys, const std::vector
             (uint32_t)polys.size(), (uint4*)out, K->n);
   return ZK_OK;
 }
-// evaluations of `polys` at the point whose pow table sits in `slot`; results appended to `out` (host, after sync)
-int eval_list(zk_pkey* K, const std::vector<const void*>& polys, uint32_t slot, std::vector<Fr>* out) {
+// evaluations of `polys` at the point whose pow table sits in `slot`, left in device memory at d_dst (canonical-range Fr)
+int eval_list_to(zk_pkey* K, const std::vector<const void*>& polys, uint32_t slot, char* d_dst) {
   zk_ctx* ctx = K->ctx;
   if (polys.empty()) return ZK_OK;
   ZK_TRY(upload_list(K, polys, nullptr));
@@ -190,7 +190,14 @@ int eval_list(zk_pkey* K, const std::vector<const void*>& polys, uint32_t slot, 
   ZK_LAUNCH(ctx, "eval_polynomial", k_eval_partial, grid, kEvalThreads, 0, (const uint4* const*)K->d_ptrs, (const uint4*)table_slot(K, slot),
             K->n, (uint4*)K->d_partial, K->eval_chunks);
   ZK_LAUNCH(ctx, "eval_polynomial", k_eval_final, blocks_for(polys.size(), 64), 64, 0, (const uint4*)K->d_partial, K->eval_chunks,
-            (uint4*)K->d_evals, (uint32_t)polys.size());
+            (uint4*)d_dst, (uint32_t)polys.size());
+  return ZK_OK;
+}
+// evaluations of `polys` at the point whose pow table sits in `slot`; results appended to `out` (host, after sync)
+int eval_list(zk_pkey* K, const std::vector<const void*>& polys, uint32_t slot, std::vector<Fr>* out) {
+  zk_ctx* ctx = K->ctx;
+  if (polys.empty()) return ZK_OK;
+  ZK_TRY(eval_list_to(K, polys, slot, K->d_evals));
   std::vector<zk_fr> h(polys.size());
   ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), K->d_evals, polys.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -252,6 +259,14 @@ int commit_enqueue(zk_pkey* K, const char* d_polys, size_t count, int which, siz
   const uint32_t world = K->group ? zk_group_world(K->group) : 1;
   if (world <= 1 || !count) return zk_msm_batch_dev(ctx, (const zk_fr*)d_polys, which, K->n, count, (zk_g1*)out);
   const uint32_t rank = zk_group_rank(K->group);
+  // A batch whose size is not a multiple of the group leaves whole columns of difference between the ranks (28 columns on 8
+  // GPUs: four ranks commit 4, four commit 3).  The multiple of `world` goes by column, the remainder by base range, which
+  // every rank shares equally.
+  if (count > world && count % world != 0 && !getenv("ZK_GROUP_NO_HYBRID_SPLIT")) {
+    const size_t whole = count - count % world;
+    ZK_TRY(commit_enqueue(K, d_polys, whole, which, slot));
+    return commit_enqueue(K, d_polys + whole * K->n * 32, count - whole, which, slot + whole);
+  }
   int mode; size_t per, lo, hi;
   zk_group_shard_plan(rank, world, count, K->n, &mode, &per, &lo, &hi);
   PtRaw* xchg = (PtRaw*)K->d_xchg;
@@ -1190,6 +1205,40 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   if (2 * (rot_of.size() + 1) > K->n_table_slots) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: opening point tables");
   for (uint32_t p = 0; p < rot_of.size(); p++) ZK_TRY(build_pow_table(K, pt_val[p], 2 * p));
   std::vector<Fr> evals(reqs.size());
+  const uint32_t eworld = (K->group && !getenv("ZK_GROUP_NO_EVAL_SHARD")) ? zk_group_world(K->group) : 1;
+  if (eworld > 1) {
+    // a group shares the evaluations: request i belongs to rank i mod world (every rank holds every coefficient form); each
+    // rank evaluates its requests point by point into its segment of the exchange area, one small exchange, then every rank
+    // replays the same enumeration to put the values back in request order
+    const uint32_t erank = zk_group_rank(K->group);
+    auto mine_of = [&](uint32_t r, uint32_t p) {
+      std::vector<size_t> idx;
+      for (size_t i = 0; i < reqs.size(); i++) if (reqs[i].point == p && i % eworld == r) idx.push_back(i);
+      return idx;
+    };
+    size_t cap = 0;
+    for (uint32_t r = 0; r < eworld; r++) { size_t c = 0; for (uint32_t p = 0; p < rot_of.size(); p++) c += mine_of(r, p).size(); cap = std::max(cap, c); }
+    if (cap > K->max_list || cap * 32 * eworld > (size_t)(K->max_list + 64) * 16 * sizeof(PtRaw)) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: evaluation exchange area");
+    char* xe = K->d_xchg;
+    size_t pos = 0;
+    for (uint32_t p = 0; p < rot_of.size(); p++) {
+      std::vector<size_t> idx = mine_of(erank, p);
+      if (idx.empty()) continue;
+      std::vector<const void*> polys;
+      for (size_t i : idx) polys.push_back(reqs[i].poly);
+      ZK_TRY(eval_list_to(K, polys, 2 * p, xe + ((size_t)erank * cap + pos) * 32));
+      pos += idx.size();
+    }
+    ZK_TRY(zk_group_allgather(K->group, ctx, xe, cap * 32));
+    std::vector<zk_fr> h(cap * eworld);
+    ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), xe, h.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t r = 0; r < eworld; r++) {
+      size_t q = 0;
+      for (uint32_t p = 0; p < rot_of.size(); p++)
+        for (size_t i : mine_of(r, p)) evals[i] = f_from_abi<Fr>(&h[(size_t)r * cap + q++]);
+    }
+  } else
   for (uint32_t p = 0; p < rot_of.size(); p++) {
     std::vector<const void*> polys; std::vector<size_t> where;
     for (size_t i = 0; i < reqs.size(); i++) if (reqs[i].point == p) { polys.push_back(reqs[i].poly); where.push_back(i); }

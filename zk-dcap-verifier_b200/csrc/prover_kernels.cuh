@@ -253,9 +253,19 @@ __global__ void k_eval_final(const uint4* partial, uint32_t nchunks, uint4* out,
 __global__ void __launch_bounds__(256) k_lincomb(const uint4* const* polys, const uint4* scalars, uint32_t m, uint4* out, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fr acc = Fr::zero();
-  for (uint32_t j = 0; j < m; j++) acc = acc + Fr::load(scalars + 2 * j) * Fr::load(polys[j] + 2 * i);
-  acc.store(out + 2 * i);
+  // two independent accumulators and loads issued four terms ahead: the terms are independent products, only the sums chain
+  // (field addition is exact, so the association order does not change the canonical result)
+  Fr acc0 = Fr::zero(), acc1 = Fr::zero();
+  uint32_t j = 0;
+  for (; j + 4 <= m; j += 4) {
+    const Fr p0 = Fr::load(polys[j] + 2 * i), p1 = Fr::load(polys[j + 1] + 2 * i), p2 = Fr::load(polys[j + 2] + 2 * i), p3 = Fr::load(polys[j + 3] + 2 * i);
+    acc0 = acc0 + Fr::load(scalars + 2 * j) * p0;
+    acc1 = acc1 + Fr::load(scalars + 2 * (j + 1)) * p1;
+    acc0 = acc0 + Fr::load(scalars + 2 * (j + 2)) * p2;
+    acc1 = acc1 + Fr::load(scalars + 2 * (j + 3)) * p3;
+  }
+  for (; j < m; j++) acc0 = acc0 + Fr::load(scalars + 2 * j) * Fr::load(polys[j] + 2 * i);
+  (acc0 + acc1).store(out + 2 * i);
 }
 // a[i] -= low[i] for i < m (m <= 8): subtracts a low-degree polynomial in place
 struct LowPoly { Fr c[8]; uint32_t m; };
