@@ -84,3 +84,39 @@ def test_group_shard_plan_covers_everything_once():
                 assert covered == list(range(total))
             else:
                 assert covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+
+
+def test_group_balance_plan_properties():
+    """zk_group_balance_plan (csrc/prover.cu): every column is placed exactly once, the count % world most expensive columns
+    are the shared ones, every rank gets count / world whole columns, the plan is deterministic, and the heaviest rank is no
+    worse than round-robin on skewed costs (bit columns next to field-element columns, as in the QE3 shape)."""
+    import ctypes as C
+    import random
+    import zkdcap_b200 as zk
+    lib = zk._abi.load()
+    rnd = random.Random(5)
+    for world in (2, 4, 8):
+        for count in (world, world + 1, 17, 22, 28, 3 * world + 2):
+            if count < world:
+                continue
+            cost = [rnd.choice([1, 1, 2, 16, 16, 11]) * 524288 + rnd.randrange(1000) for _ in range(count)]
+            arr = (C.c_uint32 * count)(*cost)
+            own = (C.c_uint32 * count)()
+            lib.zk_group_balance_plan(arr, count, world, own)
+            own2 = (C.c_uint32 * count)()
+            lib.zk_group_balance_plan(arr, count, world, own2)
+            assert list(own) == list(own2)
+            rem, per = count % world, count // world
+            shared = [i for i in range(count) if own[i] == world]
+            assert len(shared) == rem
+            assert sorted(cost[i] for i in shared) == sorted(cost, reverse=True)[:rem][::-1]
+            loads = [0] * world
+            for r in range(world):
+                mine = [i for i in range(count) if own[i] == r]
+                assert len(mine) == per
+                loads[r] = sum(cost[i] for i in mine)
+            assert all(0 <= o <= world for o in own)
+            # round-robin over the same whole columns for comparison
+            whole = [i for i in range(count) if own[i] != world]
+            rr = [sum(cost[i] for j, i in enumerate(whole) if j % world == r) for r in range(world)]
+            assert max(loads) <= max(rr)

@@ -94,7 +94,7 @@ SYMBOLS = [
     "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_pkey_aux_ctx", "zk_pkey_set_transcript", "zk_proof_randoms", "zk_proof_max_bytes",
     "zk_create_proof", "zk_verify_proof", "zk_g2_decode", "zk_g2_encode",
     "zk_group_unique_id", "zk_group_create", "zk_group_destroy", "zk_group_rank", "zk_group_world", "zk_group_p2p_enabled", "zk_pkey_set_group", "zk_msm_sharded_dev",
-    "zk_group_shard_plan",
+    "zk_group_shard_plan", "zk_group_balance_plan",
     "zk_field_op", "zk_bench_modmul", "zk_bench_imad",
 ]
 
@@ -190,6 +190,7 @@ def load():
         "zk_group_p2p_enabled": (i32, [vp]),
         "zk_pkey_set_group": (i32, [vp, vp]),
         "zk_msm_sharded_dev": (i32, [vp, vp, i32, sz, vp]),
+        "zk_group_balance_plan": (None, [C.POINTER(u32), sz, u32, C.POINTER(u32)]),
         "zk_group_shard_plan": (None, [u32, u32, sz, sz, C.POINTER(C.c_int), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]),
         "zk_field_op": (i32, [vp, i32, i32, vp, vp, vp, sz]),
         "zk_bench_modmul": (i32, [vp, i32, u32, C.POINTER(C.c_double)]),

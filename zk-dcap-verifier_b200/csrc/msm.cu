@@ -767,7 +767,20 @@ int run_msm(zk_ctx* ctx, const void* d_scalars, const void* d_points, const MsmP
   size_t off_cnt = 0, off_st = off_cnt + align(cnt_bytes), off_ent = off_st + align(st_bytes);
   size_t off_bk = off_ent + align(ent_bytes), off_r1 = off_bk + align(bucket_bytes), off_r2 = off_r1 + align(red_bytes);
   // chunked accumulation: T0 entries per thread at level 0, T1 slots per thread afterwards
-  const uint32_t T0 = getenv("ZK_MSM_T0") ? (uint32_t)atoi(getenv("ZK_MSM_T0")) : 64;
+  // Entries per thread: at most 64, and chosen so that the accumulation fills WHOLE waves of the 4 x 128-thread CTAs an SM
+  // holds -- a lone 2^19 commitment is 1024 CTAs = 1.73 waves at 64 entries per thread (the second wave runs 27 % empty);
+  // 56 entries make it two full, shorter waves.  Batches span tens of waves and are unaffected.
+  uint32_t T0 = 64;
+  if (getenv("ZK_MSM_T0")) T0 = (uint32_t)atoi(getenv("ZK_MSM_T0"));
+  else {
+    const size_t slots = (size_t)ctx->sm_count * 4 * 128, E = P.ent_per_msm * P.count;
+    const size_t waves = (E + slots * 64 - 1) / (slots * 64);
+    if (waves && waves <= 8) {
+      size_t t = (E + slots * waves - 1) / (slots * waves);
+      if (t < 24) t = 24;
+      if (t < 64) T0 = (uint32_t)t;
+    }
+  }
   const uint32_t T1 = getenv("ZK_MSM_T1") ? (uint32_t)atoi(getenv("ZK_MSM_T1")) : 8;   // short serial chains: these levels are latency bound
   const uint32_t nth0 = (uint32_t)((P.ent_per_msm + T0 - 1) / T0);
   const uint32_t Tmin = T1 < kTailT ? T1 : kTailT;

@@ -249,6 +249,26 @@ __global__ void k_eval_final(const uint4* partial, uint32_t nchunks, uint4* out,
   acc.store(out + 2 * p);
 }
 
+// cost[col] += number of non-zero 16-bit windows of the canonical values of column `col` (a proxy for the bucket additions a
+// commitment of that column performs: the group assigns columns to GPUs by it)
+__global__ void __launch_bounds__(256) k_column_cost(const uint4* cols, size_t n, unsigned int* cost) {
+  const size_t col = blockIdx.y;
+  unsigned int mine = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const Fr v = Fr::load(cols + 2 * (col * n + i)).from_mont();
+#pragma unroll
+    for (int l = 0; l < 8; l++) mine += ((v.l[l] & 0xFFFFu) != 0) + ((v.l[l] >> 16) != 0);
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&cost[col], mine);
+}
+// out[map[j]] = src[j] for XYZZ records (128 bytes)
+__global__ void k_scatter_points(const uint4* src, const unsigned int* map, uint4* out, unsigned int count) {
+  unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * 8) return;
+  out[8 * (size_t)map[t >> 3] + (t & 7)] = src[t];
+}
+
 // out[i] = sum_j scalars[j] * polys[j][i]   (+ acc_in[i] when given)
 __global__ void __launch_bounds__(256) k_lincomb(const uint4* const* polys, const uint4* scalars, uint32_t m, uint4* out, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
