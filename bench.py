@@ -1376,54 +1376,20 @@ def sweep(args, zk, torch, dev, local_rank):
 
 
 def msm_sharded(args, zk, torch, dist, dev, rank, local_rank, world):
-    """ONE MSM of 2^k points sharded by base range over the ranks: each GPU runs Pippenger on its slice of the
-    resident bases, the 96-byte partial points are all-gathered over NVLink and folded with zk_g1_sum."""
-    h2 = __import__("importlib").import_module("zk-dcap-verifier_b200.halo2")
-    ctx = zk.Context(local_rank, work_stream(torch, dev))
-    k = args.k
-    n = 1 << k
-    per = n // world
-    gen = torch.Generator(device=dev); gen.manual_seed(0x5CA1A4 + k)   # same stream on every rank: slice it
-    G = np.concatenate([zk.fq_to_limbs(1), zk.fq_to_limbs(2)])
-    sc_all = rand_fr(torch, n, dev, gen)
-    bs_all = rand_fr(torch, n, dev, gen)
-    sc = sc_all[rank * per:(rank + 1) * per].contiguous()
-    pts = torch.empty((per, 8), dtype=torch.int64, device=dev)
-    h2.fixed_base_mul_dev(ctx, G, bs_all[rank * per:(rank + 1) * per].contiguous().data_ptr(), per, pts.data_ptr())
-    del sc_all, bs_all
-    part = torch.empty((1, 12), dtype=torch.int64, device=dev)
-    gathered = torch.empty((world, 12), dtype=torch.int64, device=dev)
-    out = torch.empty((1, 12), dtype=torch.int64, device=dev)
-
-    def step():
-        h2.msm_dev(ctx, sc.data_ptr(), pts.data_ptr(), per, part.data_ptr())
+    """`--mode msm-sharded`: ONE MSM of 2^k points sharded by base range over the ranks (zk_msm_sharded_dev, the same measurement
+    the default N > 1 line carries as `sharded_msm`)."""
+    def barrier():
         if dist is not None:
-            dist.all_gather_into_tensor(gathered, part)
-        else:
-            gathered.copy_(part)
-        ctx.check(ctx.lib.zk_g1_sum_dev(ctx.h, C.c_void_p(gathered.data_ptr()), world, C.c_void_p(out.data_ptr())))
-    for _ in range(args.warmup):
-        step()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.steps
+            dist.barrier()
+        torch.cuda.synchronize()
+    if world == 1:
+        raise SystemExit("bench.py --mode msm-sharded needs torchrun with N > 1 (the single-GPU figures are in --mode sweep)")
+    res = measure_sharded_msm(args, zk, torch, dist, dev, rank, local_rank, world, barrier, k=args.k)
     if rank == 0:
-        emit({"metric": "BN254 G1 MSM sharded by base range, Gpts/s", "value": n / (ms * 1e-3) / 1e9,
-                          "unit": "Gpts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                          "dtype": "u32 limbs (254-bit modular)", "data": "synthetic",
-                          "config": {"workload": "one MSM of 2^%d points, bases sharded by contiguous range" % k},
-                          "result_point": [int(x) & 0xFFFFFFFFFFFFFFFF for x in out.cpu().view(-1).tolist()]})
+        emit({"metric": "BN254 G1 MSM sharded by base range, Gpts/s", "value": res["Gpts_s"], "unit": "Gpts/s", "n_gpus": world,
+              "steps": max(3, args.steps), "warmup": 3, "ms_per_step": res["ms"], "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+              "config": {"workload": "one MSM of 2^%d points, bases sharded by contiguous range, resident per rank" % args.k}, "sharded_msm": res})
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -25,6 +25,8 @@ static void run(int op, const unsigned* a, const unsigned* b, unsigned* out, siz
       case 9: { F xp; add8(xp.l, x.l, F::template kp<1>().l); F yp; add8(yp.l, y.l, F::template kp<1>().l); z = xp * yp; break; }
       case 10: { F xp; add8(xp.l, x.l, F::template kp<1>().l); z = xp - y; break; }
       case 11: { F xp; add8(xp.l, x.l, F::template kp<1>().l); F yp; add8(yp.l, y.l, F::template kp<1>().l); z = xp + yp; break; }
+      case 12: { F xp; add8(xp.l, x.l, F::template kp<1>().l); z = xp.sqr(); break; }      // squaring of a lazy value in [p, 2p)
+      case 13: { z = x.sqr().sqr(); break; }                                                 // chained: the input of the second is lazy
       default: z = x; break;
     }
     z = z.reduce();

@@ -57,6 +57,10 @@ def test_device_field_algorithms_on_host(ffh, field, mod):
     assert ints(run(ffh, field, 1, a, b)) == [(x - y) % mod for x, y in zip(xs, ys)]
     assert ints(run(ffh, field, 2, a, b)) == [x * y * rinv % mod for x, y in zip(xs, ys)]
     assert ints(run(ffh, field, 5, a)) == [x * x * rinv % mod for x in xs]
+    # the dedicated squaring on lazy inputs ([p, 2p)) and chained, and against operator* on the same operands
+    assert ints(run(ffh, field, 12, a)) == [x * x * rinv % mod for x in xs]
+    assert ints(run(ffh, field, 13, a)) == [pow(x * x * rinv % mod, 2, mod) * rinv % mod for x in xs]
+    assert np.array_equal(run(ffh, field, 5, a), run(ffh, field, 2, a, a))
     assert ints(run(ffh, field, 3, a)) == [(-x) % mod for x in xs]
     assert ints(run(ffh, field, 8, a)) == [2 * x % mod for x in xs]
     assert ints(run(ffh, field, 6, a)) == [x * (1 << 256) % mod for x in xs]

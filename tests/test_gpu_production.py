@@ -232,3 +232,22 @@ def test_generated_evaluator_is_in_use_and_matches_the_interpreter(ctx, orc):
         got[mode] = pk.evaluate_h(case["advice"], case["instance"], ch, L(case["y"]), L(case["beta"]), L(case["gamma"]),
                                   L(case["theta"]), case["lookup_polys"], case["z_polys"])
         assert np.array_equal(got[mode], want), mode
+
+
+def test_work_counters(ctx, orc):
+    """zk_ctx_counters: the device-side count of sorted bucket entries (= group additions of the accumulation) that bench.py's
+    integer-pipe roofline is computed from"""
+    k = 12
+    n = 1 << k
+    g = orc.gen_points(0xC7 + k, n)
+    params = zk.ParamsKZG(k, g, g, ctx, precompute=True)
+    c, W = window_bits(ctx)
+    ctx.counters(reset=True)
+    ones = pm.to_mont_limbs([1] * n, pm.R_MOD)
+    params.commit_lagrange(ones)                                   # one non-zero window per scalar
+    got = ctx.counters()
+    assert got == {"msm_bucket_entries": n, "msms": 1}
+    params.commit_lagrange(orc.gen_scalars(5, n))                  # uniform scalars: nearly every window is non-zero
+    got = ctx.counters(reset=True)
+    assert got["msms"] == 2 and 0.95 * n * W < got["msm_bucket_entries"] - n <= n * W
+    assert ctx.counters() == {"msm_bucket_entries": 0, "msms": 0}

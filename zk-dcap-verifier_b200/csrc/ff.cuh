@@ -190,6 +190,86 @@ ZK_HD void merge_shift(uint32_t* r, const uint32_t* y, const uint32_t* x) {
 #endif
 }
 
+// ---- primitives of the dedicated squaring ---------------------------------------------------------------------------------
+// N products {a[0..N-1]} * b added into N consecutive 64-bit slots acc[0..2N-1] as one carry chain; the carry out is ADDED
+// into acc[2N] (the caller guarantees that limb holds at most a few earlier carries, so it cannot overflow)
+template <int N>
+ZK_HD void mad_slots(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  if (N == 1) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t madc.hi.cc.u32 %1, %3, %4, %1;\n\t addc.u32 %2, %2, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(a[0]), "r"(b));
+  } else if (N == 2) {
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t madc.hi.cc.u32 %3, %6, %7, %3;\n\t addc.u32 %4, %4, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(a[0]), "r"(a[2]), "r"(b));
+  } else if (N == 3) {
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t madc.hi.cc.u32 %5, %9, %10, %5;\n\t addc.u32 %6, %6, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(b));
+  } else {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t madc.hi.cc.u32 %7, %12, %13, %7;\n\t addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(b));
+  }
+#else
+  uint64_t c = 0;
+  for (int j = 0; j < N; j++) {
+    uint64_t p = (uint64_t)a[2 * j] * b;
+    c += (uint64_t)acc[2 * j] + (uint32_t)p; acc[2 * j] = (uint32_t)c; c >>= 32;
+    c += (uint64_t)acc[2 * j + 1] + (uint32_t)(p >> 32); acc[2 * j + 1] = (uint32_t)c; c >>= 32;
+  }
+  acc[2 * N] += (uint32_t)c;
+#endif
+}
+// t[0..15] = 2 * t[0..15] + sum_i a[i]^2 * 2^(64 i)   (the doubling as funnel shifts, the diagonal as one carry chain)
+ZK_HD void dbl_add_diag(uint32_t* t, const uint32_t* a) {
+#pragma unroll
+  for (int i = 15; i > 0; i--) t[i] = (t[i] << 1) | (t[i - 1] >> 31);
+  t[0] <<= 1;
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %2;\n\t madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %4;\n\t madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %6;\n\t madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %8;\n\t madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %10;\n\t madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %12;\n\t madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %14;\n\t madc.hi.u32 %15, %23, %23, %15;"
+      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]),
+        "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t p = (uint64_t)a[i] * a[i];
+    c += (uint64_t)t[2 * i] + (uint32_t)p; t[2 * i] = (uint32_t)c; c >>= 32;
+    c += (uint64_t)t[2 * i + 1] + (uint32_t)(p >> 32); t[2 * i + 1] = (uint32_t)c; c >>= 32;
+  }
+#endif
+}
+// r[1..15] = e[1..15] + o[0..14] (one chain; r[0] = e[0]); the sum is known to fit 512 bits
+ZK_HD void merge_even_odd(uint32_t* e, const uint32_t* o) {
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32 %0, %0, %15;\n\t addc.cc.u32 %1, %1, %16;\n\t addc.cc.u32 %2, %2, %17;\n\t addc.cc.u32 %3, %3, %18;\n\t"
+      "addc.cc.u32 %4, %4, %19;\n\t addc.cc.u32 %5, %5, %20;\n\t addc.cc.u32 %6, %6, %21;\n\t addc.cc.u32 %7, %7, %22;\n\t"
+      "addc.cc.u32 %8, %8, %23;\n\t addc.cc.u32 %9, %9, %24;\n\t addc.cc.u32 %10, %10, %25;\n\t addc.cc.u32 %11, %11, %26;\n\t"
+      "addc.cc.u32 %12, %12, %27;\n\t addc.cc.u32 %13, %13, %28;\n\t addc.u32 %14, %14, %29;"
+      : "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]),
+        "+r"(e[9]), "+r"(e[10]), "+r"(e[11]), "+r"(e[12]), "+r"(e[13]), "+r"(e[14]), "+r"(e[15])
+      : "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]),
+        "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]));
+#else
+  uint64_t c = 0;
+  for (int i = 1; i < 16; i++) { c += (uint64_t)e[i] + o[i - 1]; e[i] = (uint32_t)c; c >>= 32; }
+#endif
+}
+
 struct FrParams {
   static constexpr uint32_t M0 = 0xf0000001u, M1 = 0x43e1f593u, M2 = 0x79b97091u, M3 = 0x2833e848u,
                             M4 = 0x8181585du, M5 = 0xb85045b6u, M6 = 0xe131a029u, M7 = 0x30644e72u;
@@ -341,7 +421,63 @@ struct Fp {
     merge_shift(r.l, Y, X);   // X[0] == 0; result = (X >> 32) + Y  < 2p
     return r;
   }
-  ZK_HD Fp sqr() const { return (*this) * (*this); }
+  // Dedicated squaring: the 28 products a[i] * a[j], i < j, are formed once (as carry chains over the even- and the
+  // odd-position product slots), doubled, and the 8 squares a[i]^2 added as one more chain: 36 wide multiplications instead
+  // of 64 for the operand products; the Montgomery reduction (64 more) then runs on the low half of the 512-bit square with
+  // the same staggered accumulators as operator*, and the high half is added at the end.  Result < 2p as for operator*
+  // ((a^2 + m p) / R with a < 2p, m < R).
+  ZK_HD Fp sqr() const {
+    const uint32_t* a = l;
+    uint32_t E[17], O[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+    // E[p]: products whose low limb sits at the even position p; O[p]: at the odd position p + 1.  Row i multiplies a[i]
+    // with a[j], j > i; the j of one parity give consecutive slots.  Carries land on limbs no later row's carry can overflow.
+    mad_slots<3>(E + 2, a + 2, a[0]);      // a0 * {a2, a4, a6}      -> positions 2..7,   carry -> 8
+    mad_slots<4>(O + 0, a + 1, a[0]);      // a0 * {a1, a3, a5, a7}  -> positions 1..8,   carry -> 9
+    mad_slots<3>(E + 4, a + 3, a[1]);      // a1 * {a3, a5, a7}      -> positions 4..9,   carry -> 10
+    mad_slots<3>(O + 2, a + 2, a[1]);      // a1 * {a2, a4, a6}      -> positions 3..8,   carry -> 9
+    mad_slots<2>(E + 6, a + 4, a[2]);      // a2 * {a4, a6}          -> positions 6..9,   carry -> 10
+    mad_slots<3>(O + 4, a + 3, a[2]);      // a2 * {a3, a5, a7}      -> positions 5..10,  carry -> 11
+    mad_slots<2>(E + 8, a + 5, a[3]);      // a3 * {a5, a7}          -> positions 8..11,  carry -> 12
+    mad_slots<2>(O + 6, a + 4, a[3]);      // a3 * {a4, a6}          -> positions 7..10,  carry -> 11
+    mad_slots<1>(E + 10, a + 6, a[4]);     // a4 * a6                -> positions 10..11, carry -> 12
+    mad_slots<2>(O + 8, a + 5, a[4]);      // a4 * {a5, a7}          -> positions 9..12,  carry -> 13
+    mad_slots<1>(E + 12, a + 7, a[5]);     // a5 * a7                -> positions 12..13, carry -> 14
+    mad_slots<1>(O + 10, a + 6, a[5]);     // a5 * a6                -> positions 11..12, carry -> 13
+    mad_slots<1>(O + 12, a + 7, a[6]);     // a6 * a7                -> positions 13..14, carry -> 15
+    merge_even_odd(E, O);                  // E = sum of the off-diagonal products
+    dbl_add_diag(E, a);                    // E = a^2 (512 bits)
+    // Montgomery reduction of the low 256 bits; X aligned at limb 0, Y at limb 1 as in operator*
+    uint32_t X[8], Y[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) X[j] = E[j];
+    {
+      uint32_t m = X[0] * P::INV, top = 0;
+      mad_row(X, top, P::M0, P::M2, P::M4, P::M6, m);
+      mul_row(Y, P::M1, P::M3, P::M5, P::M7, m);
+      // the carry out of X's row has weight 2^256 = limb 7 of Y (Y is aligned at limb 1)
+      Y[7] += top;
+    }
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+      uint32_t Xn[8], Yn[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) Xn[j] = Y[j];
+      const uint32_t m = (Y[0] + X[1]) * P::INV;
+      shift_mad_row(Xn[0], Yn, X, P::M1, P::M3, P::M5, P::M7, m);
+      mad_row(Xn, Yn[7], P::M0, P::M2, P::M4, P::M6, m);
+#pragma unroll
+      for (int j = 0; j < 8; j++) { X[j] = Xn[j]; Y[j] = Yn[j]; }
+    }
+    Fp r, hi;
+    merge_shift(r.l, Y, X);
+#pragma unroll
+    for (int j = 0; j < 8; j++) hi.l[j] = E[8 + j];
+    Fp out;
+    add8(out.l, r.l, hi.l);
+    return out;
+  }
 
   // Montgomery form -> canonical integer (multiply by 1 = one REDC pass), fully reduced
   ZK_HD Fp from_mont() const {

@@ -37,6 +37,7 @@ int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_ra
 bool zk_group_p2p_begin(zk_group* g, zk_ctx* on, size_t bytes_per_rank, zk_p2p_push* out);
 int zk_group_p2p_finish(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank);
 int zk_group_p2p_push(zk_group* g, zk_ctx* on, const zk_p2p_push& pp, const void* my_segment, size_t bytes);
+int zk_group_p2p_error(zk_group* g, zk_ctx* on);
 int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, const uint32_t* owners, size_t count, size_t height, size_t halo);
 extern "C" uint32_t zk_group_rank(const zk_group* g);
 extern "C" uint32_t zk_group_world(const zk_group* g);
@@ -1535,6 +1536,11 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     ZK_TRY(write_points(pts));
   }
   mark("done");
+  // a peer that never raised its flag leaves the wait kernels with a timeout and an error word: never hand out such a proof
+  if (K->group && zk_group_world(K->group) > 1) {
+    if (zk_group_p2p_error(K->group, ctx) || (cB && zk_group_p2p_error(K->group, cB)))
+      ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: a peer-to-peer exchange of the group timed out");
+  }
   if (rpos != zk_proof_randoms(K)) ZK_FAIL(ctx, ZK_ERR_STATE, "zk_create_proof: drew %zu randoms, expected %zu", rpos, zk_proof_randoms(K));
   if (tr.proof.size() > proof_cap) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: proof needs %zu bytes, buffer holds %zu", tr.proof.size(), proof_cap);
   memcpy(proof, tr.proof.data(), tr.proof.size());
