@@ -351,6 +351,7 @@ int launch_evalh(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr
 
 // ---- internal entry points for prover.cu: the witness cosets are produced by the caller (on another stream) -------
 // slot order: advice | instance | permutation z sets | lookup (Z, A', S') triples; 2^extended_k elements each
+size_t zk_pk_witness_bytes(zk_pk* pk) { return (pk->n_witness ? pk->n_witness : 1) * zk_domain_ext_n(pk->dom) * 32; }
 char* zk_pk_witness_slot(zk_pk* pk, size_t slot) { return (char*)pk->d_witness + slot * zk_domain_ext_n(pk->dom) * 32; }
 // rows [row0, row1) of the extended domain only (a group of GPUs splits the rows)
 int zk_evaluate_h_launch(zk_pk* pk, const zk_fr* challenges, const zk_fr* y, const zk_fr* beta, const zk_fr* gamma,

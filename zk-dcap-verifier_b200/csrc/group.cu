@@ -38,6 +38,10 @@ struct zk_group {
   void* comm2 = nullptr;     // collectives issued on another stream of the same device (the prover's transform stream)
   P2PWindow win[2];          // [0] exchanges on the context's stream, [1] on the second stream
   char* msm_xchg = nullptr;  // world XYZZ records: the partial points of zk_msm_sharded_dev
+  // buffers with the same layout on every rank whose peers are mapped (CUDA IPC): rows are copied straight into them
+  struct RegBuf { char* local; size_t bytes; char* peer[kZkMaxGroup]; };
+  std::vector<RegBuf> regs;
+  char* d_dummy = nullptr;   // 16 bytes pushed with the "rows have arrived" flag
 };
 
 namespace {
@@ -307,6 +311,10 @@ extern "C" void zk_group_destroy(zk_group* g) {
   Nccl* N = nccl();
   cudaSetDevice(g->ctx->device); cudaDeviceSynchronize();
   if (g->msm_xchg) cudaFree(g->msm_xchg);
+  if (g->d_dummy) cudaFree(g->d_dummy);
+  for (auto& r : g->regs)
+    for (uint32_t q = 0; q < g->world; q++) if (q != g->rank && r.peer[q]) cudaIpcCloseMemHandle(r.peer[q]);
+  g->regs.clear();
   p2p_teardown(g);
   if (N && g->comm) {
     cudaSetDevice(g->ctx->device); cudaDeviceSynchronize();
@@ -330,10 +338,79 @@ int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_ra
     ZK_TRY(zk_group_p2p_push(g, ctx, pp, (const char*)d_buf + (size_t)g->rank * bytes_per_rank, bytes_per_rank));
     return zk_group_p2p_finish(g, ctx, d_buf, bytes_per_rank);
   }
+  // large, inside a registered buffer (coefficient forms, h(X) rows): my segment is copied straight into every peer's copy of
+  // the buffer (copy engines over NVLink), then the "arrived" flags go round
+  for (auto& r : g->regs) {
+    char* b = (char*)d_buf;
+    if (b < r.local || b + (size_t)g->world * bytes_per_rank > r.local + r.bytes) continue;
+    // one-sided writes need the receivers' consent: a flag round first ("my previous use of this buffer is over" -- it is
+    // stream-ordered behind this rank's reads of the buffer), then the copies, then the "arrived" round
+    if (!zk_group_p2p_begin(g, ctx, 16, &pp)) break;
+    ZK_TRY(zk_group_p2p_push(g, ctx, pp, g->d_dummy + 16 * g->rank, 16));
+    ZK_TRY(zk_group_p2p_finish(g, ctx, g->d_dummy, 16));
+    if (!zk_group_p2p_begin(g, ctx, 16, &pp)) ZK_FAIL(ctx, ZK_ERR_STATE, "group: exchange window");
+    zk_timing_begin(ctx, "group_allgather");
+    char* mine = b + (size_t)g->rank * bytes_per_rank;
+    cudaError_t ce = cudaSuccess;
+    for (uint32_t q = 0; q < g->world && ce == cudaSuccess; q++)
+      if (q != g->rank) ce = cudaMemcpyAsync(r.peer[q] + (mine - r.local), mine, bytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream);
+    zk_timing_end(ctx);
+    if (ce != cudaSuccess) ZK_FAIL(ctx, ZK_ERR_CUDA, "group: peer copy: %s", cudaGetErrorString(ce));
+    ZK_TRY(zk_group_p2p_push(g, ctx, pp, g->d_dummy + 16 * g->rank, 16));
+    return zk_group_p2p_finish(g, ctx, g->d_dummy, 16);
+  }
   zk_timing_begin(ctx, "group_allgather");
   int r = N->allgather((const char*)d_buf + (size_t)g->rank * bytes_per_rank, d_buf, bytes_per_rank, /*ncclChar*/ 0, comm, ctx->stream);
   zk_timing_end(ctx);
   if (r != 0) ZK_FAIL(ctx, ZK_ERR_CUDA, "group: ncclAllGather: %s", N->err ? N->err(r) : "error");
+  return ZK_OK;
+}
+
+// Collective: every rank registers ITS buffer of the same size and layout (the evaluate_h witness slots); afterwards
+// zk_group_exchange_rows writes the peers' rows straight into their copies (device-to-device copies over NVLink through the
+// IPC mapping) instead of going through ncclSend / ncclRecv.  No-op without peer windows.
+int zk_group_register(zk_group* g, void* base, size_t bytes) {
+  if (!g || g->world <= 1 || !g->win[0].ok || !g->win[1].ok || getenv("ZK_GROUP_NO_P2P_ROWS")) return ZK_OK;
+  zk_ctx* ctx = g->ctx;
+  for (auto& r : g->regs) if (r.local == (char*)base) return ZK_OK;
+  Nccl* N = nccl();
+  if (!N) return ZK_OK;
+  zk_group::RegBuf rb; memset(&rb, 0, sizeof rb);
+  rb.local = (char*)base; rb.bytes = bytes;
+  cudaIpcMemHandle_t mine, *d_handles = nullptr;
+  std::vector<cudaIpcMemHandle_t> handles(g->world);
+  int ok = cudaIpcGetMemHandle(&mine, base) == cudaSuccess ? 1 : 0;
+  if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof mine); }
+  // the handle and a "mapping worked" word travel together; the registration only counts when EVERY rank succeeded
+  ZK_CUDA(ctx, cudaMalloc(&d_handles, g->world * sizeof mine));
+  ZK_CUDA(ctx, cudaMemcpyAsync(d_handles + g->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+  int r = N->allgather(d_handles + g->rank, d_handles, sizeof mine, 0, g->comm, ctx->stream);
+  ZK_CUDA(ctx, cudaMemcpyAsync(handles.data(), d_handles, g->world * sizeof mine, cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_handles);
+  if (r != 0) ok = 0;
+  for (uint32_t q = 0; q < g->world && ok; q++) {
+    if (q == g->rank) { rb.peer[q] = rb.local; continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, handles[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    rb.peer[q] = (char*)p;
+  }
+  int* d_ok = nullptr;
+  std::vector<int> oks(g->world, 0);
+  ZK_CUDA(ctx, cudaMalloc(&d_ok, g->world * 4));
+  ZK_CUDA(ctx, cudaMemcpyAsync(d_ok + g->rank, &ok, 4, cudaMemcpyHostToDevice, ctx->stream));
+  N->allgather(d_ok + g->rank, d_ok, 4, 0, g->comm, ctx->stream);
+  ZK_CUDA(ctx, cudaMemcpyAsync(oks.data(), d_ok, g->world * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_ok);
+  bool all = true;
+  for (int v : oks) all = all && v == 1;
+  if (!all) {
+    for (uint32_t q = 0; q < g->world; q++) if (q != g->rank && rb.peer[q]) cudaIpcCloseMemHandle(rb.peer[q]);
+    return ZK_OK;
+  }
+  if (!g->d_dummy) { ZK_CUDA(ctx, cudaMalloc(&g->d_dummy, 256)); ZK_CUDA(ctx, cudaMemsetAsync(g->d_dummy, 0, 256, ctx->stream)); }
+  g->regs.push_back(rb);
   return ZK_OK;
 }
 
@@ -343,10 +420,43 @@ int zk_group_allgather(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_ra
 // ncclSend / ncclRecv batch; nothing is staged.
 int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, const uint32_t* owners, size_t count, size_t height, size_t halo) {
   zk_ctx* ctx = on ? on : g->ctx;
+  const size_t rows = height / g->world;
+  // every column inside ONE registered buffer: the owner copies each peer's rows straight into the peer's copy of the buffer
+  // (copy engines over NVLink), then raises the "rows have arrived" flag in every peer; everybody waits for all flags
+  const zk_group::RegBuf* rb = nullptr;
+  for (auto& r : g->regs) {
+    bool inside = count > 0;
+    for (size_t c = 0; c < count && inside; c++) inside = cols[c] >= r.local && cols[c] + height * 32 <= r.local + r.bytes;
+    if (inside) { rb = &r; break; }
+  }
+  zk_p2p_push pp;
+  if (rb && zk_group_p2p_begin(g, ctx, 16, &pp)) {
+    zk_timing_begin(ctx, "group_exchange_rows");
+    cudaError_t ce = cudaSuccess;
+    for (size_t c = 0; c < count && ce == cudaSuccess; c++) {
+      if (owners[c] != g->rank) continue;
+      for (uint32_t q = 0; q < g->world && ce == cudaSuccess; q++) {
+        if (q == g->rank) continue;
+        size_t lo = (size_t)q * rows + height - halo, len = rows + 2 * halo;
+        if (len >= height) { lo = 0; len = height; }
+        lo %= height;
+        size_t first = std::min(len, height - lo);
+        for (int piece = 0; piece < 2 && ce == cudaSuccess; piece++) {
+          size_t off = piece == 0 ? lo : 0, nrow = piece == 0 ? first : len - first;
+          if (!nrow) continue;
+          char* src = cols[c] + off * 32;
+          ce = cudaMemcpyAsync(rb->peer[q] + (src - rb->local), src, nrow * 32, cudaMemcpyDeviceToDevice, ctx->stream);
+        }
+      }
+    }
+    zk_timing_end(ctx);
+    if (ce != cudaSuccess) ZK_FAIL(ctx, ZK_ERR_CUDA, "group: peer copy of rows: %s", cudaGetErrorString(ce));
+    ZK_TRY(zk_group_p2p_push(g, ctx, pp, g->d_dummy + 16 * g->rank, 16));
+    return zk_group_p2p_finish(g, ctx, g->d_dummy, 16);
+  }
   Nccl* N = nccl();
   if (!N || !N->send || !N->recv || !N->group_start || !N->group_end) ZK_FAIL(ctx, ZK_ERR_STATE, "group: NCCL point-to-point not available");
   void* comm = ctx == g->ctx ? g->comm : g->comm2;
-  const size_t rows = height / g->world;
   zk_timing_begin(ctx, "group_exchange_rows");
   int r = N->group_start();
   for (size_t c = 0; c < count && r == 0; c++) {

@@ -38,6 +38,8 @@ bool zk_group_p2p_begin(zk_group* g, zk_ctx* on, size_t bytes_per_rank, zk_p2p_p
 int zk_group_p2p_finish(zk_group* g, zk_ctx* on, void* d_buf, size_t bytes_per_rank);
 int zk_group_p2p_push(zk_group* g, zk_ctx* on, const zk_p2p_push& pp, const void* my_segment, size_t bytes);
 int zk_group_p2p_error(zk_group* g, zk_ctx* on);
+int zk_group_register(zk_group* g, void* base, size_t bytes);
+size_t zk_pk_witness_bytes(zk_pk* pk);
 int zk_group_exchange_rows(zk_group* g, zk_ctx* on, char* const* cols, const uint32_t* owners, size_t count, size_t height, size_t halo);
 extern "C" uint32_t zk_group_rank(const zk_group* g);
 extern "C" uint32_t zk_group_world(const zk_group* g);
@@ -742,6 +744,12 @@ extern "C" int zk_pkey_set_group(zk_pkey* K, zk_group* g) {
     // rows of the extended domain that evaluate_h reads relative to its own row: rotation * 2^(ext_k - k)
     K->halo_rows = (size_t)K->max_rotation * (K->ext_n / K->n);
   }
+  // the evaluate_h witness slots have the same layout on every rank: map the peers' copies, so that the row exchange of the
+  // cosets becomes plain device-to-device copies into the peers' slots (collective: every rank makes this call)
+  if (g && zk_group_world(g) > 1 && K->pk) ZK_TRY(zk_group_register(g, zk_pk_witness_slot(K->pk, 0), zk_pk_witness_bytes(K->pk)));
+  // likewise the staging area of the coefficient forms and the h(X) rows (their all-gathers become peer copies)
+  if (g && zk_group_world(g) > 1 && K->d_stage_p) ZK_TRY(zk_group_register(g, K->d_stage_p, K->stage_cols * K->n * 32));
+  if (g && zk_group_world(g) > 1 && K->d_hext) ZK_TRY(zk_group_register(g, K->d_hext, K->ext_n * 32));
   return ZK_OK;
 }
 extern "C" size_t zk_proof_randoms(const zk_pkey* K) {
