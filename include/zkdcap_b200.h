@@ -431,8 +431,8 @@ int zk_pkey_set_group(zk_pkey* pk, zk_group* g);
 int zk_msm_sharded_dev(zk_group* g, const zk_fr* d_scalars, int which, size_t n_local, zk_g1* d_out);
 /* How `count` commitments over n bases are split: *mode 0 = rank commits columns [*lo, *hi) (every rank's share padded
  * to *per columns), *mode 1 = every rank commits all of them over the bases [*lo, *hi).  Pure host function. */
-/* Cost-aware plan of a batch of `count` >= world column commitments: owner[i] = rank of column i, or `world` for the
- * count % world most expensive columns, which every rank shares by base range (host logic). */
+/* Cost-aware plan of a batch of `count` >= world column commitments: owner[i] = rank of column i (longest first onto the
+ * least loaded rank, at most ceil(count / world) columns per rank; host logic). */
 void zk_group_balance_plan(const uint32_t* cost, size_t count, uint32_t world, uint32_t* owner);
 void zk_group_shard_plan(uint32_t rank, uint32_t world, size_t count, size_t n, int* mode, size_t* per, size_t* lo, size_t* hi);
 

@@ -497,8 +497,11 @@ struct Fp {
     return acc;
   }
   ZK_HD_NOINL static Fp pow_u64(const Fp& a, uint64_t e) {
-    Fp acc = one();
-    for (int i = 63; i >= 0; i--) {
+    if (!e) return one();
+    int top = 63;
+    while (!((e >> top) & 1)) top--;          // start at the leading one: no squarings of 1 (most exponents here are < 2^21)
+    Fp acc = a;
+    for (int i = top - 1; i >= 0; i--) {
       acc = acc.sqr();
       if ((e >> i) & 1) acc = acc * a;
     }

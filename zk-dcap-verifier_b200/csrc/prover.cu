@@ -321,13 +321,13 @@ int commit_enqueue(zk_pkey* K, const char* d_polys, size_t count, int which, siz
   return ZK_OK;
 }
 // Cost-aware split of a batch of `count` >= world column commitments over the group.  Columns differ by an order of magnitude
-// in cost (a column of bits has one non-zero window per scalar, a column of field elements sixteen), and a batch size that is not
-// a multiple of the group leaves whole columns of difference: round-robin left msm_accumulate at 32.3 ms per proof on 2 GPUs
-// and 10.7 ms on 8 against 28.5 / 7.2 for an even split.  Every rank measures the same per-column cost (non-zero 16-bit
-// windows, one pass over the batch), so all ranks derive the same plan without talking: the count % world MOST expensive columns
-// are shared by base range (every rank takes 1 / world of each), the others are dealt to ranks longest-first with the same number
-// of columns per rank.  A rank's columns are gathered into a contiguous scratch area (device copies, 16 MB per column), committed
-// in one batch whose last kernel pushes the points to the peers, and a small kernel puts the points back in column order.
+// in cost (a column of bits has one non-zero window per scalar, a column of field elements sixteen): round-robin left
+// msm_accumulate at 32.3 ms per proof on 2 GPUs and 10.7 ms on 8 against 28.5 / 7.2 for an even split.  Every rank measures the
+// same per-column cost (non-zero 16-bit windows, one pass over the batch), so all ranks derive the same plan without talking
+// (zk_group_balance_plan: longest first onto the least loaded rank).  A rank's columns are gathered into a contiguous scratch
+// area when they are not adjacent (device copies, 16 MB per column), committed in ONE batch whose last kernel pushes the points
+// to the peers, and a small kernel puts the points back in column order.  (Sharing the count mod G remainder by base range was
+// tried first: the extra, tiny MSM pipeline per batch cost more latency than the even split saved.)
 int commit_balanced(zk_pkey* K, const char* d_polys, size_t count, int which, size_t slot) {
   zk_ctx* ctx = K->ctx;
   const uint32_t world = zk_group_world(K->group), rank = zk_group_rank(K->group);
@@ -342,72 +342,55 @@ int commit_balanced(zk_pkey* K, const char* d_polys, size_t count, int which, si
   std::vector<unsigned int> cost(count);
   ZK_CUDA(ctx, cudaMemcpyAsync(cost.data(), K->d_cost, count * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
   ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const size_t rem = count % world, per = count / world;
   std::vector<uint32_t> owner(count);
   zk_group_balance_plan(cost.data(), count, world, owner.data());
-  std::vector<uint32_t> shared;                                                // by base range
   std::vector<std::vector<uint32_t>> owned(world);
-  for (size_t i = 0; i < count; i++) { if (owner[i] == world) shared.push_back((uint32_t)i); else owned[owner[i]].push_back((uint32_t)i); }
-  if (shared.size() != rem) ZK_FAIL(ctx, ZK_ERR_STATE, "prover: balance plan");
-  for (auto& o : owned) if (o.size() != per) ZK_FAIL(ctx, ZK_ERR_STATE, "prover: balance plan");
-  // scratch: my `per` columns, then the `rem` shared ones
-  const size_t need = (per + rem) * nb;
+  for (size_t i = 0; i < count; i++) { if (owner[i] >= world) ZK_FAIL(ctx, ZK_ERR_STATE, "prover: balance plan"); owned[owner[i]].push_back((uint32_t)i); }
+  size_t per = 0;
+  for (auto& o : owned) per = std::max(per, o.size());
+  // scratch: my columns, contiguous
+  const size_t need = per * nb;
   if (K->balance_cap < need) {
     if (K->d_balance) { ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(K->d_balance); K->d_balance = nullptr; K->balance_cap = 0; }
     ZK_CUDA(ctx, cudaMalloc(&K->d_balance, need));
     K->balance_cap = need;
   }
-  auto gather = [&](const std::vector<uint32_t>& cols, char* dst) -> int {
-    for (size_t j = 0; j < cols.size();) {                     // runs of adjacent columns in one copy
+  const std::vector<uint32_t>& mine_cols = owned[rank];
+  const char* src = K->d_balance;
+  bool contiguous = !mine_cols.empty();
+  for (size_t j = 1; j < mine_cols.size(); j++) contiguous = contiguous && mine_cols[j] == mine_cols[j - 1] + 1;
+  if (contiguous) {
+    src = d_polys + (size_t)mine_cols[0] * nb;                  // already adjacent: commit in place
+  } else {
+    for (size_t j = 0; j < mine_cols.size();) {                 // runs of adjacent columns in one copy
       size_t e = j + 1;
-      while (e < cols.size() && cols[e] == cols[e - 1] + 1) e++;
-      ZK_CUDA(ctx, cudaMemcpyAsync(dst + j * nb, d_polys + (size_t)cols[j] * nb, (e - j) * nb, cudaMemcpyDeviceToDevice, ctx->stream));
+      while (e < mine_cols.size() && mine_cols[e] == mine_cols[e - 1] + 1) e++;
+      ZK_CUDA(ctx, cudaMemcpyAsync(K->d_balance + j * nb, d_polys + (size_t)mine_cols[j] * nb, (e - j) * nb, cudaMemcpyDeviceToDevice, ctx->stream));
       j = e;
     }
-    return ZK_OK;
-  };
+  }
   PtRaw* xchg = (PtRaw*)K->d_xchg;
   unsigned int* d_map = K->d_cost + 256;
   struct PushGuard { zk_ctx* c; ~PushGuard() { c->p2p = nullptr; } } guard{ctx};
-  if (per) {
-    ZK_TRY(gather(owned[rank], K->d_balance));
-    zk_p2p_push pp;
-    const size_t seg = per * sizeof(PtRaw);
-    const bool fused = zk_group_p2p_begin(K->group, ctx, seg, &pp);
+  zk_p2p_push pp;
+  const size_t seg = per * sizeof(PtRaw);
+  const bool fused = zk_group_p2p_begin(K->group, ctx, seg, &pp);
+  PtRaw* mine = xchg + (size_t)rank * per;
+  if (!mine_cols.empty()) {
     if (fused) ctx->p2p = &pp;
-    ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)K->d_balance, which, K->n, per, (zk_g1*)(xchg + (size_t)rank * per)));
+    ZK_TRY(zk_msm_batch_dev(ctx, (const zk_fr*)src, which, K->n, mine_cols.size(), (zk_g1*)mine));
     ctx->p2p = nullptr;
-    if (fused) ZK_TRY(zk_group_p2p_finish(K->group, ctx, xchg, seg)); else ZK_TRY(zk_group_allgather(K->group, ctx, xchg, seg));
-    std::vector<unsigned int> map;
-    for (uint32_t r = 0; r < world; r++) for (uint32_t c : owned[r]) map.push_back(c);
-    ZK_CUDA(ctx, cudaMemcpyAsync(d_map, map.data(), map.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
-    ZK_LAUNCH(ctx, "group_scatter", k_scatter_points, blocks_for(map.size() * 8, 128), 128, 0, (const uint4*)xchg, (const unsigned int*)d_map, (uint4*)out,
-              (unsigned int)map.size());
+  } else if (fused) {
+    ZK_CUDA(ctx, cudaMemsetAsync(mine, 0, seg, ctx->stream));
+    ZK_TRY(zk_group_p2p_push(K->group, ctx, pp, mine, seg));
   }
-  if (rem) {
-    char* sh = K->d_balance + per * nb;
-    ZK_TRY(gather(shared, sh));
-    const size_t p = (K->n + world - 1) / world, lo = std::min(K->n, (size_t)rank * p), hi = std::min(K->n, (size_t)(rank + 1) * p);
-    zk_p2p_push pp;
-    const size_t seg = rem * sizeof(PtRaw);
-    const bool fused = zk_group_p2p_begin(K->group, ctx, seg, &pp);
-    PtRaw* mine = xchg + (size_t)rank * rem;
-    if (hi > lo) {
-      if (fused) ctx->p2p = &pp;
-      ZK_TRY(zk_msm_range_batch_dev(ctx, (const zk_fr*)sh, which, K->n, lo, hi - lo, rem, (zk_g1*)mine));
-      ctx->p2p = nullptr;
-    } else {
-      ZK_CUDA(ctx, cudaMemsetAsync(mine, 0, seg, ctx->stream));
-      if (fused) ZK_TRY(zk_group_p2p_push(K->group, ctx, pp, mine, seg));
-    }
-    if (fused) ZK_TRY(zk_group_p2p_finish(K->group, ctx, xchg, seg)); else ZK_TRY(zk_group_allgather(K->group, ctx, xchg, seg));
-    PtRaw* summed = xchg + (size_t)world * rem;
-    ZK_TRY(zk_g1_sum_strided_dev(ctx, (const zk_g1*)xchg, world, rem, (zk_g1*)summed));
-    unsigned int* d_map2 = K->d_cost + 512;
-    ZK_CUDA(ctx, cudaMemcpyAsync(d_map2, shared.data(), rem * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
-    ZK_LAUNCH(ctx, "group_scatter", k_scatter_points, blocks_for(rem * 8, 128), 128, 0, (const uint4*)summed, (const unsigned int*)d_map2, (uint4*)out,
-              (unsigned int)rem);
-  }
+  if (fused) ZK_TRY(zk_group_p2p_finish(K->group, ctx, xchg, seg)); else ZK_TRY(zk_group_allgather(K->group, ctx, xchg, seg));
+  // xchg[r * per + j] = the point of owned[r][j]
+  std::vector<unsigned int> map((size_t)world * per, 0xFFFFFFFFu);
+  for (uint32_t r = 0; r < world; r++) for (size_t j = 0; j < owned[r].size(); j++) map[(size_t)r * per + j] = owned[r][j];
+  ZK_CUDA(ctx, cudaMemcpyAsync(d_map, map.data(), map.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+  ZK_LAUNCH(ctx, "group_scatter", k_scatter_points, blocks_for(map.size() * 8, 128), 128, 0, (const uint4*)xchg, (const unsigned int*)d_map, (uint4*)out,
+            (unsigned int)map.size());
   return ZK_OK;
 }
 int commit_fetch(zk_pkey* K, size_t count, std::vector<HostPoint>* out) {
@@ -709,22 +692,22 @@ extern "C" int zk_pkey_set_transcript(zk_pkey* K, int kind) {
   return ZK_OK;
 }
 // The plan of a cost-balanced batch of commitments (host logic, also exercised by the CPU tests): owner[i] = the rank that
-// commits column i, or `world` for the count % world most expensive columns, which all ranks share by base range.  Every rank
-// gets exactly count / world whole columns, dealt longest-first to the least loaded rank; ties go to the lower index / rank, so
-// the plan is a pure function of the costs.
+// commits column i.  Columns are dealt longest-first to the least loaded rank that still has room for one more column
+// (ceil(count / world) per rank); ties go to the lower index / rank, so the plan is a pure function of the costs.  With costs
+// spread over a factor of sixteen (columns of bits next to columns of field elements) the ranks that get one column more get
+// cheap ones, which evens the loads out without splitting any column.
 extern "C" void zk_group_balance_plan(const uint32_t* cost, size_t count, uint32_t world, uint32_t* owner) {
   if (!world) return;
   std::vector<uint32_t> order(count);
   for (size_t i = 0; i < count; i++) order[i] = (uint32_t)i;
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
-  const size_t rem = count % world, per = count / world;
-  for (size_t i = 0; i < rem; i++) owner[order[i]] = world;
+  const size_t cap = (count + world - 1) / world;
   std::vector<uint64_t> load(world, 0);
   std::vector<size_t> have(world, 0);
-  for (size_t i = rem; i < count; i++) {
+  for (size_t i = 0; i < count; i++) {
     uint32_t best = world;
     for (uint32_t r = 0; r < world; r++)
-      if (have[r] < per && (best == world || load[r] < load[best])) best = r;
+      if (have[r] < cap && (best == world || load[r] < load[best])) best = r;
     owner[order[i]] = best; have[best]++; load[best] += (uint64_t)cost[order[i]] + 1;
   }
 }
@@ -750,6 +733,7 @@ extern "C" int zk_pkey_set_group(zk_pkey* K, zk_group* g) {
   // likewise the staging area of the coefficient forms and the h(X) rows (their all-gathers become peer copies)
   if (g && zk_group_world(g) > 1 && K->d_stage_p) ZK_TRY(zk_group_register(g, K->d_stage_p, K->stage_cols * K->n * 32));
   if (g && zk_group_world(g) > 1 && K->d_hext) ZK_TRY(zk_group_register(g, K->d_hext, K->ext_n * 32));
+  if (g && zk_group_world(g) > 1 && K->d_lookup) ZK_TRY(zk_group_register(g, K->d_lookup, ((size_t)K->n_lookups * 5 + K->n_sets) * K->n * 32));
   return ZK_OK;
 }
 extern "C" size_t zk_proof_randoms(const zk_pkey* K) {
@@ -1102,6 +1086,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   const uint32_t l_per = L ? (L + gworld - 1) / gworld : 1;
   auto lookup_owner = [&](uint32_t l) { return gworld > 1 ? l / l_per : 0u; };
   const uint32_t l_lo = std::min(L, grank * l_per), l_hi = std::min(L, (grank + 1) * l_per);
+  const bool share_lookup_columns = gworld > 1 && L && !getenv("ZK_GROUP_NO_LOOKUP_SHARE");
   if (L) {
     std::vector<const void*> cols(K->CL.n_slots);
     for (uint32_t i = 0; i < K->n_fixed; i++) cols[K->CL.prog.off_fixed + i] = K->d_fixed_values + i * nb;
@@ -1149,11 +1134,23 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
       for (uint32_t r = 0; r < gworld; r++) flags |= all[4 * r];
     }
     if (flags & 6u) ZK_FAIL(ctx, ZK_ERR_ARG, "zk_create_proof: ConstraintSystemFailure (a lookup input is not in its table)");
-    std::vector<CommitJob> cj;
-    for (uint32_t l = 0; l < L; l++) cj.push_back({lk(l, 2), lookup_owner(l)});
-    for (uint32_t l = 0; l < L; l++) cj.push_back({lk(l, 3), lookup_owner(l)});
     std::vector<HostPoint> pts;
-    ZK_TRY(commit_jobs(K, cj, ZK_BASES_G_LAGRANGE, &pts));
+    if (share_lookup_columns) {
+      // A lookup's permuted columns exist only on its owner, and owners hold 1 or 2 lookups each (11 lookups on 8 GPUs): their
+      // commitments -- the most expensive columns of the proof -- would follow that imbalance.  Every owner copies its columns
+      // into all peers' lookup areas (16 MB each over NVLink, one flag round), and the 2 L columns are then committed as a
+      // replicated batch with the cost-balanced split.
+      std::vector<char*> cols; std::vector<uint32_t> owners;
+      for (int plane = 2; plane <= 3; plane++)
+        for (uint32_t l = 0; l < L; l++) { cols.push_back(lk(l, plane)); owners.push_back(lookup_owner(l)); }
+      ZK_TRY(zk_group_exchange_rows(K->group, ctx, cols.data(), owners.data(), cols.size(), K->n, K->n));
+      ZK_TRY(commit(K, lk(0, 2), 2 * (size_t)L, ZK_BASES_G_LAGRANGE, &pts));
+    } else {
+      std::vector<CommitJob> cj;
+      for (uint32_t l = 0; l < L; l++) cj.push_back({lk(l, 2), lookup_owner(l)});
+      for (uint32_t l = 0; l < L; l++) cj.push_back({lk(l, 3), lookup_owner(l)});
+      ZK_TRY(commit_jobs(K, cj, ZK_BASES_G_LAGRANGE, &pts));
+    }
     for (uint32_t l = 0; l < L; l++) ZK_TRY(write_points({pts[l], pts[L + l]}));
   }
   Fr beta = tr.squeeze_challenge();
@@ -1167,7 +1164,7 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
   };
   // single GPU: the permutation and lookup products are committed together (17 columns for the QE3 shape) -- one call's
   // fixed latency less; a group keeps its two differently sharded commitments
-  const bool merged_products = K->n_sets && L && !(K->group && zk_group_world(K->group) > 1) && !getenv("ZK_PROVER_SPLIT_PRODUCTS");
+  const bool merged_products = K->n_sets && L && (!(K->group && zk_group_world(K->group) > 1) || share_lookup_columns) && !getenv("ZK_PROVER_SPLIT_PRODUCTS");
   if (K->n_sets) {
     // every column set at once: z_s = seed_s * (exclusive prefix products of num/den), seed_{s+1} = z_s[usable]
     const uint32_t NS = K->n_sets;
@@ -1231,6 +1228,11 @@ extern "C" int zk_create_proof(zk_pkey* K, const zk_fr* const* advice_values, co
     }));
     if (merged_products) {
       // one batch of L + n_sets columns; the transcript takes the permutation points first
+      if (share_lookup_columns) {      // the owners' Z columns go to every rank first (see commit_permuted above)
+        std::vector<char*> cols; std::vector<uint32_t> owners;
+        for (uint32_t l = 0; l < L; l++) { cols.push_back(lk(l, 4)); owners.push_back(lookup_owner(l)); }
+        ZK_TRY(zk_group_exchange_rows(K->group, ctx, cols.data(), owners.data(), cols.size(), K->n, K->n));
+      }
       std::vector<HostPoint> pts;
       ZK_TRY(commit(K, lk(0, 4), L + K->n_sets, ZK_BASES_G_LAGRANGE, &pts));
       std::vector<HostPoint> perm(pts.begin() + L, pts.end()), look(pts.begin(), pts.begin() + L);

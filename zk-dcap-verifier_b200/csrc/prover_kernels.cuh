@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) k_batch_invert(uint4* v, uint4* scratch, 
 }
 
 // table[i] = z^i, i < n: thread t starts at z^(t*kPowChunk) by square-and-multiply
-constexpr int kPowChunk = 16;
+constexpr int kPowChunk = 64;      // ~20 squarings / multiplications to reach the chunk's first power, then one multiplication per entry
 __global__ void __launch_bounds__(128) k_pow_table(Fr z, uint4* table, size_t n) {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t lo = t * kPowChunk, hi = lo + kPowChunk < n ? lo + kPowChunk : n;
@@ -254,7 +254,8 @@ __global__ void k_eval_final(const uint4* partial, uint32_t nchunks, uint4* out,
 __global__ void __launch_bounds__(256) k_column_cost(const uint4* cols, size_t n, unsigned int* cost) {
   const size_t col = blockIdx.y;
   unsigned int mine = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  // every 8th row is enough for a RELATIVE cost (the columns of one batch hold the same kind of value in every row)
+  for (size_t i = 8 * (blockIdx.x * (size_t)blockDim.x + threadIdx.x); i < n; i += 8 * (size_t)gridDim.x * blockDim.x) {
     const Fr v = Fr::load(cols + 2 * (col * n + i)).from_mont();
 #pragma unroll
     for (int l = 0; l < 8; l++) mine += ((v.l[l] & 0xFFFFu) != 0) + ((v.l[l] >> 16) != 0);
@@ -266,7 +267,8 @@ __global__ void __launch_bounds__(256) k_column_cost(const uint4* cols, size_t n
 __global__ void k_scatter_points(const uint4* src, const unsigned int* map, uint4* out, unsigned int count) {
   unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count * 8) return;
-  out[8 * (size_t)map[t >> 3] + (t & 7)] = src[t];
+  const unsigned int dst = map[t >> 3];
+  if (dst != 0xFFFFFFFFu) out[8 * (size_t)dst + (t & 7)] = src[t];       // padding slots of ranks with fewer columns
 }
 
 // out[i] = sum_j scalars[j] * polys[j][i]   (+ acc_in[i] when given)
