@@ -562,7 +562,13 @@ class ProofWorkload:
         for t in ths:
             t.join()
         self.last_inflight = out[0]
-        self.inflight_identical = getattr(self, "inflight_identical", True) and all(o == out[0] for o in out)
+        ref = getattr(self, "inflight_ref", None) or out[0]
+        for i, o in enumerate(out):
+            if o != ref:                                  # diagnostic, never fatal: which transcript items differ
+                self.inflight_mismatches = getattr(self, "inflight_mismatches", 0) + 1
+                items = [j // 32 for j in range(0, max(len(o), len(ref)), 32) if o[j:j + 32] != ref[j:j + 32]]
+                print("[bench] device %s: in-flight prover %d returned a different proof: %d of %d 32-byte items differ, first %d"
+                      % (self.dev, i, len(items), len(ref) // 32, items[0] if items else -1), file=sys.stderr, flush=True)
         return len(out)
 
     serialize = False
@@ -950,6 +956,7 @@ def main():
         # throughput with several proofs in flight per GPU: the latency- and atomic-bound stages of one proof overlap
         # the integer-pipe-bound stages of another (every rank does this; rank 0 reports max over ranks)
         wl.enable_inflight(args.inflight, wl._keygen_inputs)
+        wl.inflight_ref = proof_ref
         for _ in range(2):
             wl.step_inflight()
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -959,13 +966,17 @@ def main():
             done += wl.step_inflight()
         b1.record(); barrier()
         tb = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        bad = torch.tensor([getattr(wl, "inflight_mismatches", 0)], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bad, op=dist.ReduceOp.SUM)
         batch = {"inflight_per_gpu": args.inflight, "proofs": done * world, "ms": float(tb.item()),
                  "value": world * done / (float(tb.item()) * 1e-3), "unit": "proofs/s",
-                 "proofs_identical": bool(wl.inflight_identical and wl.last_inflight == proof_ref),
+                 "proofs_identical": int(bad.item()) == 0, "mismatching_proofs": int(bad.item()),
+                 "proofs_compared": (done + 2 * args.inflight) * world,
                  "note": "independent provers on one GPU (own streams, key and work area; shared SRS), one host thread each; "
-                         "`proofs_identical`: every proof of every prover equals the proof computed alone (rank 0's view)"}
+                         "`proofs_identical`: every proof of every prover on every rank (warm-up included) equals the proof "
+                         "that rank computed alone"}
     # ---- one proof / one MSM over all GPUs (strong scaling), measured in the SAME run so that the driver's --gpus N
     # lines carry them ----------------------------------------------------------------------------
     sharded_proof = sharded_msm = None
