@@ -360,8 +360,10 @@ zk_pk* zk_pkey_pk(zk_pkey* pk);
 zk_ctx* zk_pkey_aux_ctx(zk_pkey* pk);
 /* Transcript of the key's proofs: halo2's Blake2bWrite / Challenge255 (default; circuits/src/sgx_dcap_verifier.rs:813)
  * or snark-verifier's EvmTranscript (Keccak-256, uncompressed big-endian points; gen_evm_proof_shplonk at
- * crates/p256-ecdsa/src/base.rs:193-199).  The Poseidon transcript of gen_proof (base.rs:200-211) is not implemented. */
-typedef enum { ZK_TRANSCRIPT_BLAKE2B = 0, ZK_TRANSCRIPT_EVM = 1 } zk_transcript_kind;
+ * crates/p256-ecdsa/src/base.rs:193-199), or snark-verifier's PoseidonTranscript over the native loader (T = 5, RATE = 4,
+ * R_F = 8, R_P = 60; gen_proof at base.rs:200-211, the CLI's verifier at bin/src/main.rs:239-252): points absorbed as
+ * (x mod r, y mod r) and written compressed in the halo2curves >= 0.4 encoding, challenges = the sponge output. */
+typedef enum { ZK_TRANSCRIPT_BLAKE2B = 0, ZK_TRANSCRIPT_EVM = 1, ZK_TRANSCRIPT_POSEIDON = 2 } zk_transcript_kind;
 int zk_pkey_set_transcript(zk_pkey* pk, int kind);
 /* Number of Fr::random draws one create_proof makes for this circuit. */
 size_t zk_proof_randoms(const zk_pkey* pk);
@@ -395,6 +397,11 @@ typedef struct {
 /* ParamsKZG.g2 / s_g2 between the SRS file encodings (zk_params_read* returns them as the file holds them: 64 compressed
  * bytes for the PROCESSED formats, 128 bytes of Montgomery limbs for RAW_BYTES) and the 128 uncompressed canonical bytes
  * zk_verify_proof consumes.  Host code (one Fq2 square root).  Errors: encodings off the curve / not canonical. */
+/* The Poseidon permutation behind ZK_TRANSCRIPT_POSEIDON (host code; parameters by the Grain LFSR of the Poseidon paper for
+ * width t <= 16, r_f full and r_p partial rounds over bn256::Fr), in place on `state[t]`; and the transcript's sponge (snark-verifier
+ * `Poseidon::{update, squeeze}`, T = 5, RATE = 4): absorbs `count` elements and writes `squeezes` (>= 1) successive outputs. */
+int zk_poseidon_permute(zk_fr* state, uint32_t t, uint32_t r_f, uint32_t r_p);
+int zk_poseidon_hash(const zk_fr* elements, size_t count, zk_fr* out, uint32_t squeezes);
 int zk_g2_decode(int format, const uint8_t* in, uint8_t out_uncompressed[128]);
 int zk_g2_encode(int format, const uint8_t in_uncompressed[128], uint8_t* out);
 

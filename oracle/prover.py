@@ -218,6 +218,71 @@ class EvmRead(EvmWrite):
         return len(self.rbuf)
 
 
+class PoseidonWrite:
+    """snark-verifier `PoseidonTranscript<G1Affine, NativeLoader, Vec<u8>, 5, 4, 8, 60>` (oracle/poseidon.py; the transcript of
+    `gen_proof`, crates/p256-ecdsa/src/base.rs:200-211, and of the CLI's verifier, bin/src/main.rs:242): a point is absorbed as
+    (x mod r, y mod r), a scalar as itself, a challenge is the sponge's output element.  Points are written compressed in the
+    encoding of the halo2curves version that stack pins (y's parity in bit 6: `compress_point_v04`, the encoding of the golden
+    bin/assets/proof.bin), scalars as canonical little-endian bytes."""
+
+    def __init__(self):
+        from .poseidon import Sponge
+        self.sponge = Sponge()
+        self.proof = bytearray()
+
+    def squeeze_challenge(self):
+        return self.sponge.squeeze()
+
+    def common_point(self, pt):
+        if pt is None:
+            raise ValueError("Invalid elliptic curve point encoding in proof")
+        self.sponge.update([pt[0] % R, pt[1] % R])
+
+    def common_scalar(self, s):
+        self.sponge.update([s])
+
+    def write_point(self, pt):
+        self.common_point(pt)
+        self.proof += compress_point_v04(pt)
+
+    def write_scalar(self, s):
+        self.common_scalar(s)
+        self.proof += s.to_bytes(32, "little")
+
+    def finalize(self):
+        return bytes(self.proof)
+
+
+class PoseidonRead(PoseidonWrite):
+    def __init__(self, proof):
+        super().__init__()
+        self.rbuf, self.pos = bytes(proof), 0
+
+    def read_point(self):
+        b = self.rbuf[self.pos:self.pos + 32]
+        if len(b) != 32:
+            raise ValueError("proof too short")
+        self.pos += 32
+        pt = decompress_point_v04(b)
+        self.common_point(pt)
+        return pt
+
+    def read_scalar(self):
+        b = self.rbuf[self.pos:self.pos + 32]
+        if len(b) != 32:
+            raise ValueError("proof too short")
+        self.pos += 32
+        s = int.from_bytes(b, "little")
+        if s >= R:
+            raise ValueError("invalid scalar encoding")
+        self.common_scalar(s)
+        return s
+
+    @property
+    def buf_len(self):
+        return len(self.rbuf)
+
+
 class Randoms:
     """The caller's RNG, pre-drawn: element i is the i-th `Fr::random(&mut rng)` create_proof would make."""
 

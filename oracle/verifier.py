@@ -15,7 +15,7 @@ Only tests/, __graft_entry__.smoke() and bench.py's checking leg may import this
 """
 from . import pairing
 from . import pymodel as pm
-from .prover import (Blake2bRead, EvmRead, construct_intermediate_sets, eval_small, evaluate_vanishing_polynomial,
+from .prover import (Blake2bRead, EvmRead, PoseidonRead, construct_intermediate_sets, eval_small, evaluate_vanishing_polynomial,
                      lagrange_interpolate, rotate_omega)
 
 R = pm.R_MOD
@@ -69,7 +69,8 @@ def msm_eval(terms):
 def verify_proof(params, vk, cs, k, instances, proof, transcript="blake2b"):
     """params: {"g0": G1 generator used by the SRS (affine ints), "g2": G2, "s_g2": [s]G2}.
     vk: {"fixed_commitments", "permutation_commitments", "transcript_repr"}.  transcript: "blake2b" (Blake2bRead,
-    Challenge255) or "evm" (snark-verifier EvmTranscript, Keccak-256).  Returns True / False."""
+    Challenge255), "evm" (snark-verifier EvmTranscript, Keccak-256) or "poseidon" (snark-verifier PoseidonTranscript, the
+    CLI's verifier at bin/src/main.rs:239-252).  Returns True / False."""
     try:
         return _verify(params, vk, cs, k, instances, proof, transcript)
     except (ValueError, KeyError, ZeroDivisionError):
@@ -79,7 +80,7 @@ def verify_proof(params, vk, cs, k, instances, proof, transcript="blake2b"):
 def _verify(params, vk, cs, k, instances, proof, transcript="blake2b"):
     n, bf, d = 1 << k, cs.blinding_factors(), cs.degree()
     chunk = d - 2
-    tr = Blake2bRead(proof) if transcript == "blake2b" else EvmRead(proof)
+    tr = {"blake2b": Blake2bRead, "evm": EvmRead, "poseidon": PoseidonRead}[transcript](proof)
     if len(instances) != cs.num_instance_columns:
         return False
     tr.common_scalar(vk["transcript_repr"])

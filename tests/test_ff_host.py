@@ -127,17 +127,17 @@ def test_signed_digit_recoding(ffh, c):
         assert np.array_equal(d, d2)
 
 
-@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("kind", [0, 1, 2])
 def test_transcripts_host_build_match_python(ffh, kind):
-    """csrc/transcript.hpp -- Blake2b-512 with personalisation / Challenge255 / point compression (kind 0) and the
-    Keccak-256 EVM transcript (kind 1) -- replayed on the host against oracle/prover.py's transcripts, across block
-    boundaries."""
+    """csrc/transcript.hpp -- Blake2b-512 with personalisation / Challenge255 / point compression (kind 0), the
+    Keccak-256 EVM transcript (kind 1) and the Poseidon transcript (kind 2: sponge, points absorbed mod r, bit-6 point
+    compression) -- replayed on the host against oracle/prover.py's transcripts, across block / RATE boundaries."""
     import ctypes as C
     import random
     from oracle import prover as op
     from oracle import pymodel as pm
     rnd = random.Random(7 + kind)
-    t = op.Blake2bWrite() if kind == 0 else op.EvmWrite()
+    t = [op.Blake2bWrite, op.EvmWrite, op.PoseidonWrite][kind]()
     ops = bytearray()
     want_ch = []
     pts = [pm.ec_mul(rnd.randrange(1, pm.R_MOD), (1, 2)) for _ in range(6)]

@@ -201,6 +201,29 @@ def test_first_phase_challenge_and_instance(ctx):
     assert len(got) > 0
 
 
+@pytest.mark.parametrize("shape,k", [("toy", 6), ("qe3", 9)])
+def test_poseidon_transcript_proof_bytes(ctx, shape, k):
+    """zk_pkey_set_transcript(POSEIDON): snark-verifier's PoseidonTranscript (gen_proof, crates/p256-ecdsa/src/base.rs:200-211):
+    bytes equal to the CPU prover's under the same transcript, accepted by both verifiers"""
+    case = pc.make_case(shape, k, 12)
+    p = pc.params_for(k)
+    params = zk.ParamsKZG(k, p["g"], p["g_lagrange"], ctx, precompute=True)
+    key = zk.ProverKey(params, case["circ"], case["fixed"], case["mapping"])
+    key.set_transcript("poseidon")
+    opk = pc.oracle_key(case)
+    want = op.create_proof(orc, p, opk, case["circ"], case["advice"], case["instances_int"], case["randoms"], transcript=op.PoseidonWrite())
+    got = key.create_proof(case["advice"], case["instances_limbs"], case["randoms"])
+    assert got == want, "first differing item %d" % first_diff(got, want)
+    assert ov.verify_proof(pc.verifier_params(), opk["vk"], case["cs"], k, case["instances_int"], got, transcript="poseidon")
+    fc, pcm = key.vk_commitments()
+    vp = pc.verifier_params()
+    g2b = lambda q: b"".join(v.to_bytes(32, "little") for v in (q[0][0], q[0][1], q[1][0], q[1][1]))
+    assert zk.verify_proof(case["circ"], fc, pcm, pm.affine_to_limbs([(1, 2)])[0], g2b(vp["g2"]), g2b(vp["s_g2"]),
+                           case["instances_limbs"], got, transcript="poseidon")
+    assert not zk.verify_proof(case["circ"], fc, pcm, pm.affine_to_limbs([(1, 2)])[0], g2b(vp["g2"]), g2b(vp["s_g2"]),
+                               case["instances_limbs"], got, transcript="blake2b")
+
+
 def test_evm_transcript_proof_bytes(ctx):
     """zk_pkey_set_transcript(EVM): Keccak-256 transcript, uncompressed big-endian points"""
     case = pc.make_case("toy", 6, 8)

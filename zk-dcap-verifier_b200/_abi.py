@@ -72,7 +72,7 @@ VS_CONSTANT, VS_INTERMEDIATE, VS_FIXED, VS_ADVICE, VS_INSTANCE, VS_CHALLENGE, VS
 CALC_ADD, CALC_SUB, CALC_MUL, CALC_SQUARE, CALC_DOUBLE, CALC_NEGATE, CALC_HORNER, CALC_STORE = range(8)
 COL_ADVICE, COL_FIXED, COL_INSTANCE = range(3)
 BASES_HOST, BASES_G, BASES_G_LAGRANGE = range(3)
-TRANSCRIPTS = {"blake2b": 0, "evm": 1}
+TRANSCRIPTS = {"blake2b": 0, "evm": 1, "poseidon": 2}
 
 # every symbol include/zkdcap_b200.h declares
 SYMBOLS = [
@@ -92,7 +92,7 @@ SYMBOLS = [
     "zk_pk_upload", "zk_pk_destroy", "zk_pk_domain", "zk_pk_program_stats", "zk_evalh_generate_source", "zk_pk_evaluator_kind", "zk_pk_evaluator_log",
     "zk_evaluate_h", "zk_evaluate_h_dev",
     "zk_keygen", "zk_pkey_destroy", "zk_pkey_vk_commitments", "zk_pkey_pk", "zk_pkey_aux_ctx", "zk_pkey_set_transcript", "zk_proof_randoms", "zk_proof_max_bytes",
-    "zk_create_proof", "zk_verify_proof", "zk_g2_decode", "zk_g2_encode",
+    "zk_create_proof", "zk_verify_proof", "zk_g2_decode", "zk_g2_encode", "zk_poseidon_permute", "zk_poseidon_hash",
     "zk_group_unique_id", "zk_group_create", "zk_group_destroy", "zk_group_rank", "zk_group_world", "zk_group_p2p_enabled", "zk_pkey_set_group", "zk_msm_sharded_dev",
     "zk_group_shard_plan", "zk_group_balance_plan",
     "zk_field_op", "zk_bench_modmul", "zk_bench_imad",
@@ -180,6 +180,8 @@ def load():
         "zk_proof_max_bytes": (sz, [vp]),
         "zk_create_proof": (i32, [vp, vp, vp, vp, vp, sz, vp, sz, C.POINTER(sz)]),
         "zk_verify_proof": (i32, [C.POINTER(zk_circuit_desc), C.POINTER(zk_verifier_params), vp, vp, vp, sz, C.POINTER(i32)]),
+        "zk_poseidon_permute": (i32, [vp, u32, u32, u32]),
+        "zk_poseidon_hash": (i32, [vp, sz, vp, u32]),
         "zk_g2_decode": (i32, [i32, vp, vp]),
         "zk_g2_encode": (i32, [i32, vp, vp]),
         "zk_group_unique_id": (i32, [vp]),

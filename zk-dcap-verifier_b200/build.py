@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libzkdcap_b200.so")
 SOURCES = ["api.cu", "ntt.cu", "msm.cu", "evalh.cu", "prover.cu", "group.cu", "params.cu", "verifier.cu"]
-HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", "evalh.cuh", "evalh_compile.hpp", "evalh_codegen.hpp", "prover_kernels.cuh", "transcript.hpp", os.path.join("..", "..", "include", "zkdcap_b200.h")]
+HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", "evalh.cuh", "evalh_compile.hpp", "evalh_codegen.hpp", "prover_kernels.cuh", "transcript.hpp", "poseidon.hpp", os.path.join("..", "..", "include", "zkdcap_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("ZK_NVCC_EXTRA", "").split()

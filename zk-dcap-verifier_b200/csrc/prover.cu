@@ -55,7 +55,7 @@ struct zk_pkey {
   zk_ctx* ctx = nullptr;
   zk_pk* pk = nullptr;             // evaluate_h side (cosets, compiled program); owns its own domain
   zk_domain* dom = nullptr;
-  int transcript_kind = 0;        // ZK_TRANSCRIPT_BLAKE2B / ZK_TRANSCRIPT_EVM
+  int transcript_kind = 0;        // zk_transcript_kind
   zk_group* group = nullptr;      // not owned: the GPUs that share this proof's commitments and h(X) rows
   // second stream: every lagrange_to_coeff / coeff_to_extended of the witness polynomials runs here, overlapping the
   // commitments and the lookup / permutation kernels of the main stream (they only meet again at evaluate_h)
@@ -687,7 +687,7 @@ extern "C" zk_pk* zk_pkey_pk(zk_pkey* K) { return K ? K->pk : nullptr; }
 extern "C" zk_ctx* zk_pkey_aux_ctx(zk_pkey* K) { return K ? K->ctxB : nullptr; }
 extern "C" int zk_pkey_set_transcript(zk_pkey* K, int kind) {
   if (!K) return ZK_ERR_ARG;
-  if (kind != ZK_TRANSCRIPT_BLAKE2B && kind != ZK_TRANSCRIPT_EVM) ZK_FAIL(K->ctx, ZK_ERR_ARG, "zk_pkey_set_transcript: unknown transcript kind %d", kind);
+  if (kind != ZK_TRANSCRIPT_BLAKE2B && kind != ZK_TRANSCRIPT_EVM && kind != ZK_TRANSCRIPT_POSEIDON) ZK_FAIL(K->ctx, ZK_ERR_ARG, "zk_pkey_set_transcript: unknown transcript kind %d", kind);
   K->transcript_kind = kind;
   return ZK_OK;
 }

@@ -116,6 +116,10 @@ inline Fr fr_from_bytes_wide(const uint8_t b[64]) {
   return (lo * r2 + hi * r3).reduce();
 }
 
+}  // namespace zk
+#include "poseidon.hpp"      // needs fr_from_bytes_wide (above)
+namespace zk {
+
 // Keccak-256 (padding 0x01, as Ethereum uses), FIPS 202 permutation
 struct Keccak256 {
   static uint64_t rol(uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
@@ -155,20 +159,31 @@ struct Keccak256 {
   }
 };
 
-constexpr int kTranscriptBlake2b = 0, kTranscriptEvm = 1;      // == zk_transcript_kind of the C ABI
+constexpr int kTranscriptBlake2b = 0, kTranscriptEvm = 1, kTranscriptPoseidon = 2;      // == zk_transcript_kind of the C ABI
 
 // kind 0: halo2's Blake2bWrite / Challenge255 (above).  kind 1: snark-verifier's EvmTranscript ([UPSTREAM?]
 // system/halo2/transcript/evm.rs; gen_evm_proof_shplonk at crates/p256-ecdsa/src/base.rs:193-199): a byte buffer hashed
 // with Keccak-256, points uncompressed (x, y big-endian), scalars big-endian, challenge = keccak(buf ++ [1 if |buf| = 32])
-// read big-endian mod r, the digest becomes the new buffer.
+// read big-endian mod r, the digest becomes the new buffer.  kind 2: snark-verifier's PoseidonTranscript over NativeLoader
+// (poseidon.hpp; `gen_proof`, crates/p256-ecdsa/src/base.rs:200-211): a point is absorbed as (x mod r, y mod r), a scalar as itself,
+// a challenge is the sponge's output; points are written compressed in the halo2curves >= 0.4 encoding that stack pins (y's parity
+// in bit 6 of byte 31 -- the encoding of the reference's bin/assets/proof.bin), scalars as canonical little-endian bytes.
 struct TranscriptWrite {
   int kind = kTranscriptBlake2b;
   Blake2b state;
   std::vector<uint8_t> evm_buf;
+  PoseidonSponge sponge;
   std::vector<uint8_t> proof;
   explicit TranscriptWrite(int kind_ = kTranscriptBlake2b) : kind(kind_), state("Halo2-Transcript") {}
   static void be32(const uint8_t le[32], uint8_t out[32]) { for (int i = 0; i < 32; i++) out[i] = le[31 - i]; }
+  static Fr fq_to_fr(const Fq& v) {           // fe_to_fe: the canonical integer mod r
+    uint8_t wide[64];
+    memset(wide, 0, sizeof wide);
+    f_to_repr(v, wide);
+    return fr_from_bytes_wide(wide);
+  }
   Fr squeeze_challenge() {
+    if (kind == kTranscriptPoseidon) return sponge.squeeze();
     if (kind == kTranscriptEvm) {
       std::vector<uint8_t> data = evm_buf;
       if (evm_buf.size() == 32) data.push_back(1);
@@ -185,6 +200,7 @@ struct TranscriptWrite {
     return fr_from_bytes_wide(d);
   }
   void common_scalar(const Fr& s) {
+    if (kind == kTranscriptPoseidon) { sponge.update(s.reduce()); return; }
     uint8_t b[32];
     f_to_repr(s, b);
     if (kind == kTranscriptEvm) { uint8_t r[32]; be32(b, r); evm_buf.insert(evm_buf.end(), r, r + 32); return; }
@@ -200,6 +216,7 @@ struct TranscriptWrite {
   // absorb only (the verifier replays what it has read)
   bool common_point(const Fq& x, const Fq& y, bool identity) {
     if (identity) return false;
+    if (kind == kTranscriptPoseidon) { sponge.update(fq_to_fr(x)); sponge.update(fq_to_fr(y)); return true; }
     uint8_t bx[32], by[32];
     f_to_repr(x, bx); f_to_repr(y, by);
     if (kind == kTranscriptEvm) {
@@ -224,7 +241,7 @@ struct TranscriptWrite {
       be32(by, r); proof.insert(proof.end(), r, r + 32);
       return true;
     }
-    bx[31] |= (uint8_t)((by[0] & 1) << 7);
+    bx[31] |= (uint8_t)((by[0] & 1) << (kind == kTranscriptPoseidon ? 6 : 7));
     proof.insert(proof.end(), bx, bx + 32);
     return true;
   }

@@ -225,7 +225,13 @@ struct TranscriptRead {
     uint8_t b[32]; memcpy(b, buf + pos, 32); pos += 32;
     bool allz = true; for (int i = 0; i < 32; i++) allz = allz && b[i] == 0;
     if (allz) return false;                                    // the identity cannot be absorbed
-    uint32_t sign = b[31] >> 7; b[31] &= 0x7F;
+    uint32_t sign;
+    if (t.kind == ZK_TRANSCRIPT_POSEIDON) {                      // halo2curves >= 0.4: bit 7 = identity flag, bit 6 = parity of y
+      if (b[31] & 0x80) return false;
+      sign = (b[31] >> 6) & 1u; b[31] &= 0x3F;
+    } else {
+      sign = b[31] >> 7; b[31] &= 0x7F;
+    }
     if (!f_is_canonical<Fq>(b)) return false;
     Fq x = f_canon_bytes<Fq>(b);
     Fq rhs = x.sqr() * x + fq_small(3);
@@ -409,6 +415,28 @@ Fq2 g2_b() { return f2_mul(f2(fq_small(3), Fq::zero()), f2_inv(f2(fq_small(9), F
 void put_canon(uint8_t* o, const Fq& v) { Fq c = v.from_mont(); memcpy(o, c.l, 32); }
 }  // namespace
 
+// The Poseidon permutation / sponge of the transcript (poseidon.hpp), exposed so that the parameter generation can be checked
+// against published values (any width t <= 16) and the sponge against the CPU restatement.  Values in the ABI's Montgomery form.
+extern "C" int zk_poseidon_permute(zk_fr* state, uint32_t t, uint32_t r_f, uint32_t r_p) {
+  if (!state || t < 2 || t > 16 || (r_f & 1u) || r_f > 16 || r_p > 128) return ZK_ERR_ARG;
+  const bool std_spec = t == (uint32_t)PoseidonSpec::T && r_f == (uint32_t)PoseidonSpec::RF && r_p == (uint32_t)PoseidonSpec::RP;
+  PoseidonSpec own;
+  if (!std_spec) own = poseidon_make_spec((int)t, (int)r_f, (int)r_p);
+  const PoseidonSpec& S = std_spec ? poseidon_transcript_spec() : own;
+  std::vector<Fr> st(t);
+  for (uint32_t i = 0; i < t; i++) st[i] = f_from_abi<Fr>(&state[i]);
+  poseidon_permute(S, st.data());
+  for (uint32_t i = 0; i < t; i++) f_to_abi(st[i], &state[i]);
+  return ZK_OK;
+}
+extern "C" int zk_poseidon_hash(const zk_fr* elements, size_t count, zk_fr* out, uint32_t squeezes) {
+  if ((!elements && count) || !out) return ZK_ERR_ARG;
+  PoseidonSponge sp;
+  for (size_t i = 0; i < count; i++) sp.update(f_from_abi<Fr>(&elements[i]));
+  for (uint32_t s = 0; s < (squeezes ? squeezes : 1u); s++) f_to_abi(sp.squeeze(), &out[s]);
+  return ZK_OK;
+}
+
 extern "C" int zk_g2_decode(int format, const uint8_t* in, uint8_t out[128]) {
   if (!in || !out) return ZK_ERR_ARG;
   if (format == ZK_SERDE_RAW_BYTES) {
@@ -480,7 +508,8 @@ extern "C" int zk_verify_proof(const zk_circuit_desc* cd, const zk_verifier_para
   const uint32_t delta_c[8] = {0xe533e9a2u, 0x870e56bbu, 0x5e963f25u, 0x5b5f898eu, 0xd4c86e71u, 0x64ec26aau, 0x22c6f0cau, 0x09226b6eu};
   Fr delta; memcpy(delta.l, delta_c, 32); delta = delta.to_mont();
 
-  if (vp->transcript_kind != ZK_TRANSCRIPT_BLAKE2B && vp->transcript_kind != ZK_TRANSCRIPT_EVM) return ZK_ERR_ARG;
+  if (vp->transcript_kind != ZK_TRANSCRIPT_BLAKE2B && vp->transcript_kind != ZK_TRANSCRIPT_EVM && vp->transcript_kind != ZK_TRANSCRIPT_POSEIDON)
+    return ZK_ERR_ARG;
   TranscriptRead tr(vp->transcript_kind); tr.buf = proof; tr.len = proof_len;
   tr.t.common_scalar(f_from_abi<Fr>(&cd->transcript_repr));
   for (uint32_t i = 0; i < D.n_instance; i++) {

@@ -21,6 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
+from . import keyfile
 from ._abi import ZkError
 
 R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
@@ -684,6 +685,22 @@ class ProvingKey:
         except Exception:
             pass
 
+    @classmethod
+    def read(cls, data, cs, ctx=None, fmt="raw_bytes_unchecked", num_selectors=0):
+        """ProvingKey::read / from_bytes (bin/src/main.rs:205-213 reads ./params/pk.bin with SerdeFormat::RawBytesUnchecked): the
+        extended-domain parts of the file go to HBM, the parsed key (vk commitments, Lagrange / coefficient forms) stays on the
+        instance as `file`.  Byte layout: keyfile.py (restated, unpinned)."""
+        k = int.from_bytes(bytes(data[:4]), "big")
+        ext_k = k
+        while (1 << ext_k) < (1 << k) * (cs.degree() - 1):
+            ext_k += 1
+        pk = keyfile.read_pk(data, len(cs.permutation_columns), num_selectors, fmt, extended_k=ext_k)
+        if len(pk["fixed_cosets"]) != cs.num_fixed_columns:
+            raise keyfile.KeyFileError("the key holds %d fixed columns, the circuit %d" % (len(pk["fixed_cosets"]), cs.num_fixed_columns))
+        self = cls(cs, k, pk["fixed_cosets"], pk["permutation_cosets"], pk["l0"], pk["l_last"], pk["l_active_row"], ctx=ctx)
+        self.file = pk
+        return self
+
     def program_stats(self):
         m, c = C.c_uint64(), C.c_uint64()
         self.ctx.check(self.ctx.lib.zk_pk_program_stats(self.h, C.byref(m), C.byref(c)))
@@ -779,7 +796,8 @@ class ProverKey:
             pass
 
     def set_transcript(self, kind):
-        """"blake2b" = Blake2bWrite / Challenge255 (default), "evm" = snark-verifier's EvmTranscript (Keccak-256)"""
+        """"blake2b" = Blake2bWrite / Challenge255 (default), "evm" = snark-verifier's EvmTranscript (Keccak-256), "poseidon" =
+        snark-verifier's PoseidonTranscript over the native loader (gen_proof, crates/p256-ecdsa/src/base.rs:200-211)"""
         self.ctx.check(self.ctx.lib.zk_pkey_set_transcript(self.h, _abi.TRANSCRIPTS[kind]))
         self.max_proof_bytes = int(self.ctx.lib.zk_proof_max_bytes(self.h))
         if hasattr(self, "_proof_buf"):
