@@ -75,7 +75,7 @@ extern "C" {
     pub fn zk_pkey_destroy(pk: *mut zk_pkey);
     pub fn zk_pkey_vk_commitments(pk: *const zk_pkey, fixed_commitments: *mut zk_g1_affine, perm_commitments: *mut zk_g1_affine) -> c_int;
     pub fn zk_pkey_pk(pk: *mut zk_pkey) -> *mut zk_pk;
-    pub fn zk_pkey_set_transcript(pk: *mut zk_pkey, kind: c_int) -> c_int;      // 0 Blake2b (halo2), 1 EVM / Keccak (snark-verifier)
+    pub fn zk_pkey_set_transcript(pk: *mut zk_pkey, kind: c_int) -> c_int;      // 0 Blake2b (halo2), 1 EVM / Keccak, 2 Poseidon (snark-verifier)
     pub fn zk_proof_randoms(pk: *const zk_pkey) -> usize;
     pub fn zk_proof_max_bytes(pk: *const zk_pkey) -> usize;
     pub fn zk_create_proof(pk: *mut zk_pkey, advice_values: *const *const zk_fr, instance_values: *const *const zk_fr,
@@ -108,6 +108,8 @@ extern "C" {
     pub fn zk_pk_evaluator_kind(pk: *const zk_pk) -> c_int;          // 1 = generated kernel, 0 = interpreter
     pub fn zk_evalh_generate_source(desc: *const zk_evaluator_desc, host_flavour: c_int, buf: *mut c_char, cap: usize, len: *mut usize) -> c_int;
     // ParamsKZG.g2 / s_g2: file encoding <-> the 128 uncompressed bytes zk_verify_proof takes
+    pub fn zk_poseidon_permute(state: *mut zk_fr, t: u32, r_f: u32, r_p: u32) -> c_int;
+    pub fn zk_poseidon_hash(elements: *const zk_fr, count: usize, out: *mut zk_fr, squeezes: u32) -> c_int;
     pub fn zk_g2_decode(format: c_int, input: *const u8, out_uncompressed: *mut u8) -> c_int;
     pub fn zk_g2_encode(format: c_int, in_uncompressed: *const u8, out: *mut u8) -> c_int;
     // verify_proof (host code with its own BN254 pairing)
