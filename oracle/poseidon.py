@@ -139,3 +139,84 @@ def hash_elements(elements):
     s = Sponge()
     s.update(elements)
     return s.squeeze()
+
+
+# ---- the optimised form (what snark-verifier's `Poseidon::permutation` executes): one full constant vector before the partial rounds,
+# a scalar constant per partial round, sparse matrices in the partial rounds.  Derived independently here (see csrc/poseidon.hpp for
+# the derivation); tests check that it is the same function as `permute`.
+def _mat_inv(m):
+    n = len(m)
+    a = [list(row) + [1 if i == j else 0 for j in range(n)] for i, row in enumerate(m)]
+    for c in range(n):
+        piv = next(r for r in range(c, n) if a[r][c] % R)
+        a[c], a[piv] = a[piv], a[c]
+        inv = pow(a[c][c], R - 2, R)
+        a[c] = [v * inv % R for v in a[c]]
+        for r in range(n):
+            if r != c and a[r][c]:
+                f = a[r][c]
+                a[r] = [(x - f * y) % R for x, y in zip(a[r], a[c])]
+    return [row[n:] for row in a]
+
+
+def _mat_mul(a, b):
+    return [[sum(a[i][k] * b[k][j] for k in range(len(b))) % R for j in range(len(b[0]))] for i in range(len(a))]
+
+
+def _mat_vec(m, v):
+    return [sum(x * y for x, y in zip(row, v)) % R for row in m]
+
+
+_OPT = {}
+
+
+def optimized_spec(t=T, r_f=R_F, r_p=R_P):
+    key = (t, r_f, r_p)
+    if key in _OPT:
+        return _OPT[key]
+    rc, mds = spec(t, r_f, r_p)
+    half = r_f // 2
+    minv = _mat_inv(mds)
+    part = [list(c) for c in rc[half:half + r_p]]
+    post = [0] * r_p
+    for p in range(r_p - 1, 0, -1):
+        d = _mat_vec(minv, part[p])
+        for i in range(1, t):
+            part[p - 1][i] = (part[p - 1][i] + d[i]) % R
+        post[p - 1] = d[0]
+        part[p] = [0] * t
+    sparse = [None] * r_p                                       # (m00, row[1..], col[1..])
+    cur = [list(r) for r in mds]
+    for p in range(r_p - 1, -1, -1):
+        sub = [row[1:] for row in cur[1:]]
+        sub_inv = _mat_inv(sub)
+        v = cur[0][1:]
+        vrow = [sum(v[k] * sub_inv[k][j] for k in range(t - 1)) % R for j in range(t - 1)]
+        sparse[p] = (cur[0][0], vrow, [cur[i][0] for i in range(1, t)])
+        dmat = [[1] + [0] * (t - 1)] + [[0] + sub[i] for i in range(t - 1)]
+        last_d = dmat
+        cur = _mat_mul(dmat, mds)
+    pre_sparse = cur
+    first = _mat_vec(last_d, part[0])
+    _OPT[key] = {"full_first": rc[:half], "full_last": rc[half + r_p:], "pre_sparse": pre_sparse, "first": first, "post": post,
+                 "sparse": sparse, "mds": mds}
+    return _OPT[key]
+
+
+def permute_optimized(state, t=T, r_f=R_F, r_p=R_P):
+    o = optimized_spec(t, r_f, r_p)
+    st = list(state)
+    half = r_f // 2
+    for r in range(half):
+        st = [pow((a + c) % R, 5, R) for a, c in zip(st, o["full_first"][r])]
+        st = _mat_vec(o["pre_sparse"] if r == half - 1 else o["mds"], st)
+    st = [(a + c) % R for a, c in zip(st, o["first"])]
+    for p in range(r_p):
+        m00, vrow, col = o["sparse"][p]
+        s0 = (pow(st[0], 5, R) + o["post"][p]) % R
+        new0 = (m00 * s0 + sum(x * y for x, y in zip(vrow, st[1:]))) % R
+        st = [new0] + [(c * s0 + s) % R for c, s in zip(col, st[1:])]
+    for r in range(half):
+        st = [pow((a + c) % R, 5, R) for a, c in zip(st, o["full_last"][r])]
+        st = _mat_vec(o["mds"], st)
+    return st

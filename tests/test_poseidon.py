@@ -80,6 +80,18 @@ def test_native_permutation_equals_python(t, r_f, r_p):
     assert native_permute(edge, t, r_f, r_p) == ps.permute(edge, t, r_f, r_p)
 
 
+@pytest.mark.parametrize("t,r_f,r_p", [(5, 8, 60), (3, 8, 57), (2, 8, 56)])
+def test_optimised_form_is_the_same_function(t, r_f, r_p):
+    """sparse-matrix form of the partial rounds (what snark-verifier executes; derived independently in oracle/poseidon.py and in
+    csrc/poseidon.hpp, where zk_poseidon_permute also checks it against the plain rounds on every call)"""
+    rnd = random.Random(31 * t)
+    for _ in range(3):
+        st = [rnd.randrange(R) for _ in range(t)]
+        assert ps.permute_optimized(st, t, r_f, r_p) == ps.permute(st, t, r_f, r_p)
+    o = ps.optimized_spec(t, r_f, r_p)
+    assert len(o["sparse"]) == r_p and len(o["post"]) == r_p and o["post"][-1] == 0
+
+
 def test_native_permute_rejects_bad_arguments():
     buf = np.zeros((5, 4), dtype=np.uint64)
     assert lib().zk_poseidon_permute(None, 5, 8, 60) != 0

@@ -5,8 +5,8 @@
 //   * parameters: Grain LFSR of the Poseidon paper -- 80-bit state (field = 1, sbox = 0, 254 field bits, t, R_F, R_P, thirty ones),
 //     160 bits discarded, bits emitted in pairs (first bit 1 => output the second); round constants are 254-bit MSB-first integers with
 //     rejection sampling, the MDS matrix is the Cauchy matrix 1 / (x_i + y_j) of 2t further elements taken mod r without rejection;
-//   * permutation: plain form (constants, x^5 on all / the first element, MDS), R_F/2 + R_P + R_F/2 rounds -- the same function as the
-//     optimised form snark-verifier executes;
+//   * permutation: constants, x^5 on all / the first element, MDS; R_F/2 + R_P + R_F/2 rounds.  Executed in the optimised form (sparse
+//     matrices in the partial rounds, derived below); the plain form is kept and zk_poseidon_permute checks one against the other;
 //   * sponge (`Poseidon::squeeze`): state (2^64, 0, 0, 0, 0); buffered elements are absorbed RATE at a time into state[1..], a short chunk
 //     is followed by +1 in the next position, a buffer that is a multiple of RATE gets one more permutation of an empty chunk; output
 //     state[1]; the state carries over to the next squeeze.
@@ -53,6 +53,15 @@ struct PFr {
     cond_sub(r.l, 0);                           // a + b < 2r < 2^255: no carry out of limb 3
     return r;
   }
+  friend PFr operator-(const PFr& a, const PFr& b) {          // a + (r - b); b is reduced
+    PFr nb; unsigned __int128 bw = 0;
+    for (int i = 0; i < 4; i++) { unsigned __int128 x = (unsigned __int128)kM[i] - b.l[i] - (uint64_t)bw; nb.l[i] = (uint64_t)x; bw = (x >> 64) & 1; }
+    return a + nb;                                              // r - 0 = r is folded by the conditional subtraction of operator+
+  }
+  bool is_zero() const { return (l[0] | l[1] | l[2] | l[3]) == 0; }
+  static PFr zero() { PFr r; r.l[0] = r.l[1] = r.l[2] = r.l[3] = 0; return r; }
+  static PFr one() { return from(Fr::one()); }
+  PFr inverse() const { return from(Fr::inv(to_fr())); }
   friend PFr operator*(const PFr& a, const PFr& b) {
     uint64_t t[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
@@ -75,6 +84,9 @@ struct PoseidonSpec {
   std::vector<Fr> rc;        // (RF + RP) * t round constants, Montgomery form
   std::vector<Fr> mds;       // t * t
   std::vector<PFr> rc64, mds64;
+  // optimised form (derivation below): the matrix of the last full round before the partial rounds, the one full constant vector
+  // added before them, per partial round a scalar added to state[0] after the s-box and a sparse matrix (m00, first row, first column)
+  std::vector<PFr> pre_sparse, first, post, sp_m00, sp_row, sp_col;
   int t = T, rf = RF, rp = RP;
 };
 
@@ -127,6 +139,81 @@ struct Grain {
 };
 }  // namespace poseidon_detail
 
+// The optimised form of the permutation (the same function; what snark-verifier executes, derived here independently).
+// Partial round p is  s += c_p;  s[0] = s[0]^5;  s = M s.
+//  (1) constants: c_p = M (M^-1 c_p), and M^-1 c_p =: d can be added BEFORE the multiplication by M of round p-1; its components
+//      1.. commute with the s-box of round p-1 (which touches s[0] only) and join c_(p-1), its component 0 stays behind the s-box as a
+//      scalar.  Backwards over the partial rounds: one full vector before the first partial round, one scalar per round.
+//  (2) matrices: M = S D with D = diag(1, M^) (M^ = M without row and column 0) and S = [[m00, v^T M^^-1], [w, I]] sparse.  D commutes
+//      with everything a partial round does to s[0], so it moves to the previous round's matrix: (D M) is factored again, and so on;
+//      what is left after the first partial round's matrix joins the matrix of the preceding full round (`pre_sparse` = D_0 M, and
+//      the full vector becomes D_0 c).  A partial round then costs 2t - 1 multiplications instead of t^2.
+namespace poseidon_detail {
+inline std::vector<PFr> mat_inverse(std::vector<PFr> a, int n) {          // Gauss-Jordan; a is n x n row-major and invertible
+  std::vector<PFr> inv((size_t)n * n, PFr::zero());
+  for (int i = 0; i < n; i++) inv[(size_t)i * n + i] = PFr::one();
+  for (int c = 0; c < n; c++) {
+    int piv = c;
+    while (piv < n && a[(size_t)piv * n + c].is_zero()) piv++;
+    if (piv == n) return {};
+    for (int j = 0; j < n; j++) { std::swap(a[(size_t)c * n + j], a[(size_t)piv * n + j]); std::swap(inv[(size_t)c * n + j], inv[(size_t)piv * n + j]); }
+    const PFr f = a[(size_t)c * n + c].inverse();
+    for (int j = 0; j < n; j++) { a[(size_t)c * n + j] = a[(size_t)c * n + j] * f; inv[(size_t)c * n + j] = inv[(size_t)c * n + j] * f; }
+    for (int r = 0; r < n; r++) {
+      if (r == c || a[(size_t)r * n + c].is_zero()) continue;
+      const PFr g = a[(size_t)r * n + c];
+      for (int j = 0; j < n; j++) {
+        a[(size_t)r * n + j] = a[(size_t)r * n + j] - g * a[(size_t)c * n + j];
+        inv[(size_t)r * n + j] = inv[(size_t)r * n + j] - g * inv[(size_t)c * n + j];
+      }
+    }
+  }
+  return inv;
+}
+inline void optimise(PoseidonSpec& S) {
+  const int t = S.t, half = S.rf / 2, rp = S.rp, m = t - 1;
+  const std::vector<PFr>& M = S.mds64;
+  const std::vector<PFr> Minv = mat_inverse(M, t);
+  std::vector<PFr> part(S.rc64.begin() + (size_t)half * t, S.rc64.begin() + (size_t)(half + rp) * t);
+  S.post.assign(rp, PFr::zero());
+  for (int p = rp - 1; p >= 1; p--) {
+    std::vector<PFr> d(t, PFr::zero());
+    for (int i = 0; i < t; i++)
+      for (int j = 0; j < t; j++) d[i] = d[i] + Minv[(size_t)i * t + j] * part[(size_t)p * t + j];
+    for (int i = 1; i < t; i++) part[(size_t)(p - 1) * t + i] = part[(size_t)(p - 1) * t + i] + d[i];
+    S.post[p - 1] = d[0];
+  }
+  S.sp_m00.assign(rp, PFr::zero()); S.sp_row.assign((size_t)rp * m, PFr::zero()); S.sp_col.assign((size_t)rp * m, PFr::zero());
+  std::vector<PFr> cur = M, D((size_t)t * t, PFr::zero());
+  for (int p = rp - 1; p >= 0; p--) {
+    std::vector<PFr> sub((size_t)m * m);
+    for (int i = 0; i < m; i++)
+      for (int j = 0; j < m; j++) sub[(size_t)i * m + j] = cur[(size_t)(i + 1) * t + j + 1];
+    const std::vector<PFr> sinv = mat_inverse(sub, m);
+    S.sp_m00[p] = cur[0];
+    for (int j = 0; j < m; j++) {
+      PFr acc = PFr::zero();
+      for (int k = 0; k < m; k++) acc = acc + cur[k + 1] * sinv[(size_t)k * m + j];
+      S.sp_row[(size_t)p * m + j] = acc;
+      S.sp_col[(size_t)p * m + j] = cur[(size_t)(j + 1) * t];
+    }
+    std::fill(D.begin(), D.end(), PFr::zero());
+    D[0] = PFr::one();
+    for (int i = 0; i < m; i++)
+      for (int j = 0; j < m; j++) D[(size_t)(i + 1) * t + j + 1] = sub[(size_t)i * m + j];
+    std::vector<PFr> next((size_t)t * t, PFr::zero());
+    for (int i = 0; i < t; i++)
+      for (int j = 0; j < t; j++)
+        for (int k = 0; k < t; k++) next[(size_t)i * t + j] = next[(size_t)i * t + j] + D[(size_t)i * t + k] * M[(size_t)k * t + j];
+    cur.swap(next);
+  }
+  S.pre_sparse = cur;                                   // D_0 M
+  S.first.assign(t, PFr::zero());                       // D_0 c
+  for (int i = 0; i < t; i++)
+    for (int j = 0; j < t; j++) S.first[i] = S.first[i] + D[(size_t)i * t + j] * part[j];
+}
+}  // namespace poseidon_detail
+
 inline PoseidonSpec poseidon_make_spec(int t, int rf, int rp) {
   PoseidonSpec S;
   S.t = t; S.rf = rf; S.rp = rp;
@@ -141,6 +228,7 @@ inline PoseidonSpec poseidon_make_spec(int t, int rf, int rp) {
     for (int j = 0; j < t; j++) S.mds[(size_t)i * t + j] = Fr::inv(xs[i] + ys[j]).reduce();
   for (auto& c : S.rc) S.rc64.push_back(PFr::from(c));
   for (auto& c : S.mds) S.mds64.push_back(PFr::from(c));
+  poseidon_detail::optimise(S);
   return S;
 }
 
@@ -149,7 +237,7 @@ inline const PoseidonSpec& poseidon_transcript_spec() {
   return S;
 }
 
-inline void poseidon_permute(const PoseidonSpec& S, Fr* state) {
+inline void poseidon_permute_plain(const PoseidonSpec& S, Fr* state) {
   const int t = S.t, half = S.rf / 2;
   PFr st[16], nx[16];
   for (int i = 0; i < t; i++) st[i] = PFr::from(state[i]);
@@ -169,6 +257,39 @@ inline void poseidon_permute(const PoseidonSpec& S, Fr* state) {
     }
     for (int i = 0; i < t; i++) st[i] = nx[i];
   }
+  for (int i = 0; i < t; i++) state[i] = st[i].to_fr();
+}
+
+inline void poseidon_permute(const PoseidonSpec& S, Fr* state) {
+  const int t = S.t, half = S.rf / 2, m = t - 1;
+  PFr st[16], nx[16];
+  for (int i = 0; i < t; i++) st[i] = PFr::from(state[i]);
+  auto full_round = [&](const PFr* rc, const PFr* mat) {
+    for (int i = 0; i < t; i++) {
+      PFr x = st[i] + rc[i], x2 = x * x;
+      st[i] = x2 * x2 * x;
+    }
+    for (int i = 0; i < t; i++) {
+      const PFr* row = mat + (size_t)i * t;
+      PFr acc = row[0] * st[0];
+      for (int j = 1; j < t; j++) acc = acc + row[j] * st[j];
+      nx[i] = acc;
+    }
+    for (int i = 0; i < t; i++) st[i] = nx[i];
+  };
+  for (int r = 0; r < half; r++) full_round(&S.rc64[(size_t)r * t], r == half - 1 ? S.pre_sparse.data() : S.mds64.data());
+  for (int i = 0; i < t; i++) st[i] = st[i] + S.first[i];
+  for (int p = 0; p < S.rp; p++) {
+    PFr x2 = st[0] * st[0];
+    const PFr s0 = x2 * x2 * st[0] + S.post[p];
+    const PFr* row = &S.sp_row[(size_t)p * m];
+    const PFr* col = &S.sp_col[(size_t)p * m];
+    PFr acc = S.sp_m00[p] * s0;
+    for (int j = 0; j < m; j++) acc = acc + row[j] * st[j + 1];
+    for (int j = 0; j < m; j++) st[j + 1] = st[j + 1] + col[j] * s0;
+    st[0] = acc;
+  }
+  for (int r = 0; r < half; r++) full_round(&S.rc64[(size_t)(half + S.rp + r) * t], S.mds64.data());
   for (int i = 0; i < t; i++) state[i] = st[i].to_fr();
 }
 

@@ -423,9 +423,11 @@ extern "C" int zk_poseidon_permute(zk_fr* state, uint32_t t, uint32_t r_f, uint3
   PoseidonSpec own;
   if (!std_spec) own = poseidon_make_spec((int)t, (int)r_f, (int)r_p);
   const PoseidonSpec& S = std_spec ? poseidon_transcript_spec() : own;
-  std::vector<Fr> st(t);
-  for (uint32_t i = 0; i < t; i++) st[i] = f_from_abi<Fr>(&state[i]);
+  std::vector<Fr> st(t), plain(t);
+  for (uint32_t i = 0; i < t; i++) plain[i] = st[i] = f_from_abi<Fr>(&state[i]);
   poseidon_permute(S, st.data());
+  poseidon_permute_plain(S, plain.data());                    // self-check: the optimised form is the same function
+  for (uint32_t i = 0; i < t; i++) if (st[i] != plain[i]) return ZK_ERR_STATE;
   for (uint32_t i = 0; i < t; i++) f_to_abi(st[i], &state[i]);
   return ZK_OK;
 }
