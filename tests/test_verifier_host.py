@@ -172,3 +172,12 @@ def test_verify_proof_rejects_file_encoded_g2():
     with pytest.raises(zk.ZkError, match="128 uncompressed bytes"):
         zk.verify_proof(case["circ"], fc, pcm, g1, c2, cs2, case["instances_limbs"], proof)
     assert zk.verify_proof(case["circ"], fc, pcm, g1, zk.g2_decode(c2), zk.g2_decode(cs2), case["instances_limbs"], proof)
+
+
+def test_encode_calldata():
+    """instances as 32-byte big-endian words followed by the proof (snark-verifier's encode_calldata)"""
+    inst = [pm.to_mont_limbs([1, 2, pm.R_MOD - 1], pm.R_MOD), pm.to_mont_limbs([7], pm.R_MOD)]
+    data = zk.encode_calldata(inst, b"\xaa\xbb")
+    words = [int.from_bytes(data[32 * i:32 * i + 32], "big") for i in range(4)]
+    assert words == [1, 2, pm.R_MOD - 1, 7] and data[128:] == b"\xaa\xbb" and len(data) == 130
+    assert zk.encode_calldata([], b"") == b""

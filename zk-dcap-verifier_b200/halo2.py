@@ -223,6 +223,19 @@ def g2_encode(uncompressed, fmt="processed"):
     return out.tobytes()
 
 
+def encode_calldata(instances, proof):
+    """snark-verifier `encode_calldata(&[instances], &proof)` (bin/src/main.rs:236; the input of the generated Solidity verifier):
+    every instance value as 32 big-endian bytes of its canonical form, column after column, then the proof bytes (an
+    EvmTranscript proof, `set_transcript("evm")`).  instances: one (len, 4) Montgomery-limb array per instance column."""
+    rinv = pow(1 << 256, -1, keyfile.R_MOD)
+    out = bytearray()
+    for col in instances:
+        for row in _u64(col, (-1, 4)):
+            v = sum(int(row[i]) << (64 * i) for i in range(4)) * rinv % keyfile.R_MOD
+            out += v.to_bytes(32, "big")
+    return bytes(out) + bytes(proof)
+
+
 # ---- poly/kzg/commitment.rs -----------------------------------------------------------------------
 class ParamsKZG:
     """ParamsKZG { k, n, g, g_lagrange } with both base sets resident in HBM."""
