@@ -421,7 +421,9 @@ class Workload:
 
 
 # ---- complete proofs -------------------------------------------------------------------------------------
-TRAPDOOR = 0x1c59a59b6cff4308740943526ade1d8c09f71b337a67269cc89586bcdd6dfcba     # SRS secret of the synthetic setup
+# SRS secret: Fr::random of ChaCha20Rng::from_seed([0; 32]) -- what halo2-base's gen_srs(k) would draw ([UPSTREAM?];
+# derivation checked in tests/test_prover_oracle.py)
+TRAPDOOR = 0x1c59a59b6cff4308740943526ade1d8c09f71b337a67269cc89586bcdd6dfcba
 
 
 class DevOps:

@@ -154,3 +154,35 @@ def test_fast_setup_matches_the_plain_loop():
         slow = op.setup_params(orc, k, pc.TRAPDOOR)
         g, gl = orc.setup_params(k, pc.TRAPDOOR)
         assert np.array_equal(g, slow["g"]) and np.array_equal(gl, slow["g_lagrange"])
+
+
+def test_srs_secret_is_the_zero_seed_chacha20_draw():
+    """halo2-base `gen_srs(k)` = `ParamsKZG::setup(k, ChaCha20Rng::from_seed([0; 32]))` (SURVEY.md A.6, [UPSTREAM?]): the secret is
+    `Fr::random` = the first 64 keystream bytes (RFC 7539 block function, zero key / counter / nonce) as a little-endian integer
+    mod r.  The tests' and the bench's TRAPDOOR is that value, so their SRS is the one the reference would generate."""
+    import struct
+
+    def rotl(v, c):
+        return ((v << c) & 0xFFFFFFFF) | (v >> (32 - c))
+
+    def quarter(s, a, b, c, d):
+        s[a] = (s[a] + s[b]) & 0xFFFFFFFF; s[d] = rotl(s[d] ^ s[a], 16)
+        s[c] = (s[c] + s[d]) & 0xFFFFFFFF; s[b] = rotl(s[b] ^ s[c], 12)
+        s[a] = (s[a] + s[b]) & 0xFFFFFFFF; s[d] = rotl(s[d] ^ s[a], 8)
+        s[c] = (s[c] + s[d]) & 0xFFFFFFFF; s[b] = rotl(s[b] ^ s[c], 7)
+
+    init = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + [0] * 12
+    w = list(init)
+    for _ in range(10):
+        for q in ((0, 4, 8, 12), (1, 5, 9, 13), (2, 6, 10, 14), (3, 7, 11, 15), (0, 5, 10, 15), (1, 6, 11, 12), (2, 7, 8, 13), (3, 4, 9, 14)):
+            quarter(w, *q)
+    stream = struct.pack("<16I", *[(a + b) & 0xFFFFFFFF for a, b in zip(w, init)])
+    assert stream[:16].hex() == "76b8e0ada0f13d90405d6ae55386bd28"          # the published zero-key test vector
+    s = int.from_bytes(stream, "little") % pm.R_MOD
+    assert s == pc.TRAPDOOR
+    import bench
+    assert bench.TRAPDOOR == s
+    g = pm.limbs_to_affine(pc.params_for(4)["g"][:2])
+    assert g[0] == (1, 2) and g[1] == pm.ec_mul(s, (1, 2))
+    assert g[1] == (0x0ec379d622d571768ccf88ad66c436878c1f3023a56b611f076f39283681af49,
+                    0x1ec57fbfc73af5f417110eaea857cb7854476803c5ba11248d090398017fb020)
